@@ -1,0 +1,213 @@
+// common.cuh -- context, device buffers and launch helpers shared by the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bseg.h"
+
+#define BSEG_NUM_SMS_FALLBACK 148
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+enum StageEv {
+  EV_START = 0,
+  EV_H2D,
+  EV_BBOX_KEYS,
+  EV_SORT,
+  EV_CELLS,
+  EV_KNN,
+  EV_KNN_FB,
+  EV_NORMALS,
+  EV_GROW,
+  EV_FINALIZE,
+  EV_RASTER,
+  EV_D2H,
+  EV_COUNT
+};
+
+struct bseg_ctx {
+  int device = 0;
+  int num_sms = BSEG_NUM_SMS_FALLBACK;
+  cudaStream_t stream = nullptr;
+  char err[512] = {0};
+
+  // ---- cloud ----
+  int64_t n = 0;        // points in the cloud (own + halo)
+  int64_t n_owned = 0;  // points this rank owns (== n on one GPU)
+  int32_t mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+  bool have_points = false, have_knn = false, have_grow = false;
+
+  // ---- binning state (valid after knn stage) ----
+  int32_t cell = 0;       // level-0 cell edge
+  int key_bits = 0;       // significant bits of the Morton key
+  int64_t n_cells = 0;    // occupied level-0 cells
+  int64_t n_tiles = 0;    // occupied level-1 (2x2x2) tiles
+  uint64_t hash_mask = 0;
+  int K = 0;
+
+  // ---- grow results ----
+  int32_t n_planes = 0;
+  int64_t n_plane_entries = 0;
+
+  // ---- device buffers ----
+  DevBuf xyz_raw;    // int32 [n][3], shifted to min=0, original order
+  DevBuf minmax;     // int32 [6] + scratch
+  DevBuf keys[2];    // u64 [n]
+  DevBuf vals[2];    // u32 [n]
+  DevBuf sort_cnt;   // u32 radix counters
+  DevBuf scan_tmp;   // u32 block sums for the scan
+  DevBuf pts;        // int4 [n] sorted: x,y,z,orig
+  DevBuf inv;        // u32 [n]  orig -> sorted position
+  DevBuf flags;      // u32 [n] scratch flags / scans
+  DevBuf flags2;     // u32 [n]
+  DevBuf cell_key;   // u64 [n_cells]
+  DevBuf cell_start; // u32 [n_cells+1]
+  DevBuf tile_start; // u32 [n_tiles+1]
+  DevBuf hash_keys;  // u64 [hash]
+  DevBuf hash_vals;  // u32 [hash]
+  DevBuf nbr;        // int32 [n][K] sorted-position space
+  DevBuf moments;    // int64 [n][10]
+  DevBuf nrm;        // double [n][3] sorted-position space
+  DevBuf curv;       // double [n]
+  DevBuf unresolved; // u32 [n] + counter
+  DevBuf counters;   // misc u64 counters
+  DevBuf out_tmp;    // staging for original-order exports
+  // grower
+  DevBuf g_state;    // int32 [n] planeIdx in sorted-position space
+  DevBuf g_label;    // int32 [n]
+  DevBuf g_list;     // int32 [2n+...] pointIdx lists (CSR of committed planes)
+  DevBuf g_stack;    // int2 frames
+  DevBuf g_planes;   // per-plane records
+  DevBuf g_aux;      // engine scratch
+  // raster
+  DevBuf r_hist;
+  DevBuf r_image;    // double [W*H*3]
+  DevBuf r_png;      // u8 [3][W*H*3]
+  DevBuf r_seg;      // u32 [2][W*H]
+
+  // ---- timing ----
+  cudaEvent_t ev[EV_COUNT] = {nullptr};
+  bool ev_set[EV_COUNT] = {false};
+  bseg_timings tm;
+  int64_t launches = 0;
+};
+
+int bseg_fail(bseg_ctx* c, int code, const char* fmt, ...);
+
+#define CU_CHECK(c, call)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return bseg_fail((c), BSEG_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,         \
+                       cudaGetErrorString(e__));                                              \
+  } while (0)
+
+#define RC_CHECK(call)       \
+  do {                       \
+    int rc__ = (call);       \
+    if (rc__ != 0)           \
+      return rc__;           \
+  } while (0)
+
+#define KLAUNCH_CHECK(c)                                  \
+  do {                                                    \
+    (c)->launches++;                                      \
+    CU_CHECK((c), cudaGetLastError());                    \
+  } while (0)
+
+int dev_ensure(bseg_ctx* c, DevBuf& b, size_t bytes);
+void dev_free(DevBuf& b);
+
+template <typename T>
+static inline T* dptr(DevBuf& b)
+{
+  return reinterpret_cast<T*>(b.p);
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- primitives implemented in scan.cu / sort.cu ------------------------------------------------
+// in-place exclusive prefix sum of u32; total (sum of all) written to *d_total when non-null
+int bseg_exclusive_scan_u32(bseg_ctx* c, uint32_t* d_data, int64_t n, uint32_t* d_total);
+// stable LSD radix sort of (key,val) pairs on key bits [0,key_bits); result left in keys[*out]/vals[*out]
+int bseg_sort_pairs_u64(bseg_ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, int64_t n,
+                        int key_bits, int* out_sel);
+int bseg_sort_pairs_u32(bseg_ctx* c, uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int64_t n,
+                        int key_bits, int* out_sel);
+
+// ---- stages ---------------------------------------------------------------------------------------
+int stage_bbox_shift(bseg_ctx* c);                           // bin.cu
+int stage_bin(bseg_ctx* c, const bseg_params* p);            // bin.cu
+int stage_knn(bseg_ctx* c, const bseg_params* p);            // knn.cu
+int stage_export_knn(bseg_ctx* c, const bseg_params* p, int32_t* h_neigh, double* h_normals, double* h_curv);
+int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* h_neigh, const double* h_normals);
+int stage_grow(bseg_ctx* c, const bseg_params* p);           // grow.cu
+int stage_export_grow(bseg_ctx* c, int32_t* h_plane_idx, int32_t* h_label);
+int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* centers, int64_t* offsets,
+                     int32_t* point_idx);
+int stage_paint(bseg_ctx* c, const uint16_t* h_rgb, uint16_t* h_colors);
+int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* a, uint8_t* b, uint8_t* cc,
+                 double* th, bool device_only);
+
+static inline void ev_record(bseg_ctx* c, int which)
+{
+  cudaEventRecord(c->ev[which], c->stream);
+  c->ev_set[which] = true;
+}
+
+// ---- device helpers ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t morton_spread21(uint32_t v)
+{
+  uint64_t x = v & 0x1fffffULL;
+  x = (x | x << 32) & 0x1f00000000ffffULL;
+  x = (x | x << 16) & 0x1f0000ff0000ffULL;
+  x = (x | x << 8) & 0x100f00f00f00f00fULL;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+  x = (x | x << 2) & 0x1249249249249249ULL;
+  return x;
+}
+__device__ __forceinline__ uint32_t morton_compact21(uint64_t x)
+{
+  x &= 0x1249249249249249ULL;
+  x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ULL;
+  x = (x ^ (x >> 4)) & 0x100f00f00f00f00fULL;
+  x = (x ^ (x >> 8)) & 0x1f0000ff0000ffULL;
+  x = (x ^ (x >> 16)) & 0x1f00000000ffffULL;
+  x = (x ^ (x >> 32)) & 0x1fffffULL;
+  return (uint32_t)x;
+}
+__device__ __forceinline__ uint64_t morton3(uint32_t x, uint32_t y, uint32_t z)
+{
+  return morton_spread21(x) | (morton_spread21(y) << 1) | (morton_spread21(z) << 2);
+}
+__device__ __forceinline__ uint64_t hash64(uint64_t k)
+{
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+#define HASH_EMPTY 0xffffffffffffffffULL
+__device__ __forceinline__ uint32_t hash_lookup(const uint64_t* __restrict__ hk, const uint32_t* __restrict__ hv,
+                                                uint64_t mask, uint64_t key)
+{
+  uint64_t h = hash64(key) & mask;
+  for (;;) {
+    uint64_t k = hk[h];
+    if (k == key)
+      return hv[h];
+    if (k == HASH_EMPTY)
+      return 0xffffffffu;
+    h = (h + 1) & mask;
+  }
+}
+#endif

@@ -1,0 +1,163 @@
+/*
+ * bseg.h -- C ABI of libbseg.so, the B200 (sm_100a) implementation of buildingSegment's
+ * per-point segmentation hot path.
+ *
+ * The reference has no FFI: its boundary is plain C++ inside one process
+ * (/root/reference/tmc3/TMC3.cpp:202-229 calls my_function.h / my_function.cpp directly).
+ * This header is the boundary a maintainer binds instead; every entry point names the
+ * reference interface it replaces.  The C++ shims in buildingsegment_b200/host/ present the
+ * reference's own signatures on top of it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer, the library owns all
+ *     device memory; nothing throws across the boundary;
+ *   - every function returns 0 on success or a negative bseg_status; bseg_last_error() holds text;
+ *   - a context is bound to one CUDA device and one stream, and is not thread-safe;
+ *   - there is no CPU fallback: without a CUDA device bseg_create fails with BSEG_E_NODEVICE.
+ *   - coordinates are int32 (millimetres after ply::read's x1000); after the shift to the cloud
+ *     minimum every extent must be < 2^21 kNN cells and < 2^25 units.
+ */
+#ifndef BSEG_H
+#define BSEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(BSEG_BUILD)
+#define BSEG_API __attribute__((visibility("default")))
+#else
+#define BSEG_API
+#endif
+
+typedef struct bseg_ctx bseg_ctx;
+
+typedef enum bseg_status {
+  BSEG_OK = 0,
+  BSEG_E_ARG = -1,      /* bad argument / parameter out of the supported range */
+  BSEG_E_NODEVICE = -2, /* no usable CUDA device -- there is no CPU path */
+  BSEG_E_CUDA = -3,     /* a CUDA call failed; see bseg_last_error */
+  BSEG_E_STATE = -4,    /* stage called out of order (e.g. grow before knn_normals) */
+  BSEG_E_CAPACITY = -5, /* an internal table overflowed */
+  BSEG_E_NOMEM = -6
+} bseg_status;
+
+/* Every literal of the reference, as a parameter.  bseg_default_params fills the values below. */
+typedef struct bseg_params {
+  int32_t K;              /* 15    neighbours per row, self included   TMC3.cpp:215-216        */
+  int32_t max_nn;         /* 50    hybrid search cap                   my_function.h:63        */
+  double radius;          /* 100.0 hybrid search radius (strict <)     my_function.h:63        */
+  int32_t th_thickness;   /* 300   |(p-c).n| <= th                     my_function.h:117       */
+  int32_t th_point_count; /* 400   plane kept if pointIdx.size() > th  my_function.h:118       */
+  double th_dot;          /* 0.88  n.n_i >= th                         my_function.cpp:230     */
+  int32_t bin;            /* 100   raster pixel edge                   TMC3.cpp:177            */
+  int32_t bin_height;     /* 1000  z-histogram bin of groundTH         TMC3.cpp:177            */
+  double count_bias;      /* 20.0  added to log(count+1) when non-zero TMC3.cpp:163            */
+  int32_t cell;           /* 0 = auto: kNN grid cell edge, >= ceil(radius)                      */
+  int32_t grow_mode;      /* 0 = speculative parallel engine, 1 = single-warp sequential engine */
+  int32_t reserved[5];
+} bseg_params;
+
+/* Per-stage device time of the last call, milliseconds (CUDA events on the context's stream). */
+typedef struct bseg_timings {
+  float h2d, bbox_keys, sort, cells, knn, knn_fallback, normals, grow, finalize, raster, d2h, total;
+  int64_t n_unresolved;   /* queries that needed the ring-expansion fallback */
+  int64_t grow_steps;     /* Broad() calls executed (committed work)          */
+  int64_t grow_rounds;    /* rounds of the speculative engine                 */
+  int64_t kernel_launches;/* kernels launched since bseg_reset_counters       */
+} bseg_timings;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+BSEG_API int bseg_create(bseg_ctx** out, int device);
+BSEG_API void bseg_destroy(bseg_ctx* ctx);
+BSEG_API int bseg_default_params(bseg_params* p);
+BSEG_API const char* bseg_last_error(const bseg_ctx* ctx);
+BSEG_API const char* bseg_version(void);
+
+/* ---- stage a3: buildingSeg::buildingSeg (TMC3.cpp:55-79) ------------------------------------
+ * Uploads the N x 3 int32 AoS cloud (what &cloud[0][0] points at, PCCPointSet.h:271-275), finds
+ * the bounding box on the device and shifts the device copy to min = 0.  out_min/out_max receive
+ * the UNSHIFTED box; the caller's cloud is shifted too when xyz_shifted_out != NULL (the reference
+ * ctor shifts the caller's cloud, TMC3.cpp:71).  xyz_aos may be pinned or pageable. */
+BSEG_API int bseg_set_points(bseg_ctx* ctx, const int32_t* xyz_aos, int64_t n, int32_t out_min[3],
+                             int32_t out_max[3], int32_t* xyz_shifted_out);
+
+/* Same, for a cloud already resident in device memory (bench "value" leg, multi-GPU slabs). */
+BSEG_API int bseg_set_points_device(bseg_ctx* ctx, const int32_t* d_xyz_aos, int64_t n, int32_t out_min[3],
+                                    int32_t out_max[3]);
+
+/* ---- stages a4 + a5: get_Normal_and_K_neighbor<K> (my_function.h:48-85) ----------------------
+ * Morton binning (radix sort), exact kNN ordered by (d^2, index), hybrid-radius PCA normals
+ * oriented to +z.  Outputs are optional (NULL = keep on device only):
+ *   neigh_NxK    row i = the K nearest of point i in ORIGINAL indices, -1 padded when N < K
+ *   normals_Nx3  unit normals
+ *   curvature_N  lambda0/(l0+l1+l2) -- extension, the reference computes none */
+BSEG_API int bseg_knn_normals(bseg_ctx* ctx, const bseg_params* p, int32_t* neigh_NxK, double* normals_Nx3,
+                              double* curvature_N);
+
+/* Replace the device-resident normals / neighbour rows with caller-supplied ones (original
+ * indexing).  Lets tests drive the grower with adversarial inputs, as the reference's
+ * seg_plane constructor accepts arbitrary vectors (my_function.h:98). */
+BSEG_API int bseg_override_neigh_normals(bseg_ctx* ctx, const bseg_params* p, const int32_t* neigh_NxK,
+                                         const double* normals_Nx3);
+
+/* ---- stages a7-a9: seg_plane::seg_plane + get_planes + Broad (my_function.cpp:180-258) --------
+ *   plane_idx_N  the reference's Cloud.planeIdx after get_planes: -1 free, else a plane id
+ *                (orphan marks of failed seeds included)
+ *   label_N      0, or the id of the last plane whose pointIdx holds the point
+ *   n_planes     number of committed planes */
+BSEG_API int bseg_grow_planes(bseg_ctx* ctx, const bseg_params* p, int32_t* plane_idx_N, int32_t* label_N,
+                              int32_t* n_planes);
+
+/* std::vector<plane> of get_planes (my_function.h:25-30): ids are 1..P in order;
+ * offsets_Pp1/point_idx are pointIdx in the reference's order, duplicates kept.
+ * Call with point_idx == NULL to size the buffers (total entries = offsets[P]). */
+BSEG_API int bseg_get_planes(bseg_ctx* ctx, int32_t* seeds_P, double* normals_Px3, int32_t* centers_Px3,
+                             int64_t* offsets_Pp1, int32_t* point_idx);
+
+/* ---- stage a10: seg_plane::set_plane_color (my_function.cpp:260-275) --------------------------
+ * plane_rgb_Px3 is the host's rand() sequence (55 + rand() % 200, three per plane). */
+BSEG_API int bseg_paint(bseg_ctx* ctx, const uint16_t* plane_rgb_Px3, uint16_t* colors_Nx3);
+
+/* ---- stages a13-a15: groundTH + compute_gird_picture + save_image pixels (TMC3.cpp:81-198) -----
+ * image_WxHx3: doubles, pixel(x,y,ch) = image[(y*W+x)*3+ch]; png_rgb[0..2]: the three W*H*3
+ * uint8 images handed to stbi_write_png (A: mean height in byte 0, B: log count in byte 1,
+ * C: always zero).  Any output may be NULL.  W,H are also available from bseg_raster_size. */
+BSEG_API int bseg_raster_size(bseg_ctx* ctx, const bseg_params* p, int32_t* W, int32_t* H);
+BSEG_API int bseg_raster(bseg_ctx* ctx, const bseg_params* p, double* image_WxHx3, uint8_t* png_a,
+                         uint8_t* png_b, uint8_t* png_c, double* ground_th);
+
+/* ---- whole path, device resident (no host transfers): what bench.py times as `value` --------- */
+#define BSEG_RUN_KNN 1
+#define BSEG_RUN_GROW 2
+#define BSEG_RUN_RASTER 4
+#define BSEG_RUN_ALL 7
+BSEG_API int bseg_run_device(bseg_ctx* ctx, const bseg_params* p, int stages);
+
+/* ---- whole path through host buffers: what bench.py times as `e2e` --------------------------- */
+BSEG_API int bseg_segment_host(bseg_ctx* ctx, const bseg_params* p, const int32_t* xyz_aos, int64_t n,
+                               int32_t* xyz_shifted_out, int32_t* label_N, int32_t* n_planes,
+                               uint8_t* png_a, uint8_t* png_b, int32_t* W, int32_t* H);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+BSEG_API int bseg_get_timings(bseg_ctx* ctx, bseg_timings* out);
+BSEG_API int bseg_reset_counters(bseg_ctx* ctx);
+BSEG_API void* bseg_stream(bseg_ctx* ctx); /* cudaStream_t the context launches on */
+BSEG_API int64_t bseg_point_count(const bseg_ctx* ctx);
+
+/* ---- multi-GPU slabs (one context per rank; the exchange itself is the caller's NCCL) --------- */
+/* Declares that the first n_owned points of the cloud passed to bseg_set_points are this rank's
+ * own slab and the rest are halo copies: halo points serve as neighbours only. */
+BSEG_API int bseg_set_owned(bseg_ctx* ctx, int64_t n_owned);
+
+/* ---- self-test hooks used by tests/ (exercise the hand-written primitives in isolation) ------- */
+BSEG_API int bseg_debug_sort_pairs(bseg_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);
+BSEG_API int bseg_debug_exclusive_scan(bseg_ctx* ctx, uint32_t* data, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSEG_H */
