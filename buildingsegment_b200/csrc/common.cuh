@@ -9,6 +9,9 @@
 #include "../../include/bseg.h"
 
 #define BSEG_NUM_SMS_FALLBACK 148
+#define BSEG_MAX_K 32          // neighbours per row (lane-resident lists in the grower / fallback)
+#define BSEG_MAX_COORD (1 << 23)  // shifted coordinates must stay below this: moment sums exact in fp64
+#define BSEG_MAX_CELL 2048     // kNN cell edge limit: per-lane int32 moment partials cannot overflow
 
 struct DevBuf {
   void* p = nullptr;
@@ -18,17 +21,27 @@ struct DevBuf {
 enum StageEv {
   EV_START = 0,
   EV_H2D,
-  EV_BBOX_KEYS,
+  EV_BBOX,
   EV_SORT,
   EV_CELLS,
   EV_KNN,
   EV_KNN_FB,
-  EV_NORMALS,
   EV_GROW,
   EV_FINALIZE,
   EV_RASTER,
   EV_D2H,
   EV_COUNT
+};
+
+// per-plane record produced by the grower (device and host view)
+struct PlaneRec {
+  int32_t seed;       // original index of the seed
+  int32_t pad;
+  int64_t off;        // first entry in the list pool
+  int64_t len;        // entries (duplicates kept)
+  double nrm[3];      // cur_normal after the last Broad
+  int32_t ctr[3];     // cur_center after the last Broad
+  int32_t pad2;
 };
 
 struct bseg_ctx {
@@ -43,57 +56,66 @@ struct bseg_ctx {
   int32_t mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
   bool have_points = false, have_knn = false, have_grow = false;
 
-  // ---- binning state (valid after knn stage) ----
-  int32_t cell = 0;       // level-0 cell edge
-  int key_bits = 0;       // significant bits of the Morton key
-  int64_t n_cells = 0;    // occupied level-0 cells
-  int64_t n_tiles = 0;    // occupied level-1 (2x2x2) tiles
+  // ---- binning state (valid after the knn stage) ----
+  int32_t cell = 0;     // kNN cell edge
+  int key_bits = 0;     // significant bits of the Morton key
+  int64_t n_cells = 0;  // occupied cells
   uint64_t hash_mask = 0;
+  int sort_sel = 0;     // which of keys[]/vals[] holds the sorted result
   int K = 0;
 
   // ---- grow results ----
   int32_t n_planes = 0;
   int64_t n_plane_entries = 0;
+  int64_t pool_cap = 0;
+  void* h_planes = nullptr;  // std::vector<PlaneRec>*, host copy sorted by seed
+
+  // ---- raster ----
+  int32_t rW = 0, rH = 0;
 
   // ---- device buffers ----
-  DevBuf xyz_raw;    // int32 [n][3], shifted to min=0, original order
-  DevBuf minmax;     // int32 [6] + scratch
-  DevBuf keys[2];    // u64 [n]
-  DevBuf vals[2];    // u32 [n]
-  DevBuf sort_cnt;   // u32 radix counters
-  DevBuf scan_tmp;   // u32 block sums for the scan
-  DevBuf pts;        // int4 [n] sorted: x,y,z,orig
-  DevBuf inv;        // u32 [n]  orig -> sorted position
-  DevBuf flags;      // u32 [n] scratch flags / scans
-  DevBuf flags2;     // u32 [n]
-  DevBuf cell_key;   // u64 [n_cells]
-  DevBuf cell_start; // u32 [n_cells+1]
-  DevBuf tile_start; // u32 [n_tiles+1]
-  DevBuf hash_keys;  // u64 [hash]
-  DevBuf hash_vals;  // u32 [hash]
-  DevBuf nbr;        // int32 [n][K] sorted-position space
-  DevBuf moments;    // int64 [n][10]
-  DevBuf nrm;        // double [n][3] sorted-position space
-  DevBuf curv;       // double [n]
-  DevBuf unresolved; // u32 [n] + counter
-  DevBuf counters;   // misc u64 counters
-  DevBuf out_tmp;    // staging for original-order exports
-  // grower
-  DevBuf g_state;    // int32 [n] planeIdx in sorted-position space
-  DevBuf g_label;    // int32 [n]
-  DevBuf g_list;     // int32 [2n+...] pointIdx lists (CSR of committed planes)
-  DevBuf g_stack;    // int2 frames
-  DevBuf g_planes;   // per-plane records
-  DevBuf g_aux;      // engine scratch
+  DevBuf xyz_raw;     // int32 [n][3], shifted to min=0, original order
+  DevBuf minmax;      // int32 [8]
+  DevBuf keys[2];     // u64 [n]
+  DevBuf vals[2];     // u32 [n]
+  DevBuf sort_cnt;    // u32 radix counters
+  DevBuf scan_tmp;    // u32 block sums for the scan
+  DevBuf pts;         // int4 [n] sorted: x,y,z,orig
+  DevBuf inv;         // u32 [n]  orig -> sorted position
+  DevBuf flags;       // u32 [n+1] scratch flags / scans
+  DevBuf cell_key;    // u64 [n_cells]
+  DevBuf cell_start;  // u32 [n_cells+1]
+  DevBuf hash_keys;   // u64 [hash]
+  DevBuf hash_vals;   // u32 [hash]
+  DevBuf nbr;         // int32 [n][K] sorted-position space, -1 padded
+  DevBuf nrm;         // double [n][3] sorted-position space
+  DevBuf curv;        // double [n]
+  DevBuf worklist;    // u32 lists: overflow cells, unresolved queries
+  DevBuf counters;    // u64 [64] misc counters
+  DevBuf out_tmp;     // staging for original-order exports
+  // grower (sorted-position space unless noted)
+  DevBuf g_state;     // int32 [n]: -1 free, else original index of the owning seed
+  DevBuf g_res;       // u32 [n]: reservation = min original seed index that accepted the point
+  DevBuf g_spec;      // u32 [n] (original index space): speculation record of the seed
+  DevBuf g_pool;      // int32 list pool (sorted positions): pointIdx of running / committed planes
+  DevBuf g_planes;    // PlaneRec []
+  DevBuf g_tx;        // grower transaction slots
+  DevBuf g_queue;     // u32 grower queue
+  DevBuf g_stack;     // int2 DFS frames of grower slots
+  DevBuf g_label;     // int32 [n] label in original order
+  DevBuf g_pidx;      // int32 [n] planeIdx in original order
   // raster
   DevBuf r_hist;
-  DevBuf r_image;    // double [W*H*3]
-  DevBuf r_png;      // u8 [3][W*H*3]
-  DevBuf r_seg;      // u32 [2][W*H]
+  DevBuf r_image;     // double [W*H*3]
+  DevBuf r_png;       // u8 [3][W*H*3]
+  DevBuf r_pix;       // u32 [W*H+1] pixel starts
 
   // ---- timing ----
-  cudaEvent_t ev[EV_COUNT] = {nullptr};
+  cudaEvent_t ev[EV_COUNT] = {nullptr};      // stage begin
+  cudaEvent_t ev_end[EV_COUNT] = {nullptr};  // stage end
   bool ev_set[EV_COUNT] = {false};
+  void* pinned = nullptr;  // small pinned host scratch for readbacks
+  size_t pinned_cap = 0;
   bseg_timings tm;
   int64_t launches = 0;
 };
@@ -135,7 +157,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // ---- primitives implemented in scan.cu / sort.cu ------------------------------------------------
 // in-place exclusive prefix sum of u32; total (sum of all) written to *d_total when non-null
 int bseg_exclusive_scan_u32(bseg_ctx* c, uint32_t* d_data, int64_t n, uint32_t* d_total);
-// stable LSD radix sort of (key,val) pairs on key bits [0,key_bits); result left in keys[*out]/vals[*out]
+// stable LSD radix sort of (key,val) pairs on key bits [0,key_bits); result left in k{out}/v{out}
 int bseg_sort_pairs_u64(bseg_ctx* c, uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, int64_t n,
                         int key_bits, int* out_sel);
 int bseg_sort_pairs_u32(bseg_ctx* c, uint32_t* k0, uint32_t* k1, uint32_t* v0, uint32_t* v1, int64_t n,
@@ -148,21 +170,29 @@ int stage_knn(bseg_ctx* c, const bseg_params* p);            // knn.cu
 int stage_export_knn(bseg_ctx* c, const bseg_params* p, int32_t* h_neigh, double* h_normals, double* h_curv);
 int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* h_neigh, const double* h_normals);
 int stage_grow(bseg_ctx* c, const bseg_params* p);           // grow.cu
+void grow_host_free(bseg_ctx* c);
 int stage_export_grow(bseg_ctx* c, int32_t* h_plane_idx, int32_t* h_label);
 int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* centers, int64_t* offsets,
                      int32_t* point_idx);
 int stage_paint(bseg_ctx* c, const uint16_t* h_rgb, uint16_t* h_colors);
+int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H);
 int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* a, uint8_t* b, uint8_t* cc,
                  double* th, bool device_only);
 
-static inline void ev_record(bseg_ctx* c, int which)
-{
-  cudaEventRecord(c->ev[which], c->stream);
-  c->ev_set[which] = true;
-}
+#define STAGE_BEGIN(c, which) cudaEventRecord((c)->ev[which], (c)->stream)
+#define STAGE_END(c, which)                            \
+  do {                                                 \
+    cudaEventRecord((c)->ev_end[which], (c)->stream);  \
+    (c)->ev_set[which] = true;                         \
+  } while (0)
+
+// small device -> host readback through pinned memory (synchronises the stream)
+int read_back(bseg_ctx* c, void* host_dst, const void* dev_src, size_t bytes);
 
 // ---- device helpers ---------------------------------------------------------------------------------
 #ifdef __CUDACC__
+#define FULL_MASK 0xffffffffu
+
 __device__ __forceinline__ uint64_t morton_spread21(uint32_t v)
 {
   uint64_t x = v & 0x1fffffULL;
@@ -202,12 +232,18 @@ __device__ __forceinline__ uint32_t hash_lookup(const uint64_t* __restrict__ hk,
 {
   uint64_t h = hash64(key) & mask;
   for (;;) {
-    uint64_t k = hk[h];
+    uint64_t k = __ldg(hk + h);
     if (k == key)
-      return hv[h];
+      return __ldg(hv + h);
     if (k == HASH_EMPTY)
       return 0xffffffffu;
     h = (h + 1) & mask;
   }
+}
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
 }
 #endif

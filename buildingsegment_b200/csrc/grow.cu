@@ -1,0 +1,518 @@
+// grow.cu -- north_star stage (4): plane region growing, order-faithful.
+//
+// Replaces seg_plane::get_planes / Broad / set_plane_color (my_function.cpp:180-275).  The
+// reference is a sequential, index-ordered, seeded greedy grower whose result depends on the
+// point order, so "label-exact" means reproducing its sequential
+// semantics, not connected components.  What is reproduced, line by line:
+//   :184-191  seeds are visited in original index order; a seed is appended but NOT marked (Q1)
+//   :224-236  neighbours 1..K-1 of the node are tested against the model as it was BEFORE the call:
+//             planeIdx <= 0, |(p - centre) . n| <= th_thickness, n . n_i >= th_dot; accepted
+//             points are marked and appended in neighbour order
+//   :238-239  at depth 0 all K-1 must be accepted, else the call fails and the marks stay (Q2)
+//   :241-250  model = normalised running sum of normals (fp64, acceptance order) and the int32
+//             wrapping centroid sum divided through uint64 (Q6); running sums are bit-identical
+//             to the reference's from-scratch re-summation (Q10)
+//   :252-255  depth-first descent into the accepted points, in order
+//   :199-209  commit when pointIdx.size() > th_point_count, else un-mark the list
+//
+// Engines
+//   sequential (grow_mode 1, and the head runner of mode 0): ONE warp walks the seeds in order;
+//     lane j tests neighbour j, the model lives in registers, the DFS frames in a global stack.
+//     O(1) per Broad call instead of the reference's O(P) re-summation.
+//   speculative (grow_mode 0): transactions (one per free seed) of a window of indices run
+//     concurrently against the committed state, reserving every point they accept with
+//     atomicMin(original seed index).  A transaction's decisions depend only on the state of the
+//     points it accepted, so it is valid iff it still holds all its reservations and its seed was
+//     not accepted by a lower transaction; the valid PREFIX of the window commits, the first
+//     invalid seed is re-run at the head.  Deterministic: the result is the sequential one.
+//
+// Layout: everything is indexed by Morton-sorted position s (neighbours are close in memory);
+// seed order and every exported index use the original numbering (pts[s].w, inv[orig]).
+// state[s] = -1 free, else ORIGINAL index of the seed whose transaction marked it; plane ids are
+// assigned at the end: id(owner) = 1 + #committed plane seeds below owner (cur_planeId at that time).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "bseg_arith.h"
+
+namespace {
+
+constexpr uint32_t RES_FREE = 0xffffffffu;
+
+struct GrowArgs {
+  const int4* pts;
+  const double* nrm;
+  const int32_t* nbr;
+  const uint32_t* inv;
+  int32_t* state;
+  uint32_t* res;
+  int64_t n;
+  int K;
+  double th_thick, th_dot;
+  int64_t th_count;
+  int32_t* pool;       // committed lists (CSR), the running list of the sequential engine at its end
+  int64_t pool_cap;
+  int2* stack;         // DFS frames of the sequential engine
+  PlaneRec* planes;
+  int64_t planes_cap;
+  // control block: [0] next seed (frontier), [1] pool used, [2] planes, [3] steps, [4] error, [5] transactions
+  unsigned long long* ctl;
+};
+
+enum { CTL_FRONTIER = 0, CTL_POOL = 1, CTL_PLANES = 2, CTL_STEPS = 3, CTL_ERR = 4, CTL_TX = 5 };
+
+// model of the running plane, replicated on every lane of the warp
+struct Model {
+  double mn0, mn1, mn2;  // cur_normal
+  int32_t mc0, mc1, mc2; // cur_center
+  double sn0, sn1, sn2;  // running sum of normals
+  uint32_t sc0, sc1, sc2;// running (wrapping) sum of positions
+};
+
+__device__ __forceinline__ void model_init(Model& m, const int4& p, const double* __restrict__ nr)
+{
+  m.mn0 = nr[0]; m.mn1 = nr[1]; m.mn2 = nr[2];
+  m.mc0 = p.x; m.mc1 = p.y; m.mc2 = p.z;
+  m.sn0 = 0.0 + m.mn0; m.sn1 = 0.0 + m.mn1; m.sn2 = 0.0 + m.mn2;
+  m.sc0 = (uint32_t)p.x; m.sc1 = (uint32_t)p.y; m.sc2 = (uint32_t)p.z;
+}
+
+// my_function.cpp:227-230 for one neighbour
+__device__ __forceinline__ bool geo_test(const Model& m, const int4& p, double n0, double n1, double n2,
+                                         double th_thick, double th_dot)
+{
+  int32_t p0 = (int32_t)((uint32_t)p.x - (uint32_t)m.mc0);
+  int32_t p1 = (int32_t)((uint32_t)p.y - (uint32_t)m.mc1);
+  int32_t p2 = (int32_t)((uint32_t)p.z - (uint32_t)m.mc2);
+  double dist = bseg_fabs((double)p0 * m.mn0 + (double)p1 * m.mn1 + (double)p2 * m.mn2);
+  double dot = m.mn0 * n0 + m.mn1 * n1 + m.mn2 * n2;
+  return dist <= th_thick && dot >= th_dot;
+}
+
+// my_function.cpp:241-250 after the accepted points were added to the running sums
+__device__ __forceinline__ void model_update(Model& m, int64_t len)
+{
+  double nn = bseg_sqrt((m.sn0 * m.sn0) + (m.sn1 * m.sn1) + (m.sn2 * m.sn2));
+  m.mn0 = m.sn0 / nn; m.mn1 = m.sn1 / nn; m.mn2 = m.sn2 / nn;
+  uint64_t dv = (uint64_t)len;
+  m.mc0 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc0) / dv);
+  m.mc1 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc1) / dv);
+  m.mc2 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc2) / dv);
+}
+
+// add the accepted lanes' normals / positions to the running sums in neighbour order
+__device__ __forceinline__ void model_accumulate(Model& m, uint32_t acc, const int4& p, double n0, double n1, double n2)
+{
+  while (acc) {
+    int b = __ffs(acc) - 1;
+    acc &= acc - 1;
+    m.sn0 += __shfl_sync(FULL_MASK, n0, b);
+    m.sn1 += __shfl_sync(FULL_MASK, n1, b);
+    m.sn2 += __shfl_sync(FULL_MASK, n2, b);
+    m.sc0 += (uint32_t)__shfl_sync(FULL_MASK, p.x, b);
+    m.sc1 += (uint32_t)__shfl_sync(FULL_MASK, p.y, b);
+    m.sc2 += (uint32_t)__shfl_sync(FULL_MASK, p.z, b);
+  }
+}
+
+// keep only the lowest lane of every group of accepted lanes that name the same point
+// (a row with repeated ids: the second occurrence sees planeIdx already set, :226)
+__device__ __forceinline__ bool dedupe(bool ok, int32_t id)
+{
+  uint32_t same = __match_any_sync(FULL_MASK, ok ? id : -1 - (int)(threadIdx.x & 31));
+  return ok && ((same & lanemask_lt()) == 0);
+}
+
+// ---- sequential engine -----------------------------------------------------------------------------
+// One warp.  Runs transactions in seed order starting at ctl[FRONTIER] until `max_tx` transactions
+// or `max_steps` Broad calls were executed (checked between transactions) or the cloud is done.
+__global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long long max_tx, unsigned long long max_steps)
+{
+  const int lane = threadIdx.x;
+  const int K = A.K;
+  int64_t frontier = (int64_t)A.ctl[CTL_FRONTIER];
+  int64_t pool_used = (int64_t)A.ctl[CTL_POOL];
+  int64_t n_planes = (int64_t)A.ctl[CTL_PLANES];
+  unsigned long long steps = 0, ntx = 0;
+  bool stop = false;
+
+  for (int64_t base = frontier; base < A.n && !stop; base += 32) {
+    const int64_t i_l = base + lane;
+    uint32_t s_l = 0;
+    bool free_l = false;
+    if (i_l < A.n) {
+      s_l = __ldg(A.inv + i_l);
+      free_l = __ldcg(A.state + s_l) == -1;
+    }
+    uint32_t todo = __ballot_sync(FULL_MASK, free_l);
+    frontier = base;
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      if (ntx >= max_tx || steps >= max_steps) {
+        frontier = base + b;
+        stop = true;
+        break;
+      }
+      todo &= todo - 1;
+      const int64_t seed_i = base + b;
+      const uint32_t seed_s = __shfl_sync(FULL_MASK, s_l, b);
+      if (__ldcg(A.state + seed_s) != -1)
+        continue;  // taken by a transaction of this very batch
+      ++ntx;
+      if (pool_used + A.n + 2 > A.pool_cap || n_planes >= A.planes_cap) {
+        if (lane == 0) A.ctl[CTL_ERR] = 1;
+        frontier = seed_i;
+        stop = true;
+        break;
+      }
+      int32_t* list = A.pool + pool_used;
+      int64_t len = 1;
+      if (lane == 0) list[0] = (int32_t)seed_s;
+      Model m;
+      model_init(m, __ldg(A.pts + seed_s), A.nrm + 3 * (int64_t)seed_s);
+      int64_t sp = 0;           // frames below the register-cached top
+      int64_t top_cur = 0, top_end = 0;
+      bool have_top = false;
+      uint32_t node = seed_s;
+      bool depth0 = true, ok_tx = true;
+      for (;;) {
+        ++steps;
+        int32_t id = -1;
+        if (lane >= 1 && lane < K)
+          id = __ldg(A.nbr + (int64_t)node * K + lane);
+        bool ok = false;
+        int4 p = make_int4(0, 0, 0, 0);
+        double n0 = 0, n1 = 0, n2 = 0;
+        if (id >= 0 && __ldcg(A.state + id) == -1) {
+          p = __ldg(A.pts + id);
+          const double* nr = A.nrm + 3 * (int64_t)id;
+          n0 = nr[0]; n1 = nr[1]; n2 = nr[2];
+          ok = geo_test(m, p, n0, n1, n2, A.th_thick, A.th_dot);
+        }
+        ok = dedupe(ok, id);
+        const uint32_t acc = __ballot_sync(FULL_MASK, ok);
+        const int cnt = __popc(acc);
+        if (ok) {
+          list[len + __popc(acc & lanemask_lt())] = id;
+          A.state[id] = (int32_t)seed_i;
+        }
+        __syncwarp();
+        if (depth0 && cnt < K - 1) {
+          ok_tx = false;  // :238-239 -- the marks stay (orphans)
+          break;
+        }
+        depth0 = false;
+        model_accumulate(m, acc, p, n0, n1, n2);
+        const int64_t s0 = len;
+        len += cnt;
+        model_update(m, len);
+        if (cnt > 0) {
+          if (have_top && top_cur < top_end) {
+            if (lane == 0) A.stack[sp] = make_int2((int)top_cur, (int)top_end);
+            ++sp;
+          }
+          top_cur = s0;
+          top_end = len;
+          have_top = true;
+        }
+        // next call in DFS pre-order
+        while (have_top && top_cur == top_end) {
+          if (sp > 0) {
+            --sp;
+            __syncwarp();
+            int2 f = A.stack[sp];
+            top_cur = f.x;
+            top_end = f.y;
+          } else {
+            have_top = false;
+          }
+        }
+        if (!have_top)
+          break;
+        node = (uint32_t)list[top_cur];
+        ++top_cur;
+      }
+      if (!ok_tx)
+        continue;
+      if (len > A.th_count) {  // :199
+        if (lane == 0) {
+          PlaneRec r;
+          r.seed = (int32_t)seed_i; r.pad = 0;
+          r.off = pool_used; r.len = len;
+          r.nrm[0] = m.mn0; r.nrm[1] = m.mn1; r.nrm[2] = m.mn2;
+          r.ctr[0] = m.mc0; r.ctr[1] = m.mc1; r.ctr[2] = m.mc2; r.pad2 = 0;
+          A.planes[n_planes] = r;
+        }
+        pool_used += len;
+        ++n_planes;
+      } else {
+        for (int64_t t = lane; t < len; t += 32)  // :203-209
+          A.state[list[t]] = -1;
+        __syncwarp();
+      }
+    }
+    if (!stop)
+      frontier = base + 32 < A.n ? base + 32 : A.n;
+  }
+  if (lane == 0) {
+    A.ctl[CTL_FRONTIER] = (unsigned long long)frontier;
+    A.ctl[CTL_POOL] = (unsigned long long)pool_used;
+    A.ctl[CTL_PLANES] = (unsigned long long)n_planes;
+    A.ctl[CTL_STEPS] += steps;
+    A.ctl[CTL_TX] += ntx;
+  }
+}
+
+// ---- finalize: plane ids, planeIdx and label in original order ------------------------------------------
+// id(owner) = 1 + #plane seeds < owner; label = id when the owner IS a plane seed, else the id of the
+// plane seeded at the point itself (a seed is in its own pointIdx without being marked), else 0.
+__device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int n, int32_t v)
+{
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void finalize_kernel(const int32_t* __restrict__ state, const uint32_t* __restrict__ inv,
+                                const int32_t* __restrict__ seeds, int n_planes, int64_t n,
+                                int32_t* __restrict__ pidx, int32_t* __restrict__ label)
+{
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n)
+    return;
+  int32_t owner = state[inv[o]];
+  int32_t pi = -1, lb = 0;
+  if (owner >= 0) {
+    int r = lower_bound_i32(seeds, n_planes, owner);
+    pi = r + 1;
+    if (r < n_planes && seeds[r] == owner)
+      lb = r + 1;
+  }
+  if (lb == 0) {
+    int r = lower_bound_i32(seeds, n_planes, (int32_t)o);
+    if (r < n_planes && seeds[r] == (int32_t)o)
+      lb = r + 1;
+  }
+  pidx[o] = pi;
+  label[o] = lb;
+}
+
+__global__ void export_list_kernel(const int32_t* __restrict__ pool, const int4* __restrict__ pts, int64_t src_off,
+                                   int64_t len, int32_t* __restrict__ out)
+{
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < len)
+    out[t] = pts[pool[src_off + t]].w;
+}
+
+__global__ void paint_kernel(const int32_t* __restrict__ label, const uint16_t* __restrict__ rgb, int64_t n,
+                             uint16_t* __restrict__ colors)
+{
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n)
+    return;
+  int32_t l = label[o];
+  uint16_t r = 0, g = 0, b = 0;
+  if (l > 0) {
+    r = rgb[3 * (l - 1)];
+    g = rgb[3 * (l - 1) + 1];
+    b = rgb[3 * (l - 1) + 2];
+  }
+  colors[3 * o] = r;
+  colors[3 * o + 1] = g;
+  colors[3 * o + 2] = b;
+}
+
+}  // namespace
+
+// host copy of the committed planes, sorted by seed (kept between grow and get_planes)
+static std::vector<PlaneRec>& host_planes(bseg_ctx* c)
+{
+  if (!c->h_planes)
+    c->h_planes = new std::vector<PlaneRec>();
+  return *static_cast<std::vector<PlaneRec>*>(c->h_planes);
+}
+
+void grow_host_free(bseg_ctx* c)
+{
+  if (c->h_planes)
+    delete static_cast<std::vector<PlaneRec>*>(c->h_planes);
+  c->h_planes = nullptr;
+}
+
+// temporary: mode 0 drives the sequential engine in budgeted rounds until the speculative engine lands
+static int stage_grow_speculative(bseg_ctx* c, const bseg_params*, GrowArgs& A)
+{
+  int64_t rounds = 0;
+  for (;;) {
+    grow_seq_kernel<<<1, 32, 0, c->stream>>>(A, 1ull << 16, 1ull << 20);
+    KLAUNCH_CHECK(c);
+    ++rounds;
+    unsigned long long ctl[8];
+    RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
+    if (ctl[CTL_ERR] || (int64_t)ctl[CTL_FRONTIER] >= A.n)
+      break;
+  }
+  c->tm.grow_rounds = rounds;
+  return 0;
+}
+
+int stage_grow(bseg_ctx* c, const bseg_params* p)
+{
+  const int64_t n = c->n;
+  c->n_planes = 0;
+  c->n_plane_entries = 0;
+  host_planes(c).clear();
+  if (n == 0)
+    return 0;
+  const int64_t planes_cap = n / (p->th_point_count > 0 ? p->th_point_count : 1) + 16;
+  const int64_t pool_cap = 2 * n + planes_cap + 64;
+  RC_CHECK(dev_ensure(c, c->g_state, (size_t)n * 4));
+  RC_CHECK(dev_ensure(c, c->g_res, (size_t)n * 4));
+  RC_CHECK(dev_ensure(c, c->g_pool, (size_t)pool_cap * 4));
+  RC_CHECK(dev_ensure(c, c->g_stack, (size_t)(n + 64) * 8));
+  RC_CHECK(dev_ensure(c, c->g_planes, (size_t)planes_cap * sizeof(PlaneRec)));
+  RC_CHECK(dev_ensure(c, c->g_label, (size_t)n * 4));
+  RC_CHECK(dev_ensure(c, c->g_pidx, (size_t)n * 4));
+  RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
+  c->pool_cap = pool_cap;
+
+  GrowArgs A;
+  A.pts = dptr<int4>(c->pts);
+  A.nrm = dptr<double>(c->nrm);
+  A.nbr = dptr<int32_t>(c->nbr);
+  A.inv = dptr<uint32_t>(c->inv);
+  A.state = dptr<int32_t>(c->g_state);
+  A.res = dptr<uint32_t>(c->g_res);
+  A.n = n;
+  A.K = p->K;
+  A.th_thick = (double)p->th_thickness;
+  A.th_dot = p->th_dot;
+  A.th_count = p->th_point_count;
+  A.pool = dptr<int32_t>(c->g_pool);
+  A.pool_cap = pool_cap;
+  A.stack = dptr<int2>(c->g_stack);
+  A.planes = dptr<PlaneRec>(c->g_planes);
+  A.planes_cap = planes_cap;
+  A.ctl = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 40;
+
+  STAGE_BEGIN(c, EV_GROW);
+  CU_CHECK(c, cudaMemsetAsync(A.state, 0xff, (size_t)n * 4, c->stream));
+  CU_CHECK(c, cudaMemsetAsync(A.res, 0xff, (size_t)n * 4, c->stream));
+  CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 8 * sizeof(unsigned long long), c->stream));
+  int64_t rounds = 0;
+  if (p->grow_mode == 1) {
+    grow_seq_kernel<<<1, 32, 0, c->stream>>>(A, ~0ull, ~0ull);
+    KLAUNCH_CHECK(c);
+    rounds = 1;
+  } else {
+    RC_CHECK(stage_grow_speculative(c, p, A));
+    rounds = c->tm.grow_rounds;
+  }
+  STAGE_END(c, EV_GROW);
+
+  unsigned long long ctl[8];
+  RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
+  if (ctl[CTL_ERR])
+    return bseg_fail(c, BSEG_E_CAPACITY, "plane grower ran out of list/plane capacity (code %llu)", ctl[CTL_ERR]);
+  if ((int64_t)ctl[CTL_FRONTIER] < n)
+    return bseg_fail(c, BSEG_E_STATE, "plane grower stopped at seed %llu of %lld", ctl[CTL_FRONTIER], (long long)n);
+  c->n_planes = (int32_t)ctl[CTL_PLANES];
+  c->tm.grow_steps = (int64_t)ctl[CTL_STEPS];
+  c->tm.grow_rounds = rounds;
+
+  // ---- finalize: ordinal plane ids (seed order), planeIdx and labels ----
+  STAGE_BEGIN(c, EV_FINALIZE);
+  std::vector<PlaneRec>& hp = host_planes(c);
+  hp.resize((size_t)c->n_planes);
+  if (c->n_planes > 0) {
+    CU_CHECK(c, cudaMemcpyAsync(hp.data(), A.planes, hp.size() * sizeof(PlaneRec), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    std::sort(hp.begin(), hp.end(), [](const PlaneRec& a, const PlaneRec& b) { return a.seed < b.seed; });
+  }
+  std::vector<int32_t> seeds(hp.size() + 1);
+  int64_t entries = 0;
+  for (size_t i = 0; i < hp.size(); ++i) {
+    seeds[i] = hp[i].seed;
+    entries += hp[i].len;
+  }
+  c->n_plane_entries = entries;
+  RC_CHECK(dev_ensure(c, c->g_queue, (seeds.size() + 4) * 4));
+  if (!hp.empty())
+    CU_CHECK(c, cudaMemcpyAsync(c->g_queue.p, seeds.data(), hp.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  finalize_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(A.state, A.inv, dptr<int32_t>(c->g_queue),
+                                                                      c->n_planes, n, dptr<int32_t>(c->g_pidx),
+                                                                      dptr<int32_t>(c->g_label));
+  KLAUNCH_CHECK(c);
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));  // `seeds` must outlive the upload
+  STAGE_END(c, EV_FINALIZE);
+  return 0;
+}
+
+int stage_export_grow(bseg_ctx* c, int32_t* h_plane_idx, int32_t* h_label)
+{
+  const int64_t n = c->n;
+  if (n == 0)
+    return 0;
+  STAGE_BEGIN(c, EV_D2H);
+  if (h_plane_idx)
+    CU_CHECK(c, cudaMemcpyAsync(h_plane_idx, c->g_pidx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (h_label)
+    CU_CHECK(c, cudaMemcpyAsync(h_label, c->g_label.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  STAGE_END(c, EV_D2H);
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* centers, int64_t* offsets,
+                     int32_t* point_idx)
+{
+  std::vector<PlaneRec>& hp = host_planes(c);
+  int64_t off = 0;
+  for (size_t i = 0; i < hp.size(); ++i) {
+    if (seeds) seeds[i] = hp[i].seed;
+    if (normals)
+      for (int k = 0; k < 3; ++k) normals[3 * i + k] = hp[i].nrm[k];
+    if (centers)
+      for (int k = 0; k < 3; ++k) centers[3 * i + k] = hp[i].ctr[k];
+    if (offsets) offsets[i] = off;
+    off += hp[i].len;
+  }
+  if (offsets) offsets[hp.size()] = off;
+  if (point_idx && off > 0) {
+    RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)off * 4));
+    int64_t o = 0;
+    for (size_t i = 0; i < hp.size(); ++i) {
+      export_list_kernel<<<(unsigned)ceil_div64(hp[i].len, 256), 256, 0, c->stream>>>(
+          dptr<int32_t>(c->g_pool), dptr<int4>(c->pts), hp[i].off, hp[i].len, dptr<int32_t>(c->out_tmp) + o);
+      KLAUNCH_CHECK(c);
+      o += hp[i].len;
+    }
+    CU_CHECK(c, cudaMemcpyAsync(point_idx, c->out_tmp.p, (size_t)off * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int stage_paint(bseg_ctx* c, const uint16_t* h_rgb, uint16_t* h_colors)
+{
+  const int64_t n = c->n;
+  if (n == 0)
+    return 0;
+  const size_t rgb_bytes = (size_t)c->n_planes * 6;
+  RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * 6 + rgb_bytes + 64));
+  uint16_t* d_colors = dptr<uint16_t>(c->out_tmp);
+  uint16_t* d_rgb = d_colors + 3 * n + 8;
+  if (rgb_bytes)
+    CU_CHECK(c, cudaMemcpyAsync(d_rgb, h_rgb, rgb_bytes, cudaMemcpyHostToDevice, c->stream));
+  paint_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->g_label), d_rgb, n, d_colors);
+  KLAUNCH_CHECK(c);
+  CU_CHECK(c, cudaMemcpyAsync(h_colors, d_colors, (size_t)n * 6, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}

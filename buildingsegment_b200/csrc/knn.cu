@@ -1,0 +1,707 @@
+// knn.cu -- north_star stages (2) + (3): exact k-nearest-neighbour / fixed-radius gather over the
+// voxel grid with the PCA normal fused into the epilogue.
+//
+// Replaces get_Normal_and_K_neighbor<K> (my_function.h:48-85): Open3D EstimateNormals with
+// KDTreeSearchParamHybrid(radius, max_nn) + OrientNormalsToAlignWithDirection((0,0,1)) (:63-64)
+// and KDTreeFlann::SearchKNN(p, K) per point (:75-78).  Both neighbour sets are prefixes of ONE
+// total order, (d^2 ascending, original index ascending), d^2 exact in integers:
+//   row(i)    = first K entries                                   (self included)
+//   hybrid(i) = first min(max_nn, #{d^2 < radius^2}) entries      -> covariance -> normal
+//
+// One warp owns one occupied cell.  It looks its 27 neighbour cells up in the hash table, stages
+// their points in shared memory (x,y,z,orig + sorted position), then serves the cell's queries
+// one after another: every lane evaluates M/32 candidates, the K-th / max_nn-th smallest
+// (d^2, idx) is found by a warp-wide bisection on d^2 (count with one REDUX per probe) and, only
+// when ties straddle the cut, a second bisection on the index.  The selected candidates'
+// integer moments are reduced over the warp; once 32 queries are done each lane runs the
+// closed-form fp64 eigen-solver (bseg_arith.h) for one of them.
+//
+// A row is exact when its K-th distance is below cell+1 (nothing outside the 27 cells can be
+// closer); other queries go to the ring-expansion fallback (level-L ancestor cells are contiguous
+// key ranges of the Morton-sorted cloud).  The hybrid set is always exact because cell >= radius.
+#include "common.cuh"
+#include "bseg_arith.h"
+
+namespace {
+
+constexpr int KW = 4;                  // warps per block
+constexpr int KTHREADS = KW * 32;
+constexpr int CAP = 512;               // staged candidates per warp
+
+struct KnnArgs {
+  const int4* pts;
+  const uint64_t* keys;       // sorted cell keys, one per point
+  const uint32_t* cell_start;
+  const uint64_t* cell_key;
+  uint32_t n_cells;
+  const uint64_t* hk;
+  const uint32_t* hv;
+  uint64_t hmask;
+  int32_t cell;
+  uint32_t gmax[3];           // largest cell coordinate per axis
+  int K, max_nn;
+  uint32_t r2i;               // d2 < radius^2  <=>  d2 < r2i
+  uint32_t guar2;             // (cell+1)^2: rows whose K-th d2 is below are exact
+  int32_t* nbr;
+  double* nrm;
+  double* curv;
+  uint32_t* big_cells;        // cells whose 27-neighbourhood exceeds CAP
+  uint32_t* n_big;
+  uint32_t* unres;            // queries needing ring expansion
+  uint32_t* n_unres;
+  int64_t n;
+};
+
+// selection predicate: d2 < t, plus (eq && d2 == t && idx <= u)
+struct Sel {
+  uint32_t t, u;
+  int eq;
+  __device__ __forceinline__ bool take(uint32_t d2, uint32_t idx) const
+  {
+    return d2 < t || (eq && d2 == t && idx <= u);
+  }
+};
+
+__device__ __forceinline__ uint32_t dist2(const int4& a, const int4& q)
+{
+  int dx = a.x - q.x, dy = a.y - q.y, dz = a.z - q.z;
+  return (uint32_t)(dx * dx) + (uint32_t)(dy * dy) + (uint32_t)(dz * dz);
+}
+
+// ---- candidate views --------------------------------------------------------------------------------
+// staged in shared memory, d2 cached in R registers per lane
+template <int R>
+struct CachedView {
+  uint32_t d2[R];
+  const int4* sp;
+  const uint32_t* spos;
+  int M, lane;
+  __device__ __forceinline__ void load(const int4& q)
+  {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int j = r * 32 + lane;
+      d2[r] = j < M ? dist2(sp[j], q) : 0xffffffffu;
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each(F&& f) const
+  {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int j = r * 32 + lane;
+      if (j < M)
+        f(d2[r], sp[j], spos[j]);
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_d2(F&& f) const
+  {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      f(d2[r]);
+  }
+};
+
+// streamed from global memory through the 27 ranges, d2 recomputed on every pass
+struct GlobalView {
+  const int4* pts;
+  const uint32_t* rs;  // range starts (shared)
+  const uint32_t* rl;  // range lengths (shared)
+  int4 q;
+  int lane;
+  __device__ __forceinline__ void load(const int4& qq) { q = qq; }
+  template <class F>
+  __device__ __forceinline__ void for_each(F&& f) const
+  {
+    for (int c = 0; c < 27; ++c) {
+      uint32_t s = rs[c], l = rl[c];
+      for (uint32_t t = lane; t < l; t += 32) {
+        int4 p = __ldg(pts + s + t);
+        f(dist2(p, q), p, s + t);
+      }
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each_d2(F&& f) const
+  {
+    for_each([&](uint32_t d2, const int4&, uint32_t) { f(d2); });
+  }
+};
+
+template <class V>
+__device__ __forceinline__ uint32_t count_le(const V& v, uint32_t t)
+{
+  uint32_t c = 0;
+  v.for_each_d2([&](uint32_t d2) { c += (d2 <= t) ? 1u : 0u; });
+  return __reduce_add_sync(FULL_MASK, c);
+}
+
+// k smallest by (d2, idx) among candidates with d2 <= hi; precondition count_le(hi) >= k, hi < 2^32-1
+template <class V>
+__device__ Sel select_k(const V& v, uint32_t k, uint32_t hi, uint32_t idx_hi)
+{
+  uint32_t lo = 0;
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    uint32_t c = count_le(v, mid);
+    if (c == k)
+      return Sel{mid + 1, 0, 0};
+    if (c > k) hi = mid;
+    else lo = mid + 1;
+  }
+  const uint32_t t = lo;
+  uint32_t less = 0, ties = 0;
+  v.for_each_d2([&](uint32_t d2) {
+    less += (d2 < t) ? 1u : 0u;
+    ties += (d2 == t) ? 1u : 0u;
+  });
+  less = __reduce_add_sync(FULL_MASK, less);
+  ties = __reduce_add_sync(FULL_MASK, ties);
+  const uint32_t need = k - less;
+  if (ties == need)
+    return Sel{t + 1, 0, 0};
+  // ties straddle the cut: the `need` smallest original indices among d2 == t
+  uint32_t ulo = 0, uhi = idx_hi;
+  while (ulo < uhi) {
+    uint32_t mid = ulo + ((uhi - ulo) >> 1);
+    uint32_t c = 0;
+    v.for_each([&](uint32_t d2, const int4& p, uint32_t) { c += (d2 == t && (uint32_t)p.w <= mid) ? 1u : 0u; });
+    c = __reduce_add_sync(FULL_MASK, c);
+    if (c >= need) uhi = mid;
+    else ulo = mid + 1;
+  }
+  return Sel{t, ulo, 1};
+}
+
+struct WarpScratch {
+  uint32_t rs[27], rl[27];
+  uint32_t sel_d2[32], sel_idx[32], sel_pos[32];
+};
+
+// One query: K-row + hybrid moments.  Returns the moments in (cnt, ms[9]) on every lane.
+template <class V>
+__device__ __forceinline__ void serve_query(const KnnArgs& A, V& v, WarpScratch* ws, const int4& q, uint32_t qpos,
+                                            uint32_t M, const int3& org, int lane, int& cnt_out, int (&ms)[9])
+{
+  v.load(q);
+  // ---------------- K-row ----------------
+  const uint32_t K = (uint32_t)A.K;
+  uint32_t nsel = 0;
+  bool resolved = false;
+  if (M >= K) {
+    uint32_t mx = 0;
+    v.for_each_d2([&](uint32_t d2) { mx = (d2 != 0xffffffffu && d2 > mx) ? d2 : mx; });
+    mx = __reduce_max_sync(FULL_MASK, mx);
+    Sel s = select_k(v, K, mx, (uint32_t)(A.n - 1));
+    uint32_t kth = 0;
+    v.for_each([&](uint32_t d2, const int4& p, uint32_t) {
+      if (s.take(d2, (uint32_t)p.w) && d2 > kth) kth = d2;
+    });
+    kth = __reduce_max_sync(FULL_MASK, kth);
+    resolved = kth < A.guar2;
+    // compact the K selected into scratch (per-lane serial slots, warp-wide exclusive offsets)
+    uint32_t mine = 0;
+    v.for_each([&](uint32_t d2, const int4& p, uint32_t) { mine += s.take(d2, (uint32_t)p.w) ? 1u : 0u; });
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t w = incl - mine;
+    v.for_each([&](uint32_t d2, const int4& p, uint32_t pos) {
+      if (s.take(d2, (uint32_t)p.w)) {
+        if (w < 32) {
+          ws->sel_d2[w] = d2;
+          ws->sel_idx[w] = (uint32_t)p.w;
+          ws->sel_pos[w] = pos;
+        }
+        ++w;
+      }
+    });
+    nsel = K;
+  } else {
+    // fewer candidates than K: take them all, leave the row to the fallback
+    uint32_t mine = 0;
+    v.for_each([&](uint32_t, const int4&, uint32_t) { ++mine; });
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t w = incl - mine;
+    v.for_each([&](uint32_t d2, const int4& p, uint32_t pos) {
+      if (w < 32) {
+        ws->sel_d2[w] = d2;
+        ws->sel_idx[w] = (uint32_t)p.w;
+        ws->sel_pos[w] = pos;
+      }
+      ++w;
+    });
+    nsel = M;
+  }
+  __syncwarp();
+  {
+    int32_t* row = A.nbr + (int64_t)qpos * A.K;
+    if ((uint32_t)lane < nsel) {
+      uint32_t md = ws->sel_d2[lane], mi = ws->sel_idx[lane];
+      uint32_t rank = 0;
+      for (uint32_t m = 0; m < nsel; ++m) {
+        uint32_t od = ws->sel_d2[m], oi = ws->sel_idx[m];
+        rank += (od < md || (od == md && oi < mi)) ? 1u : 0u;
+      }
+      row[rank] = (int32_t)ws->sel_pos[lane];
+    } else if (lane < A.K) {
+      row[lane] = -1;
+    }
+    if (!resolved && lane == 0) {
+      uint32_t slot = atomicAdd(A.n_unres, 1u);
+      A.unres[slot] = qpos;
+    }
+  }
+  __syncwarp();
+  // ---------------- hybrid set -> integer moments ----------------
+  uint32_t cin = 0;
+  v.for_each_d2([&](uint32_t d2) { cin += (d2 < A.r2i) ? 1u : 0u; });
+  cin = __reduce_add_sync(FULL_MASK, cin);
+  Sel h{A.r2i, 0, 0};
+  uint32_t cnt = cin;
+  if (cin > (uint32_t)A.max_nn) {
+    h = select_k(v, (uint32_t)A.max_nn, A.r2i - 1, (uint32_t)(A.n - 1));
+    cnt = (uint32_t)A.max_nn;
+  }
+  int a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  v.for_each([&](uint32_t d2, const int4& p, uint32_t) {
+    if (h.take(d2, (uint32_t)p.w)) {
+      int x = p.x - org.x, y = p.y - org.y, z = p.z - org.z;
+      a[0] += x; a[1] += y; a[2] += z;
+      a[3] += x * x; a[4] += x * y; a[5] += x * z;
+      a[6] += y * y; a[7] += y * z; a[8] += z * z;
+    }
+  });
+#pragma unroll
+  for (int m = 0; m < 9; ++m)
+    ms[m] = __reduce_add_sync(FULL_MASK, a[m]);
+  cnt_out = (int)cnt;
+}
+
+// per-lane epilogue: relative integer moments -> absolute exact sums -> fp64 normal (+ curvature)
+__device__ __forceinline__ void finish_normal(const KnnArgs& A, uint32_t qpos, int cnt, const int (&ms)[9],
+                                              const int3& org)
+{
+  const int64_t n = cnt, ox = org.x, oy = org.y, oz = org.z;
+  const int64_t sx = ms[0], sy = ms[1], sz = ms[2];
+  double sums[9];
+  sums[0] = (double)(sx + n * ox);
+  sums[1] = (double)(sy + n * oy);
+  sums[2] = (double)(sz + n * oz);
+  sums[3] = (double)((int64_t)ms[3] + 2 * ox * sx + n * ox * ox);
+  sums[4] = (double)((int64_t)ms[4] + ox * sy + oy * sx + n * ox * oy);
+  sums[5] = (double)((int64_t)ms[5] + ox * sz + oz * sx + n * ox * oz);
+  sums[6] = (double)((int64_t)ms[6] + 2 * oy * sy + n * oy * oy);
+  sums[7] = (double)((int64_t)ms[7] + oy * sz + oz * sy + n * oy * oz);
+  sums[8] = (double)((int64_t)ms[8] + 2 * oz * sz + n * oz * oz);
+  double nr[3], cv;
+  bseg_normal_from_sums(sums, cnt, nr, &cv);
+  double* o = A.nrm + (int64_t)qpos * 3;
+  o[0] = nr[0];
+  o[1] = nr[1];
+  o[2] = nr[2];
+  A.curv[qpos] = cv;
+}
+
+template <class V>
+__device__ __forceinline__ void serve_cell(const KnnArgs& A, V& v, WarpScratch* ws, uint32_t qstart, uint32_t qlen,
+                                           uint32_t M, const int3& org, int lane)
+{
+  for (uint32_t b0 = 0; b0 < qlen; b0 += 32) {
+    const uint32_t nb = min(32u, qlen - b0);
+    int my_cnt = 0;
+    int my_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t qi = 0; qi < nb; ++qi) {
+      const uint32_t qpos = qstart + b0 + qi;
+      const int4 q = __ldg(A.pts + qpos);
+      int cnt;
+      int ms[9];
+      serve_query(A, v, ws, q, qpos, M, org, lane, cnt, ms);
+      if ((uint32_t)lane == qi) {
+        my_cnt = cnt;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) my_ms[m] = ms[m];
+      }
+    }
+    if ((uint32_t)lane < nb)
+      finish_normal(A, qstart + b0 + lane, my_cnt, my_ms, org);
+  }
+}
+
+// locate the 27 neighbour cells of `cell`; fills ws->rs/rl, returns the total candidate count
+__device__ __forceinline__ uint32_t find_ranges(const KnnArgs& A, uint32_t cell, WarpScratch* ws, int lane, int3& org)
+{
+  const uint64_t key = __ldg(A.cell_key + cell);
+  const uint32_t cx = morton_compact21(key), cy = morton_compact21(key >> 1), cz = morton_compact21(key >> 2);
+  org = make_int3((int)cx * A.cell, (int)cy * A.cell, (int)cz * A.cell);
+  uint32_t start = 0, len = 0;
+  if (lane < 27) {
+    int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+    int64_t nx = (int64_t)cx + dx, ny = (int64_t)cy + dy, nz = (int64_t)cz + dz;
+    if (nx >= 0 && ny >= 0 && nz >= 0 && nx <= A.gmax[0] && ny <= A.gmax[1] && nz <= A.gmax[2]) {
+      uint32_t c = (dx == 0 && dy == 0 && dz == 0)
+                       ? cell
+                       : hash_lookup(A.hk, A.hv, A.hmask, morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+      if (c != 0xffffffffu) {
+        start = __ldg(A.cell_start + c);
+        len = __ldg(A.cell_start + c + 1) - start;
+      }
+    }
+    ws->rs[lane] = start;
+    ws->rl[lane] = len;
+  }
+  uint32_t tot = __reduce_add_sync(FULL_MASK, len);
+  __syncwarp();
+  return tot;
+}
+
+__global__ void __launch_bounds__(KTHREADS) knn_cells_kernel(KnnArgs A)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int4* sp = reinterpret_cast<int4*>(smem) + (size_t)w * CAP;
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem + (size_t)KW * CAP * 16) + (size_t)w * CAP;
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + (size_t)KW * CAP * 20) + w;
+
+  const uint32_t cell = blockIdx.x * KW + w;
+  if (cell >= A.n_cells)
+    return;
+  int3 org;
+  const uint32_t M = find_ranges(A, cell, ws, lane, org);
+  const uint32_t qstart = __ldg(A.cell_start + cell);
+  const uint32_t qlen = __ldg(A.cell_start + cell + 1) - qstart;
+  if (M > CAP) {
+    if (lane == 0) {
+      uint32_t slot = atomicAdd(A.n_big, 1u);
+      A.big_cells[slot] = cell;
+    }
+    return;
+  }
+  // stage the candidates
+  uint32_t off = 0;
+  for (int c = 0; c < 27; ++c) {
+    const uint32_t s = ws->rs[c], l = ws->rl[c];
+    for (uint32_t t = lane; t < l; t += 32) {
+      sp[off + t] = __ldg(A.pts + s + t);
+      spos[off + t] = s + t;
+    }
+    off += l;
+  }
+  __syncwarp();
+  if (M <= 128) {
+    CachedView<4> v;
+    v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
+    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
+  } else if (M <= 256) {
+    CachedView<8> v;
+    v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
+    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
+  } else {
+    CachedView<16> v;
+    v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
+    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
+  }
+}
+
+// cells whose neighbourhood does not fit the staging buffer: stream candidates from global memory
+__global__ void __launch_bounds__(KTHREADS) knn_big_cells_kernel(KnnArgs A)
+{
+  __shared__ WarpScratch wss[KW];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nbig = *A.n_big;
+  for (uint32_t i = blockIdx.x * KW + w; i < nbig; i += gridDim.x * KW) {
+    const uint32_t cell = A.big_cells[i];
+    WarpScratch* ws = &wss[w];
+    int3 org;
+    const uint32_t M = find_ranges(A, cell, ws, lane, org);
+    const uint32_t qstart = __ldg(A.cell_start + cell);
+    const uint32_t qlen = __ldg(A.cell_start + cell + 1) - qstart;
+    GlobalView v;
+    v.pts = A.pts; v.rs = ws->rs; v.rl = ws->rl; v.lane = lane;
+    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
+    __syncwarp();
+  }
+}
+
+// ---- ring-expansion fallback: one warp per unresolved query, lane l holds the l-th best ------------
+__device__ __forceinline__ bool cand_less(uint64_t d2a, uint32_t ia, uint64_t d2b, uint32_t ib)
+{
+  return d2a < d2b || (d2a == d2b && ia < ib);
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ a, uint32_t n, uint64_t v)
+{
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(a + mid) < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(KTHREADS) knn_fallback_kernel(KnnArgs A, int max_level)
+{
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nun = *A.n_unres;
+  const uint32_t kmask = A.K >= 32 ? 0xffffffffu : ((1u << A.K) - 1u);
+  for (uint32_t i = blockIdx.x * KW + w; i < nun; i += gridDim.x * KW) {
+    const uint32_t qpos = A.unres[i];
+    const int4 q = __ldg(A.pts + qpos);
+    const uint32_t qcx = (uint32_t)q.x / (uint32_t)A.cell, qcy = (uint32_t)q.y / (uint32_t)A.cell,
+                   qcz = (uint32_t)q.z / (uint32_t)A.cell;
+    uint64_t bd2 = ~0ull;
+    uint32_t bidx = 0xffffffffu, bpos = 0xffffffffu;
+    for (int L = 1; L <= max_level; ++L) {
+      bd2 = ~0ull; bidx = 0xffffffffu; bpos = 0xffffffffu;
+      const uint32_t X = qcx >> L, Y = qcy >> L, Z = qcz >> L;
+      const uint32_t gx = A.gmax[0] >> L, gy = A.gmax[1] >> L, gz = A.gmax[2] >> L;
+      uint32_t rs = 0, re = 0;
+      if (lane < 27) {
+        int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+        int64_t nx = (int64_t)X + dx, ny = (int64_t)Y + dy, nz = (int64_t)Z + dz;
+        if (nx >= 0 && ny >= 0 && nz >= 0 && nx <= gx && ny <= gy && nz <= gz) {
+          uint64_t P = morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+          rs = lower_bound_u64(A.keys, (uint32_t)A.n, P << (3 * L));
+          re = lower_bound_u64(A.keys, (uint32_t)A.n, (P + 1) << (3 * L));
+        }
+      }
+      for (int c = 0; c < 27; ++c) {
+        const uint32_t s = __shfl_sync(FULL_MASK, rs, c), e = __shfl_sync(FULL_MASK, re, c);
+        for (uint32_t t0 = s; t0 < e; t0 += 32) {
+          const uint32_t t = t0 + lane;
+          uint64_t d2 = ~0ull;
+          uint32_t idx = 0xffffffffu;
+          if (t < e) {
+            int4 p = __ldg(A.pts + t);
+            int64_t dx = (int64_t)p.x - q.x, dy = (int64_t)p.y - q.y, dz = (int64_t)p.z - q.z;
+            d2 = (uint64_t)(dx * dx + dy * dy + dz * dz);
+            idx = (uint32_t)p.w;
+          }
+          uint64_t kd2 = __shfl_sync(FULL_MASK, bd2, A.K - 1);
+          uint32_t kidx = __shfl_sync(FULL_MASK, bidx, A.K - 1);
+          uint32_t mask = __ballot_sync(FULL_MASK, t < e && cand_less(d2, idx, kd2, kidx));
+          while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint64_t cd2 = __shfl_sync(FULL_MASK, d2, src);
+            const uint32_t cidx = __shfl_sync(FULL_MASK, idx, src);
+            const uint32_t cpos = t0 + src;
+            // position = number of list entries ahead of the candidate
+            const uint32_t ahead = __ballot_sync(FULL_MASK, cand_less(bd2, bidx, cd2, cidx)) & kmask;
+            const int pos = __popc(ahead);
+            const uint64_t ud2 = __shfl_up_sync(FULL_MASK, bd2, 1);
+            const uint32_t uidx = __shfl_up_sync(FULL_MASK, bidx, 1);
+            const uint32_t upos = __shfl_up_sync(FULL_MASK, bpos, 1);
+            if (pos < A.K) {
+              if (lane > pos) { bd2 = ud2; bidx = uidx; bpos = upos; }
+              else if (lane == pos) { bd2 = cd2; bidx = cidx; bpos = cpos; }
+            }
+          }
+        }
+      }
+      const uint64_t kd2 = __shfl_sync(FULL_MASK, bd2, A.K - 1);
+      const uint64_t reach = ((uint64_t)A.cell << L) + 1;
+      const bool covered = (X <= 1) && (Y <= 1) && (Z <= 1) && (X + 1 >= gx) && (Y + 1 >= gy) && (Z + 1 >= gz);
+      if (covered || (kd2 != ~0ull && kd2 < reach * reach))
+        break;
+    }
+    if (lane < A.K)
+      A.nbr[(int64_t)qpos * A.K + lane] = (bd2 == ~0ull) ? -1 : (int32_t)bpos;
+    __syncwarp();
+  }
+}
+
+// ---- exports ---------------------------------------------------------------------------------------------
+__global__ void export_rows_kernel(const int32_t* __restrict__ nbr, const int4* __restrict__ pts, int64_t n, int K,
+                                   int32_t* __restrict__ out)
+{
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * K)
+    return;
+  int64_t s = e / K;
+  int k = (int)(e - s * K);
+  int32_t v = nbr[e];
+  int32_t o = pts[s].w;
+  out[(int64_t)o * K + k] = v < 0 ? -1 : pts[v].w;
+}
+
+__global__ void export_normals_kernel(const double* __restrict__ nrm, const double* __restrict__ curv,
+                                      const int4* __restrict__ pts, int64_t n, double* __restrict__ out_n,
+                                      double* __restrict__ out_c)
+{
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n)
+    return;
+  int64_t o = pts[s].w;
+  if (out_n) {
+    out_n[3 * o] = nrm[3 * s];
+    out_n[3 * o + 1] = nrm[3 * s + 1];
+    out_n[3 * o + 2] = nrm[3 * s + 2];
+  }
+  if (out_c)
+    out_c[o] = curv[s];
+}
+
+__global__ void import_rows_kernel(const int32_t* __restrict__ in, const uint32_t* __restrict__ inv, int64_t n, int K,
+                                   int32_t* __restrict__ nbr)
+{
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * K)
+    return;
+  int64_t o = e / K;
+  int k = (int)(e - o * K);
+  int32_t v = in[e];
+  nbr[(int64_t)inv[o] * K + k] = (v < 0 || v >= n) ? -1 : (int32_t)inv[v];
+}
+
+__global__ void import_normals_kernel(const double* __restrict__ in, const uint32_t* __restrict__ inv, int64_t n,
+                                      double* __restrict__ nrm)
+{
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n)
+    return;
+  int64_t s = inv[o];
+  nrm[3 * s] = in[3 * o];
+  nrm[3 * s + 1] = in[3 * o + 1];
+  nrm[3 * s + 2] = in[3 * o + 2];
+}
+
+}  // namespace
+
+int stage_knn(bseg_ctx* c, const bseg_params* p)
+{
+  const int64_t n = c->n;
+  if (n == 0)
+    return 0;
+  RC_CHECK(dev_ensure(c, c->nbr, (size_t)n * p->K * 4));
+  RC_CHECK(dev_ensure(c, c->nrm, (size_t)n * 24));
+  RC_CHECK(dev_ensure(c, c->curv, (size_t)n * 8));
+  RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + (size_t)c->n_cells + 16) * 4));
+  RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
+
+  KnnArgs A;
+  A.pts = dptr<int4>(c->pts);
+  A.keys = dptr<uint64_t>(c->keys[c->sort_sel]);
+  A.cell_start = dptr<uint32_t>(c->cell_start);
+  A.cell_key = dptr<uint64_t>(c->cell_key);
+  A.n_cells = (uint32_t)c->n_cells;
+  A.hk = dptr<uint64_t>(c->hash_keys);
+  A.hv = dptr<uint32_t>(c->hash_vals);
+  A.hmask = c->hash_mask;
+  A.cell = c->cell;
+  for (int k = 0; k < 3; ++k)
+    A.gmax[k] = (uint32_t)(c->mx[k] - c->mn[k]) / (uint32_t)c->cell;
+  A.K = p->K;
+  A.max_nn = p->max_nn;
+  {
+    double r2 = p->radius * p->radius;
+    uint32_t r2i = (uint32_t)r2;
+    if ((double)r2i < r2) ++r2i;  // d2 < r2  <=>  d2 < ceil(r2) for integer d2
+    A.r2i = r2i;
+  }
+  A.guar2 = (uint32_t)(c->cell + 1) * (uint32_t)(c->cell + 1);
+  A.nbr = dptr<int32_t>(c->nbr);
+  A.nrm = dptr<double>(c->nrm);
+  A.curv = dptr<double>(c->curv);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(dptr<uint64_t>(c->counters)) + 32;
+  A.n_big = cnt;
+  A.n_unres = cnt + 1;
+  A.big_cells = dptr<uint32_t>(c->worklist);
+  A.unres = dptr<uint32_t>(c->worklist) + c->n_cells + 8;
+  A.n = n;
+
+  STAGE_BEGIN(c, EV_KNN);
+  CU_CHECK(c, cudaMemsetAsync(cnt, 0, 2 * sizeof(uint32_t), c->stream));
+  const size_t smem = (size_t)KW * CAP * 20 + KW * sizeof(WarpScratch);
+  knn_cells_kernel<<<(unsigned)ceil_div64(c->n_cells, KW), KTHREADS, smem, c->stream>>>(A);
+  KLAUNCH_CHECK(c);
+  knn_big_cells_kernel<<<c->num_sms * 8, KTHREADS, 0, c->stream>>>(A);
+  KLAUNCH_CHECK(c);
+  STAGE_END(c, EV_KNN);
+
+  STAGE_BEGIN(c, EV_KNN_FB);
+  int max_level = 1;
+  {
+    uint32_t g = A.gmax[0] > A.gmax[1] ? A.gmax[0] : A.gmax[1];
+    if (A.gmax[2] > g) g = A.gmax[2];
+    while ((g >> max_level) > 0) ++max_level;
+    ++max_level;
+  }
+  knn_fallback_kernel<<<c->num_sms * 8, KTHREADS, 0, c->stream>>>(A, max_level);
+  KLAUNCH_CHECK(c);
+  STAGE_END(c, EV_KNN_FB);
+  uint32_t h[2];
+  RC_CHECK(read_back(c, h, cnt, sizeof(h)));
+  c->tm.n_unresolved = h[1];
+  c->tm.n_big_cells = h[0];
+  return 0;
+}
+
+int stage_export_knn(bseg_ctx* c, const bseg_params* p, int32_t* h_neigh, double* h_normals, double* h_curv)
+{
+  const int64_t n = c->n;
+  if (n == 0)
+    return 0;
+  const int K = p->K;
+  STAGE_BEGIN(c, EV_D2H);
+  if (h_neigh) {
+    RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * K * 4));
+    export_rows_kernel<<<(unsigned)ceil_div64(n * K, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->nbr), dptr<int4>(c->pts),
+                                                                              n, K, dptr<int32_t>(c->out_tmp));
+    KLAUNCH_CHECK(c);
+    CU_CHECK(c, cudaMemcpyAsync(h_neigh, c->out_tmp.p, (size_t)n * K * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  if (h_normals || h_curv) {
+    RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * 32));
+    double* on = dptr<double>(c->out_tmp);
+    double* oc = on + 3 * n;
+    export_normals_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(
+        dptr<double>(c->nrm), dptr<double>(c->curv), dptr<int4>(c->pts), n, h_normals ? on : nullptr,
+        h_curv ? oc : nullptr);
+    KLAUNCH_CHECK(c);
+    if (h_normals)
+      CU_CHECK(c, cudaMemcpyAsync(h_normals, on, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (h_curv)
+      CU_CHECK(c, cudaMemcpyAsync(h_curv, oc, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  STAGE_END(c, EV_D2H);
+  return 0;
+}
+
+int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* h_neigh, const double* h_normals)
+{
+  const int64_t n = c->n;
+  if (n == 0)
+    return 0;
+  const int K = p->K;
+  if (h_neigh) {
+    RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * K * 4));
+    CU_CHECK(c, cudaMemcpyAsync(c->out_tmp.p, h_neigh, (size_t)n * K * 4, cudaMemcpyHostToDevice, c->stream));
+    import_rows_kernel<<<(unsigned)ceil_div64(n * K, 256), 256, 0, c->stream>>>(
+        dptr<int32_t>(c->out_tmp), dptr<uint32_t>(c->inv), n, K, dptr<int32_t>(c->nbr));
+    KLAUNCH_CHECK(c);
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  if (h_normals) {
+    RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * 24));
+    CU_CHECK(c, cudaMemcpyAsync(c->out_tmp.p, h_normals, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
+    import_normals_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<double>(c->out_tmp),
+                                                                             dptr<uint32_t>(c->inv), n,
+                                                                             dptr<double>(c->nrm));
+    KLAUNCH_CHECK(c);
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}

@@ -1,0 +1,271 @@
+// raster.cu -- north_star stage (5): ground threshold, height / count rasterisation, PNG pixels.
+//
+// Replaces buildingSeg::groundTH (TMC3.cpp:181-198), compute_gird_picture (:127-172) and the pixel
+// part of save_image (:81-121); the PNG encode itself stays with stb_image_write on the host.
+//
+// The reference accumulates fp64 sums per pixel IN POINT ORDER (:132-148), so atomics would change
+// the rounding.  Instead: kept points (z >= th) are stably radix-sorted by their source pixel
+// (y/bin * W + x/bin), which leaves every pixel's points in original index order; one thread per
+// OUTPUT pixel then merges the four source pixels that splat into it (taps (0,0) (1,0) (0,1) (1,1))
+// by ascending point index and adds s and s*z exactly as the reference does.  Bit-exact, no atomics
+// on doubles.  Then mean height, log(count+1)+bias (shared fdlibm log, bseg_arith.h), per-channel max
+// and the three uint8 images.
+//
+// Traffic: histogram R 4 B/pt; keys R 12 W 8 B/pt; sort 4 passes x 16 B/pt; accumulate gathers
+// 12 B per tap (4 taps/pt) and writes 24 B/pixel; PNG pass R 24 W 9 B/pixel.
+#include <vector>
+
+#include "common.cuh"
+#include "bseg_arith.h"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__global__ void __launch_bounds__(TPB) zhist_kernel(const int32_t* __restrict__ xyz, int64_t n, int32_t bin_height,
+                                                    uint32_t* __restrict__ hist, int nb_bins)
+{
+  extern __shared__ uint32_t sh[];
+  const bool use_sh = nb_bins <= 4096;
+  if (use_sh) {
+    for (int i = threadIdx.x; i < nb_bins; i += TPB) sh[i] = 0;
+    __syncthreads();
+  }
+  int64_t stride = (int64_t)gridDim.x * TPB;
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+    int b = xyz[3 * i + 2] / bin_height;
+    if (use_sh) atomicAdd(&sh[b], 1u);
+    else atomicAdd(&hist[b], 1u);
+  }
+  if (use_sh) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb_bins; i += TPB)
+      if (sh[i]) atomicAdd(&hist[i], sh[i]);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) pixkey_kernel(const int32_t* __restrict__ xyz, int64_t n, int32_t bin, int32_t W,
+                                                     int32_t th, uint32_t sentinel, uint32_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ vals)
+{
+  int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n)
+    return;
+  int32_t x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  keys[i] = (z < th) ? sentinel : (uint32_t)((y / bin) * W + (x / bin));
+  vals[i] = (uint32_t)i;
+}
+
+// start[px] = first sorted position whose key >= px, for px in 0..P (P = sentinel)
+__global__ void __launch_bounds__(TPB) pixstart_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t P,
+                                                       uint32_t* __restrict__ start)
+{
+  int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (t > n)
+    return;
+  uint32_t k = t < n ? min(keys[t], P) : P;
+  int64_t kp = t > 0 ? (int64_t)min(keys[t - 1], P) : -1;
+  for (int64_t j = kp + 1; j <= (int64_t)k; ++j)
+    start[j] = (uint32_t)t;
+}
+
+struct Run {
+  uint32_t cur, end;
+  int xi, yi;
+};
+
+__global__ void __launch_bounds__(TPB) accumulate_kernel(const int32_t* __restrict__ xyz, const uint32_t* __restrict__ vals,
+                                                         const uint32_t* __restrict__ start, int32_t W, int32_t H,
+                                                         int32_t bin, double bias, double* __restrict__ image,
+                                                         unsigned long long* __restrict__ maxbits)
+{
+  int64_t px = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  double c0 = 0.0, c1 = 0.0;
+  if (px < (int64_t)W * H) {
+    const int X = (int)(px % W), Y = (int)(px / W);
+    Run r[4];
+    int nr = 0;
+    for (int yi = 0; yi < 2; ++yi)
+      for (int xi = 0; xi < 2; ++xi) {
+        int sx = X - xi, sy = Y - yi;
+        if (sx >= 0 && sy >= 0) {
+          uint32_t sp = (uint32_t)(sy * W + sx);
+          uint32_t a = start[sp], b = start[sp + 1];
+          if (a < b) {
+            r[nr].cur = a; r[nr].end = b; r[nr].xi = xi; r[nr].yi = yi;
+            ++nr;
+          }
+        }
+      }
+    uint32_t head[4];
+    for (int k = 0; k < 4; ++k)
+      head[k] = k < nr ? vals[r[k].cur] : 0xffffffffu;
+    for (;;) {
+      int best = -1;
+      uint32_t bi = 0xffffffffu;
+      for (int k = 0; k < 4; ++k)
+        if (k < nr && head[k] < bi) { bi = head[k]; best = k; }
+      if (best < 0)
+        break;
+      const int32_t p0 = xyz[3 * (int64_t)bi], p1 = xyz[3 * (int64_t)bi + 1], p2 = xyz[3 * (int64_t)bi + 2];
+      const int x = p0 / bin, y = p1 / bin;
+      const double w = 1.0 * p0 / bin - x;  // TMC3.cpp:141-142
+      const double h = 1.0 * p1 / bin - y;
+      const double s = ((r[best].xi == 1) ? w : (1 - w)) * ((r[best].yi == 1) ? h : (1 - h));  // :143
+      c1 += s;        // :144
+      c0 += s * p2;   // :145
+      ++r[best].cur;
+      head[best] = r[best].cur < r[best].end ? vals[r[best].cur] : 0xffffffffu;
+    }
+    if (c1 != 0) c0 = c0 / c1;          // :152-157
+    c1 = bseg_log(c1 + 1);              // :161
+    if (c1 != 0) c1 += bias;            // :162-163
+    image[3 * px] = c0;
+    image[3 * px + 1] = c1;
+    image[3 * px + 2] = 0.0;
+  }
+  // per-channel maximum (values are >= 0, so the bit patterns order like the doubles)
+  unsigned long long b0 = (unsigned long long)__double_as_longlong(c0 > 0 ? c0 : 0.0);
+  unsigned long long b1 = (unsigned long long)__double_as_longlong(c1 > 0 ? c1 : 0.0);
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t0 = __shfl_xor_sync(FULL_MASK, b0, o), t1 = __shfl_xor_sync(FULL_MASK, b1, o);
+    b0 = t0 > b0 ? t0 : b0;
+    b1 = t1 > b1 ? t1 : b1;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (b0) atomicMax(&maxbits[0], b0);
+    if (b1) atomicMax(&maxbits[1], b1);
+  }
+}
+
+// TMC3.cpp:93-119: three W*H*3 uint8 images
+__global__ void __launch_bounds__(TPB) png_kernel(const double* __restrict__ image, int64_t npx,
+                                                  const unsigned long long* __restrict__ maxbits,
+                                                  uint8_t* __restrict__ a, uint8_t* __restrict__ b,
+                                                  uint8_t* __restrict__ cimg)
+{
+  int64_t px = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (px >= npx)
+    return;
+  const double m0 = __longlong_as_double((long long)maxbits[0]);
+  const double m1 = __longlong_as_double((long long)maxbits[1]);
+  uint8_t va = 0, vb = 0;
+  if (m0 != 0) va = (uint8_t)(255.0 * (1.0 * image[3 * px] / m0));
+  if (m1 != 0) vb = (uint8_t)(255.0 * (1.0 * image[3 * px + 1] / m1));
+  a[3 * px] = va; a[3 * px + 1] = 0; a[3 * px + 2] = 0;
+  b[3 * px] = 0; b[3 * px + 1] = vb; b[3 * px + 2] = 0;
+  cimg[3 * px] = 0; cimg[3 * px + 1] = 0; cimg[3 * px + 2] = 0;
+}
+
+}  // namespace
+
+int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H)
+{
+  int32_t w = 0, h = 0;
+  if (c->n > 0) {
+    w = (c->mx[0] - c->mn[0]) / p->bin + 2;  // TMC3.cpp:75-76
+    h = (c->mx[1] - c->mn[1]) / p->bin + 2;
+  }
+  c->rW = w;
+  c->rH = h;
+  if (W) *W = w;
+  if (H) *H = h;
+  return 0;
+}
+
+int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_a, uint8_t* h_b, uint8_t* h_c,
+                 double* h_th, bool device_only)
+{
+  const int64_t n = c->n;
+  RC_CHECK(stage_raster_size(c, p, nullptr, nullptr));
+  if (n == 0) {
+    if (h_th) *h_th = 0.0;
+    return 0;
+  }
+  const int32_t W = c->rW, H = c->rH;
+  const int64_t npx = (int64_t)W * H;
+  if (npx >= ((int64_t)1 << 31) - 2)
+    return bseg_fail(c, BSEG_E_ARG, "raster of %d x %d pixels exceeds 2^31", W, H);
+  const int32_t zext = c->mx[2] - c->mn[2];
+  const int nb_bins = zext / p->bin_height + 1;
+
+  STAGE_BEGIN(c, EV_RASTER);
+  // ---- groundTH: z histogram, first bin where the cumulative count exceeds N/2 ----
+  RC_CHECK(dev_ensure(c, c->r_hist, (size_t)nb_bins * 4 + 64));
+  uint32_t* d_hist = dptr<uint32_t>(c->r_hist);
+  CU_CHECK(c, cudaMemsetAsync(d_hist, 0, (size_t)nb_bins * 4, c->stream));
+  {
+    int g = (int)ceil_div64(n, TPB * 8);
+    if (g > c->num_sms * 8) g = c->num_sms * 8;
+    if (g < 1) g = 1;
+    size_t sh = nb_bins <= 4096 ? (size_t)nb_bins * 4 : 0;
+    zhist_kernel<<<g, TPB, sh, c->stream>>>(dptr<int32_t>(c->xyz_raw), n, p->bin_height, d_hist, nb_bins);
+    KLAUNCH_CHECK(c);
+  }
+  std::vector<uint32_t> hist((size_t)nb_bins);
+  RC_CHECK(read_back(c, hist.data(), d_hist, (size_t)nb_bins * 4));
+  int32_t th;
+  {
+    const int TH = (int)(n / 2);
+    int total = 0;
+    int i;
+    for (i = 0; i < nb_bins; ++i) {
+      total += (int)hist[(size_t)i];
+      if (total > TH)
+        break;
+    }
+    th = i * p->bin_height;
+  }
+  if (h_th) *h_th = (double)th;
+
+  // ---- source-pixel keys, stable sort, pixel starts ----
+  for (int i = 0; i < 2; ++i) {
+    RC_CHECK(dev_ensure(c, c->keys[i], (size_t)n * 8));
+    RC_CHECK(dev_ensure(c, c->vals[i], (size_t)n * 4));
+  }
+  // keys[] doubles as u32 key storage here; this invalidates the kNN stage's sorted Morton keys,
+  // which only the (already finished) fallback needed
+  uint32_t* k0 = dptr<uint32_t>(c->keys[0]);
+  uint32_t* k1 = dptr<uint32_t>(c->keys[1]);
+  uint32_t* v0 = dptr<uint32_t>(c->vals[0]);
+  uint32_t* v1 = dptr<uint32_t>(c->vals[1]);
+  const unsigned nbk = (unsigned)ceil_div64(n, TPB);
+  pixkey_kernel<<<nbk, TPB, 0, c->stream>>>(dptr<int32_t>(c->xyz_raw), n, p->bin, W, th, (uint32_t)npx, k0, v0);
+  KLAUNCH_CHECK(c);
+  int bits = 1;
+  while (((int64_t)1 << bits) <= npx) ++bits;
+  int sel = 0;
+  RC_CHECK(bseg_sort_pairs_u32(c, k0, k1, v0, v1, n, bits, &sel));
+  const uint32_t* keys = sel ? k1 : k0;
+  const uint32_t* vals = sel ? v1 : v0;
+  RC_CHECK(dev_ensure(c, c->r_pix, (size_t)(npx + 2) * 4));
+  pixstart_kernel<<<(unsigned)ceil_div64(n + 1, TPB), TPB, 0, c->stream>>>(keys, n, (uint32_t)npx,
+                                                                         dptr<uint32_t>(c->r_pix));
+  KLAUNCH_CHECK(c);
+
+  // ---- ordered accumulation + finalisation ----
+  RC_CHECK(dev_ensure(c, c->r_image, (size_t)npx * 24));
+  RC_CHECK(dev_ensure(c, c->r_png, (size_t)npx * 9 + 64));
+  RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
+  unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 56;
+  CU_CHECK(c, cudaMemsetAsync(maxbits, 0, 2 * sizeof(unsigned long long), c->stream));
+  accumulate_kernel<<<(unsigned)ceil_div64(npx, TPB), TPB, 0, c->stream>>>(
+      dptr<int32_t>(c->xyz_raw), vals, dptr<uint32_t>(c->r_pix), W, H, p->bin, p->count_bias, dptr<double>(c->r_image),
+      maxbits);
+  KLAUNCH_CHECK(c);
+  uint8_t* da = dptr<uint8_t>(c->r_png);
+  uint8_t* db = da + 3 * npx;
+  uint8_t* dc = db + 3 * npx;
+  png_kernel<<<(unsigned)ceil_div64(npx, TPB), TPB, 0, c->stream>>>(dptr<double>(c->r_image), npx, maxbits, da, db, dc);
+  KLAUNCH_CHECK(c);
+  STAGE_END(c, EV_RASTER);
+
+  if (!device_only) {
+    if (h_image) CU_CHECK(c, cudaMemcpyAsync(h_image, c->r_image.p, (size_t)npx * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (h_a) CU_CHECK(c, cudaMemcpyAsync(h_a, da, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (h_b) CU_CHECK(c, cudaMemcpyAsync(h_b, db, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (h_c) CU_CHECK(c, cudaMemcpyAsync(h_c, dc, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}

@@ -13,9 +13,13 @@ namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                      // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 4096 keys per block
 constexpr int RS_RADIX = 256;
+// keys per thread: the scatter tile (keys + values + counters) must fit 48 KB of static shared memory
+template <typename KeyT>
+struct RsCfg {
+  static constexpr int ITEMS = sizeof(KeyT) == 8 ? 12 : 16;
+  static constexpr int TILE = RS_THREADS * ITEMS;
+};
 
 template <typename KeyT>
 __device__ __forceinline__ uint32_t digit_of(KeyT k, int shift)
@@ -30,6 +34,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
   __shared__ uint32_t h[RS_RADIX];
   h[threadIdx.x] = 0;
   __syncthreads();
+  constexpr int RS_ITEMS = RsCfg<KeyT>::ITEMS;
+  constexpr int RS_TILE = RsCfg<KeyT>::TILE;
   int64_t base = (int64_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
   for (int r = 0; r < RS_ITEMS; ++r) {
@@ -48,6 +54,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KeyT* __re
                                                                uint32_t* __restrict__ vals_out, int64_t n, int shift,
                                                                const uint32_t* __restrict__ offsets, uint32_t nblocks)
 {
+  constexpr int RS_ITEMS = RsCfg<KeyT>::ITEMS;
+  constexpr int RS_TILE = RsCfg<KeyT>::TILE;
   __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];  // per-warp digit counters -> per-warp bases
   __shared__ uint32_t dig_off[RS_RADIX];             // exclusive offset of each digit inside the tile
   __shared__ uint32_t dig_glob[RS_RADIX];            // global output offset of each digit for this block
@@ -145,6 +153,7 @@ int sort_pairs(bseg_ctx* c, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, int6
   if (n >= ((int64_t)1 << 32))
     return bseg_fail(c, BSEG_E_ARG, "sort: n >= 2^32");
   int passes = (key_bits + 7) / 8;
+  constexpr int RS_TILE = RsCfg<KeyT>::TILE;
   uint32_t nb = (uint32_t)ceil_div64(n, RS_TILE);
   size_t ncnt = (size_t)RS_RADIX * nb;
   RC_CHECK(dev_ensure(c, c->sort_cnt, (ncnt + 4) * sizeof(uint32_t)));

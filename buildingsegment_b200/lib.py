@@ -1,0 +1,263 @@
+"""ctypes binding of libbseg.so (include/bseg.h) -- the C ABI a maintainer binds from the reference's
+C++ (INTEGRATION.md shows the C++ side).  Used by tests/, bench.py and __graft_entry__.py.
+
+There is no CPU path: if libbseg.so is missing or no CUDA device is usable, every entry fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbseg.so")
+CSRC = os.path.join(HERE, "csrc")
+
+EXPORTS = [
+    "bseg_create", "bseg_destroy", "bseg_default_params", "bseg_last_error", "bseg_version",
+    "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
+    "bseg_grow_planes", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster",
+    "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
+    "bseg_point_count", "bseg_set_owned", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("K", C.c_int32), ("max_nn", C.c_int32), ("radius", C.c_double),
+        ("th_thickness", C.c_int32), ("th_point_count", C.c_int32), ("th_dot", C.c_double),
+        ("bin", C.c_int32), ("bin_height", C.c_int32), ("count_bias", C.c_double),
+        ("cell", C.c_int32), ("grow_mode", C.c_int32), ("reserved", C.c_int32 * 5),
+    ]
+
+
+class Timings(C.Structure):
+    _fields_ = [(k, C.c_float) for k in
+                ("h2d", "bbox_keys", "sort", "cells", "knn", "knn_fallback", "normals", "grow", "finalize",
+                 "raster", "d2h", "total")] + \
+               [(k, C.c_int64) for k in ("n_unresolved", "grow_steps", "grow_rounds", "kernel_launches",
+                                         "n_big_cells")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class BsegError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libbseg error {code}: {msg}")
+        self.code = code
+
+
+_LIB = None
+
+
+def build(force=False):
+    """Compile libbseg.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-s", "-C", CSRC, "clean"], check=True)
+    subprocess.run(["make", "-s", "-j8", "-C", CSRC], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise BsegError(-2, f"{LIB_PATH} is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32p, i64, i32 = C.c_void_p, C.c_void_p, C.c_int64, C.c_int32
+        L.bseg_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.bseg_destroy.argtypes = [vp]
+        L.bseg_destroy.restype = None
+        L.bseg_default_params.argtypes = [C.POINTER(Params)]
+        L.bseg_last_error.argtypes = [vp]
+        L.bseg_last_error.restype = C.c_char_p
+        L.bseg_version.restype = C.c_char_p
+        L.bseg_set_points.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.bseg_set_points_device.argtypes = [vp, vp, i64, vp, vp]
+        L.bseg_knn_normals.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
+        L.bseg_override_neigh_normals.argtypes = [vp, C.POINTER(Params), vp, vp]
+        L.bseg_grow_planes.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
+        L.bseg_get_planes.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.bseg_paint.argtypes = [vp, vp, vp]
+        L.bseg_raster_size.argtypes = [vp, C.POINTER(Params), vp, vp]
+        L.bseg_raster.argtypes = [vp, C.POINTER(Params), vp, vp, vp, vp, vp]
+        L.bseg_run_device.argtypes = [vp, C.POINTER(Params), C.c_int]
+        L.bseg_segment_host.argtypes = [vp, C.POINTER(Params), vp, i64, vp, vp, vp, vp, vp, vp, vp]
+        L.bseg_get_timings.argtypes = [vp, C.POINTER(Timings)]
+        L.bseg_reset_counters.argtypes = [vp]
+        L.bseg_stream.argtypes = [vp]
+        L.bseg_stream.restype = vp
+        L.bseg_point_count.argtypes = [vp]
+        L.bseg_point_count.restype = i64
+        L.bseg_set_owned.argtypes = [vp, i64]
+        L.bseg_debug_sort_pairs.argtypes = [vp, vp, vp, i64, C.c_int]
+        L.bseg_debug_exclusive_scan.argtypes = [vp, vp, i64]
+        _LIB = L
+    return _LIB
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().bseg_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+RUN_KNN, RUN_GROW, RUN_RASTER, RUN_ALL = 1, 2, 4, 7
+
+
+class Context:
+    """One libbseg context = one CUDA device + one stream.  Mirrors the call order of the reference's
+    main (TMC3.cpp:202-229): set_points -> knn_normals -> grow_planes -> paint / raster."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().bseg_create(C.byref(self._h), device)
+        if rc != 0:
+            raise BsegError(rc, lib().bseg_last_error(None).decode())
+        self.n = 0
+
+    def close(self):
+        if self._h:
+            lib().bseg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BsegError(rc, lib().bseg_last_error(self._h).decode())
+
+    # -- a3 ---------------------------------------------------------------------------------------
+    def set_points(self, xyz, want_shifted=True):
+        xyz = np.ascontiguousarray(xyz, np.int32)
+        assert xyz.ndim == 2 and xyz.shape[1] == 3
+        self.n = len(xyz)
+        mn = np.zeros(3, np.int32)
+        mx = np.zeros(3, np.int32)
+        out = np.empty_like(xyz) if want_shifted else None
+        self._ck(lib().bseg_set_points(self._h, _ptr(xyz), self.n, _ptr(mn), _ptr(mx), _ptr(out)))
+        return mn, mx, out
+
+    def set_points_device(self, dev_ptr, n):
+        self.n = int(n)
+        mn = np.zeros(3, np.int32)
+        mx = np.zeros(3, np.int32)
+        self._ck(lib().bseg_set_points_device(self._h, dev_ptr, self.n, _ptr(mn), _ptr(mx)))
+        return mn, mx
+
+    def set_owned(self, n_owned):
+        self._ck(lib().bseg_set_owned(self._h, int(n_owned)))
+
+    # -- a4 + a5 ----------------------------------------------------------------------------------
+    def knn_normals(self, p: Params, want_neigh=True, want_normals=True, want_curvature=False):
+        n = self.n
+        neigh = np.empty((n, p.K), np.int32) if want_neigh else None
+        nrm = np.empty((n, 3), np.float64) if want_normals else None
+        curv = np.empty(n, np.float64) if want_curvature else None
+        self._ck(lib().bseg_knn_normals(self._h, C.byref(p), _ptr(neigh), _ptr(nrm), _ptr(curv)))
+        return neigh, nrm, curv
+
+    def override(self, p: Params, neigh=None, normals=None):
+        if neigh is not None:
+            neigh = np.ascontiguousarray(neigh, np.int32)
+            assert neigh.shape == (self.n, p.K)
+        if normals is not None:
+            normals = np.ascontiguousarray(normals, np.float64)
+            assert normals.shape == (self.n, 3)
+        self._ck(lib().bseg_override_neigh_normals(self._h, C.byref(p), _ptr(neigh), _ptr(normals)))
+
+    # -- a7-a9 ------------------------------------------------------------------------------------
+    def grow_planes(self, p: Params, want_arrays=True):
+        n = self.n
+        pidx = np.empty(n, np.int32) if want_arrays else None
+        label = np.empty(n, np.int32) if want_arrays else None
+        npl = C.c_int32(0)
+        self._ck(lib().bseg_grow_planes(self._h, C.byref(p), _ptr(pidx), _ptr(label), C.addressof(npl)))
+        return pidx, label, int(npl.value)
+
+    def get_planes(self, n_planes):
+        P = int(n_planes)
+        seeds = np.empty(P, np.int32)
+        normals = np.empty((P, 3), np.float64)
+        centers = np.empty((P, 3), np.int32)
+        off = np.zeros(P + 1, np.int64)
+        self._ck(lib().bseg_get_planes(self._h, _ptr(seeds), _ptr(normals), _ptr(centers), _ptr(off), None))
+        idx = np.empty(int(off[P]), np.int32)
+        self._ck(lib().bseg_get_planes(self._h, _ptr(seeds), _ptr(normals), _ptr(centers), _ptr(off), _ptr(idx)))
+        return seeds, normals, centers, off, idx
+
+    # -- a10 --------------------------------------------------------------------------------------
+    def paint(self, plane_rgb):
+        plane_rgb = np.ascontiguousarray(plane_rgb, np.uint16)
+        colors = np.empty((self.n, 3), np.uint16)
+        self._ck(lib().bseg_paint(self._h, _ptr(plane_rgb), _ptr(colors)))
+        return colors
+
+    # -- a13-a15 ----------------------------------------------------------------------------------
+    def raster_size(self, p: Params):
+        W = C.c_int32(0)
+        H = C.c_int32(0)
+        self._ck(lib().bseg_raster_size(self._h, C.byref(p), C.addressof(W), C.addressof(H)))
+        return int(W.value), int(H.value)
+
+    def raster(self, p: Params, want_image=True, want_png=True):
+        W, H = self.raster_size(p)
+        img = np.empty((H, W, 3), np.float64) if want_image else None
+        a = np.empty((H, W, 3), np.uint8) if want_png else None
+        b = np.empty((H, W, 3), np.uint8) if want_png else None
+        c = np.empty((H, W, 3), np.uint8) if want_png else None
+        th = C.c_double(0.0)
+        self._ck(lib().bseg_raster(self._h, C.byref(p), _ptr(img), _ptr(a), _ptr(b), _ptr(c), C.addressof(th)))
+        return img, a, b, c, float(th.value)
+
+    # -- whole path -------------------------------------------------------------------------------
+    def run_device(self, p: Params, stages=RUN_ALL):
+        self._ck(lib().bseg_run_device(self._h, C.byref(p), stages))
+
+    def segment_host(self, p: Params, xyz, shifted_out, label_out, png_a=None, png_b=None):
+        """bseg_segment_host on caller-owned (ideally pinned) numpy buffers; returns (n_planes, W, H)."""
+        npl = C.c_int32(0)
+        W = C.c_int32(0)
+        H = C.c_int32(0)
+        self.n = len(xyz)
+        self._ck(lib().bseg_segment_host(self._h, C.byref(p), _ptr(xyz), len(xyz), _ptr(shifted_out), _ptr(label_out),
+                                         C.addressof(npl), _ptr(png_a), _ptr(png_b), C.addressof(W), C.addressof(H)))
+        return int(npl.value), int(W.value), int(H.value)
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._ck(lib().bseg_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def reset_counters(self):
+        self._ck(lib().bseg_reset_counters(self._h))
+
+    @property
+    def stream(self):
+        return lib().bseg_stream(self._h)
+
+    # -- self-test hooks --------------------------------------------------------------------------
+    def debug_sort_pairs(self, keys, vals, key_bits):
+        keys = np.ascontiguousarray(keys, np.uint64).copy()
+        vals = np.ascontiguousarray(vals, np.uint32).copy()
+        self._ck(lib().bseg_debug_sort_pairs(self._h, _ptr(keys), _ptr(vals), len(keys), key_bits))
+        return keys, vals
+
+    def debug_exclusive_scan(self, data):
+        data = np.ascontiguousarray(data, np.uint32).copy()
+        self._ck(lib().bseg_debug_exclusive_scan(self._h, _ptr(data), len(data)))
+        return data

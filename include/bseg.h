@@ -68,6 +68,7 @@ typedef struct bseg_timings {
   int64_t grow_steps;     /* Broad() calls executed (committed work)          */
   int64_t grow_rounds;    /* rounds of the speculative engine                 */
   int64_t kernel_launches;/* kernels launched since bseg_reset_counters       */
+  int64_t n_big_cells;    /* cells whose 27-neighbourhood did not fit the shared-memory stage */
 } bseg_timings;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
