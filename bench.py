@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- points/s of the segmentation hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points P] [--workload C2]
+
+A step = one pass of the whole hot path over one synthetic cloud:
+  bbox+shift -> Morton binning -> exact kNN + PCA normals -> order-faithful plane growing ->
+  labels -> ground threshold + height/count raster.
+`value`  : cloud already in HBM when the timed region starts (bseg_set_points_device + bseg_run_device)
+`e2e`    : through bseg_segment_host with pinned HOST buffers, H2D of the cloud and D2H of the shifted
+           cloud, labels and PNG bytes inside the timed region
+N > 1    : one process per GPU (torchrun); every rank runs its own x-slab of the city tile
+           (weak scaling, no data-path collective yet -- see DESIGN.md "multi-GPU")
+--impl reference : the CPU path (oracle/_ref = the reference's own grower/raster lines, oracle port for
+           the Open3D kNN/normals the reference links but does not vendor) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# algorithmic (compulsory) bytes per point, SURVEY.md 8(d) / DESIGN.md "roofline"
+BYTES_PER_POINT = {
+    "bbox_keys": 12 + 12 + 12,      # bbox read, shift read+write
+    "sort": 12 + 12 + 16 + 4,       # keys write, gather: read xyz, write pts + inv (radix passes are internal)
+    "cells": 8 + 4,
+    "knn": 12 + 60 + 24 + 8,        # read pts, write K=15 row, normal, curvature
+    "grow": 106,                    # per visit: row 60 + pos 12 + normal 24 + state/label 10
+    "raster": 16,
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, n, rank=0, world=1):
+    """Synthetic cloud of config `name` at `n` points per rank (int32 mm, unshifted)."""
+    from buildingsegment_b200 import synth
+
+    if world > 1:
+        # C5-style: every rank owns one 500 m block-slab of the city tile, offset along x
+        rng = np.random.default_rng(1005 + rank)
+        nb = max(4, int(40 * (500.0 / 200.0) ** 2))
+        pts = synth._block(rng, n, rank * 500.0, 0.0, 500.0, nb, 0.15, "shuffled")
+        return np.ascontiguousarray(synth.to_mm(pts))
+    return synth.make(name, n)
+
+
+def crop_sample(xyz, target):
+    """Spatial crop (same density as the full cloud): the corner square holding ~target points."""
+    if len(xyz) <= target:
+        return xyz
+    x = xyz[:, 0] - xyz[:, 0].min()
+    y = xyz[:, 1] - xyz[:, 1].min()
+    frac = np.sqrt(target / len(xyz))
+    side = frac * max(x.max(), y.max())
+    for _ in range(20):
+        m = (x < side) & (y < side)
+        k = int(m.sum())
+        if k < 0.8 * target:
+            side *= 1.1
+        elif k > 1.2 * target:
+            side *= 0.95
+        else:
+            break
+    return np.ascontiguousarray(xyz[m])
+
+
+def cpu_path(xyz, use_ref):
+    """The CPU path on one cloud: oracle port for kNN/normals (OpenMP, all cores), the reference's own
+    grower/raster lines when oracle/_ref is built (use_ref) else the oracle port.  Returns seconds."""
+    import oracle_lib as O
+
+    t0 = time.perf_counter()
+    xs, mn, mx, wh = O.bbox_shift(xyz)
+    idx, d2 = O.knn(xs, 50, cell=100)
+    nrm, _, _ = O.normals(xs, idx, d2, 100.0, 50)
+    neigh = np.ascontiguousarray(idx[:, :15])
+    if use_ref:
+        O.ref_grow(xs, nrm, neigh)
+        O.ref_raster(xyz)
+    else:
+        O.grow(xs, nrm, neigh)
+        img = O.raster(xs, mx[2] - mn[2], int(wh[0]), int(wh[1]))
+        O.save_image(img)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+
+    O.orc()
+    have_ref = O.ref() is not None
+    cores = os.cpu_count() or 1
+    n_full = args.points
+    xyz_full = make_workload(args.workload, n_full)
+    sample_n = args.ref_sample
+    xyz = crop_sample(xyz_full, sample_n)
+    del xyz_full
+    times = []
+    for it in range(args.warmup + args.steps):
+        dt = cpu_path(xyz, have_ref)
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = len(xyz) * len(times) / total
+    kind = "reference" if have_ref else "port"
+    sample = (f"spatial crop of {len(xyz)} points of {args.workload} ({n_full} points); kNN/normals = oracle port "
+              f"(Open3D 0.19 is not vendored), OpenMP x{cores}; grower+raster = "
+              + ("the reference's own lines (oracle/_ref), single thread as in the reference"
+                 if have_ref else "oracle port, single thread"))
+    out = {
+        "impl": "reference", "metric": "points/sec segmented end-to-end", "value": value, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} synthetic, {n_full} points (CPU arm timed on a {len(xyz)}-point crop)"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from buildingsegment_b200 import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    n = args.points
+    xyz = make_workload(args.workload, n, rank, world)
+    n = len(xyz)
+    ctx = lib.Context(local)
+    p = lib.default_params()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    d_xyz = torch.from_numpy(xyz).to(dev)
+    W, H = None, None
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        ctx.set_points_device(d_xyz.data_ptr(), n)
+        ctx.run_device(p, lib.RUN_ALL)
+
+    # ---- device-resident leg ----
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ctx.reset_counters()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    stage_ms = {}
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        t = ctx.timings()
+        for k in ("bbox_keys", "sort", "cells", "knn", "knn_fallback", "grow", "finalize", "raster"):
+            stage_ms[k] = stage_ms.get(k, 0.0) + t[k]
+        last_t = t
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_dev = e0.elapsed_time(e1)
+    launches = last_t["kernel_launches"]
+    t_max = torch.tensor([ms_dev], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_dev = float(t_max.item())
+    value = n * world * args.steps / (ms_dev * 1e-3)
+
+    # ---- end-to-end leg: pinned host buffers through bseg_segment_host ----
+    W, H = ctx.raster_size(p)
+    h_xyz = torch.from_numpy(xyz).pin_memory()
+    h_shift = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+    h_label = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_a = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+    h_b = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+    np_xyz, np_shift, np_label, np_a, np_b = (h_xyz.numpy(), h_shift.numpy(), h_label.numpy(), h_a.numpy(), h_b.numpy())
+
+    def step_host():
+        return ctx.segment_host(p, np_xyz, np_shift, np_label, np_a, np_b)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        npl, _, _ = step_host()
+    torch.cuda.synchronize(dev)
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    t_max = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t_max.item())
+    e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
+    h2d = n * 12
+    d2h = n * 12 + n * 4 + 2 * 3 * W * H
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_step = {k: v / args.steps for k, v in stage_ms.items()}
+        dom = max(per_step, key=lambda k: per_step[k])
+        stages = {}
+        for k, ms in per_step.items():
+            b = BYTES_PER_POINT.get(k)
+            if b and ms > 0:
+                gbs = b * n / (ms * 1e-3) / 1e9
+                stages[k] = {"ms": round(ms, 3), "bytes_per_point": b, "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+            else:
+                stages[k] = {"ms": round(ms, 3)}
+        # the kNN kernel is the single largest launch; the grower is many small launches (latency-bound)
+        roof_stage = "knn" if "knn" in stages and "gbs" in stages["knn"] else dom
+        rs = stages[roof_stage]
+        roofline = {"bound": "hbm", "kernel": "knn_cells_kernel (exact kNN + fused PCA normal)" if roof_stage == "knn" else roof_stage,
+                    "achieved": rs.get("gbs"), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": rs.get("frac"), "traffic": None, "dominant_stage": dom, "stages": stages}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import oracle_lib as O
+
+            O.orc()
+            sample = crop_sample(xyz, args.cpu_sample)
+            dt = cpu_path(sample, False)
+            cpu = {"value": len(sample) / dt, "unit": "points/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"spatial crop of {len(sample)} points of the same cloud, one pass, {dt:.1f} s; kNN/normals "
+                             f"OpenMP on all cores, grower/raster single thread (as the reference)"}
+        out = {
+            "metric": "points/sec segmented end-to-end", "value": value, "unit": "points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} synthetic suburban block, {n} points per GPU, reference defaults "
+                                   f"(K=15, r=100 mm, max_nn=50, 300 mm, 0.88, 400)" if world == 1 else
+                                   f"C5-style city tile, one 500 m block-slab of {n} points per GPU, reference defaults",
+                       "points_per_gpu": n, "l2": "inputs larger than L2 (cloud + neighbour rows >> 126 MB)",
+                       "grow_engine": "speculative (grow_mode 0)", "planes": int(npl)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "grow": {"steps": int(last_t["grow_steps"]), "rounds": int(last_t["grow_rounds"]),
+                     "n_unresolved_knn": int(last_t["n_unresolved"]), "n_big_items": int(last_t["n_big_cells"])},
+        }
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--points", type=int, default=10_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--ref-sample", type=int, default=60_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

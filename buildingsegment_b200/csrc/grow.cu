@@ -33,100 +33,14 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
-#include "bseg_arith.h"
+#include "grow.cuh"
 
 namespace {
-
-constexpr uint32_t RES_FREE = 0xffffffffu;
-
-struct GrowArgs {
-  const int4* pts;
-  const double* nrm;
-  const int32_t* nbr;
-  const uint32_t* inv;
-  int32_t* state;
-  uint32_t* res;
-  int64_t n;
-  int K;
-  double th_thick, th_dot;
-  int64_t th_count;
-  int32_t* pool;       // committed lists (CSR), the running list of the sequential engine at its end
-  int64_t pool_cap;
-  int2* stack;         // DFS frames of the sequential engine
-  PlaneRec* planes;
-  int64_t planes_cap;
-  // control block: [0] next seed (frontier), [1] pool used, [2] planes, [3] steps, [4] error, [5] transactions
-  unsigned long long* ctl;
-};
-
-enum { CTL_FRONTIER = 0, CTL_POOL = 1, CTL_PLANES = 2, CTL_STEPS = 3, CTL_ERR = 4, CTL_TX = 5 };
-
-// model of the running plane, replicated on every lane of the warp
-struct Model {
-  double mn0, mn1, mn2;  // cur_normal
-  int32_t mc0, mc1, mc2; // cur_center
-  double sn0, sn1, sn2;  // running sum of normals
-  uint32_t sc0, sc1, sc2;// running (wrapping) sum of positions
-};
-
-__device__ __forceinline__ void model_init(Model& m, const int4& p, const double* __restrict__ nr)
-{
-  m.mn0 = nr[0]; m.mn1 = nr[1]; m.mn2 = nr[2];
-  m.mc0 = p.x; m.mc1 = p.y; m.mc2 = p.z;
-  m.sn0 = 0.0 + m.mn0; m.sn1 = 0.0 + m.mn1; m.sn2 = 0.0 + m.mn2;
-  m.sc0 = (uint32_t)p.x; m.sc1 = (uint32_t)p.y; m.sc2 = (uint32_t)p.z;
-}
-
-// my_function.cpp:227-230 for one neighbour
-__device__ __forceinline__ bool geo_test(const Model& m, const int4& p, double n0, double n1, double n2,
-                                         double th_thick, double th_dot)
-{
-  int32_t p0 = (int32_t)((uint32_t)p.x - (uint32_t)m.mc0);
-  int32_t p1 = (int32_t)((uint32_t)p.y - (uint32_t)m.mc1);
-  int32_t p2 = (int32_t)((uint32_t)p.z - (uint32_t)m.mc2);
-  double dist = bseg_fabs((double)p0 * m.mn0 + (double)p1 * m.mn1 + (double)p2 * m.mn2);
-  double dot = m.mn0 * n0 + m.mn1 * n1 + m.mn2 * n2;
-  return dist <= th_thick && dot >= th_dot;
-}
-
-// my_function.cpp:241-250 after the accepted points were added to the running sums
-__device__ __forceinline__ void model_update(Model& m, int64_t len)
-{
-  double nn = bseg_sqrt((m.sn0 * m.sn0) + (m.sn1 * m.sn1) + (m.sn2 * m.sn2));
-  m.mn0 = m.sn0 / nn; m.mn1 = m.sn1 / nn; m.mn2 = m.sn2 / nn;
-  uint64_t dv = (uint64_t)len;
-  m.mc0 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc0) / dv);
-  m.mc1 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc1) / dv);
-  m.mc2 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc2) / dv);
-}
-
-// add the accepted lanes' normals / positions to the running sums in neighbour order
-__device__ __forceinline__ void model_accumulate(Model& m, uint32_t acc, const int4& p, double n0, double n1, double n2)
-{
-  while (acc) {
-    int b = __ffs(acc) - 1;
-    acc &= acc - 1;
-    m.sn0 += __shfl_sync(FULL_MASK, n0, b);
-    m.sn1 += __shfl_sync(FULL_MASK, n1, b);
-    m.sn2 += __shfl_sync(FULL_MASK, n2, b);
-    m.sc0 += (uint32_t)__shfl_sync(FULL_MASK, p.x, b);
-    m.sc1 += (uint32_t)__shfl_sync(FULL_MASK, p.y, b);
-    m.sc2 += (uint32_t)__shfl_sync(FULL_MASK, p.z, b);
-  }
-}
-
-// keep only the lowest lane of every group of accepted lanes that name the same point
-// (a row with repeated ids: the second occurrence sees planeIdx already set, :226)
-__device__ __forceinline__ bool dedupe(bool ok, int32_t id)
-{
-  uint32_t same = __match_any_sync(FULL_MASK, ok ? id : -1 - (int)(threadIdx.x & 31));
-  return ok && ((same & lanemask_lt()) == 0);
-}
 
 // ---- sequential engine -----------------------------------------------------------------------------
 // One warp.  Runs transactions in seed order starting at ctl[FRONTIER] until `max_tx` transactions
 // or `max_steps` Broad calls were executed (checked between transactions) or the cloud is done.
+template <bool NOTIFY>
 __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long long max_tx, unsigned long long max_steps)
 {
   const int lane = threadIdx.x;
@@ -159,6 +73,11 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
       const uint32_t seed_s = __shfl_sync(FULL_MASK, s_l, b);
       if (__ldcg(A.state + seed_s) != -1)
         continue;  // taken by a transaction of this very batch
+      if (NOTIFY && A.hasslot[seed_i]) {  // a speculative grower owns this seed: leave it to the window
+        frontier = seed_i;
+        stop = true;
+        break;
+      }
       ++ntx;
       if (pool_used + A.n + 2 > A.pool_cap || n_planes >= A.planes_cap) {
         if (lane == 0) A.ctl[CTL_ERR] = 1;
@@ -196,6 +115,11 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
         if (ok) {
           list[len + __popc(acc & lanemask_lt())] = id;
           A.state[id] = (int32_t)seed_i;
+          if (NOTIFY) {  // in-flight higher transactions that hold / are seeded at this point are void
+            uint32_t old = atomicMin(A.res + id, (uint32_t)seed_i);
+            if (old != RES_FREE && old > (uint32_t)seed_i) A.doom[old] = 1;
+            if (p.w > (int32_t)seed_i) A.doom[p.w] = 1;
+          }
         }
         __syncwarp();
         if (depth0 && cnt < K - 1) {
@@ -247,8 +171,10 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
         pool_used += len;
         ++n_planes;
       } else {
-        for (int64_t t = lane; t < len; t += 32)  // :203-209
+        for (int64_t t = lane; t < len; t += 32) {  // :203-209
           A.state[list[t]] = -1;
+          if (NOTIFY) atomicCAS(A.res + list[t], (uint32_t)seed_i, RES_FREE);
+        }
         __syncwarp();
       }
     }
@@ -345,21 +271,14 @@ void grow_host_free(bseg_ctx* c)
   c->h_planes = nullptr;
 }
 
-// temporary: mode 0 drives the sequential engine in budgeted rounds until the speculative engine lands
-static int stage_grow_speculative(bseg_ctx* c, const bseg_params*, GrowArgs& A)
+int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A);  // grow_spec.cu
+
+void launch_grow_seq(bseg_ctx* c, const GrowArgs& A, bool notify, unsigned long long max_tx, unsigned long long max_steps)
 {
-  int64_t rounds = 0;
-  for (;;) {
-    grow_seq_kernel<<<1, 32, 0, c->stream>>>(A, 1ull << 16, 1ull << 20);
-    KLAUNCH_CHECK(c);
-    ++rounds;
-    unsigned long long ctl[8];
-    RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
-    if (ctl[CTL_ERR] || (int64_t)ctl[CTL_FRONTIER] >= A.n)
-      break;
-  }
-  c->tm.grow_rounds = rounds;
-  return 0;
+  if (notify)
+    grow_seq_kernel<true><<<1, 32, 0, c->stream>>>(A, max_tx, max_steps);
+  else
+    grow_seq_kernel<false><<<1, 32, 0, c->stream>>>(A, max_tx, max_steps);
 }
 
 int stage_grow(bseg_ctx* c, const bseg_params* p)
@@ -400,14 +319,16 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.planes = dptr<PlaneRec>(c->g_planes);
   A.planes_cap = planes_cap;
   A.ctl = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 40;
+  A.doom = nullptr;
+  A.hasslot = nullptr;
 
   STAGE_BEGIN(c, EV_GROW);
   CU_CHECK(c, cudaMemsetAsync(A.state, 0xff, (size_t)n * 4, c->stream));
   CU_CHECK(c, cudaMemsetAsync(A.res, 0xff, (size_t)n * 4, c->stream));
-  CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 8 * sizeof(unsigned long long), c->stream));
+  CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 16 * sizeof(unsigned long long), c->stream));
   int64_t rounds = 0;
   if (p->grow_mode == 1) {
-    grow_seq_kernel<<<1, 32, 0, c->stream>>>(A, ~0ull, ~0ull);
+    launch_grow_seq(c, A, false, ~0ull, ~0ull);
     KLAUNCH_CHECK(c);
     rounds = 1;
   } else {

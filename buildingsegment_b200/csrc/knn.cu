@@ -45,7 +45,7 @@ struct KnnArgs {
   int32_t* nbr;
   double* nrm;
   double* curv;
-  uint32_t* big_cells;        // cells whose 27-neighbourhood exceeds CAP
+  uint32_t* big_cells;        // work items (cell, batch of 32 queries) of cells whose block exceeds CAP
   uint32_t* n_big;
   uint32_t* unres;            // queries needing ring expansion
   uint32_t* n_unres;
@@ -179,13 +179,13 @@ struct WarpScratch {
   uint32_t sel_d2[32], sel_idx[32], sel_pos[32];
 };
 
-// One query: K-row + hybrid moments.  Returns the moments in (cnt, ms[9]) on every lane.
+// K-row of one query from a candidate view holding `M` candidates.  `complete` says the view is
+// known to contain every point with d2 < A.guar2 (true for the 27-cell block).  Returns false when
+// the row could not be proven exact (left to the ring-expansion fallback).
 template <class V>
-__device__ __forceinline__ void serve_query(const KnnArgs& A, V& v, WarpScratch* ws, const int4& q, uint32_t qpos,
-                                            uint32_t M, const int3& org, int lane, int& cnt_out, int (&ms)[9])
+__device__ __forceinline__ bool row_from_view(const KnnArgs& A, const V& v, WarpScratch* ws, uint32_t qpos, uint32_t M,
+                                              int lane)
 {
-  v.load(q);
-  // ---------------- K-row ----------------
   const uint32_t K = (uint32_t)A.K;
   uint32_t nsel = 0;
   bool resolved = false;
@@ -193,16 +193,17 @@ __device__ __forceinline__ void serve_query(const KnnArgs& A, V& v, WarpScratch*
     uint32_t mx = 0;
     v.for_each_d2([&](uint32_t d2) { mx = (d2 != 0xffffffffu && d2 > mx) ? d2 : mx; });
     mx = __reduce_max_sync(FULL_MASK, mx);
-    Sel s = select_k(v, K, mx, (uint32_t)(A.n - 1));
-    uint32_t kth = 0;
+    const Sel s = select_k(v, K, mx, (uint32_t)(A.n - 1));
+    uint32_t kth = 0, mine = 0;
     v.for_each([&](uint32_t d2, const int4& p, uint32_t) {
-      if (s.take(d2, (uint32_t)p.w) && d2 > kth) kth = d2;
+      if (s.take(d2, (uint32_t)p.w)) {
+        ++mine;
+        if (d2 > kth) kth = d2;
+      }
     });
     kth = __reduce_max_sync(FULL_MASK, kth);
     resolved = kth < A.guar2;
     // compact the K selected into scratch (per-lane serial slots, warp-wide exclusive offsets)
-    uint32_t mine = 0;
-    v.for_each([&](uint32_t d2, const int4& p, uint32_t) { mine += s.take(d2, (uint32_t)p.w) ? 1u : 0u; });
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -243,26 +244,35 @@ __device__ __forceinline__ void serve_query(const KnnArgs& A, V& v, WarpScratch*
     nsel = M;
   }
   __syncwarp();
-  {
-    int32_t* row = A.nbr + (int64_t)qpos * A.K;
-    if ((uint32_t)lane < nsel) {
-      uint32_t md = ws->sel_d2[lane], mi = ws->sel_idx[lane];
-      uint32_t rank = 0;
-      for (uint32_t m = 0; m < nsel; ++m) {
-        uint32_t od = ws->sel_d2[m], oi = ws->sel_idx[m];
-        rank += (od < md || (od == md && oi < mi)) ? 1u : 0u;
-      }
-      row[rank] = (int32_t)ws->sel_pos[lane];
-    } else if (lane < A.K) {
-      row[lane] = -1;
+  int32_t* row = A.nbr + (int64_t)qpos * A.K;
+  if ((uint32_t)lane < nsel) {
+    uint32_t md = ws->sel_d2[lane], mi = ws->sel_idx[lane];
+    uint32_t rank = 0;
+    for (uint32_t m = 0; m < nsel; ++m) {
+      uint32_t od = ws->sel_d2[m], oi = ws->sel_idx[m];
+      rank += (od < md || (od == md && oi < mi)) ? 1u : 0u;
     }
-    if (!resolved && lane == 0) {
-      uint32_t slot = atomicAdd(A.n_unres, 1u);
-      A.unres[slot] = qpos;
-    }
+    row[rank] = (int32_t)ws->sel_pos[lane];
+  } else if (lane < A.K) {
+    row[lane] = -1;
   }
   __syncwarp();
-  // ---------------- hybrid set -> integer moments ----------------
+  return resolved;
+}
+
+__device__ __forceinline__ void push_unresolved(const KnnArgs& A, uint32_t qpos, int lane)
+{
+  if (lane == 0) {
+    uint32_t slot = atomicAdd(A.n_unres, 1u);
+    A.unres[slot] = qpos;
+  }
+}
+
+// hybrid set of one query -> integer moments relative to `org`, on every lane
+template <class V>
+__device__ __forceinline__ void hybrid_from_view(const KnnArgs& A, const V& v, const int3& org, int& cnt_out,
+                                                 int (&ms)[9])
+{
   uint32_t cin = 0;
   v.for_each_d2([&](uint32_t d2) { cin += (d2 < A.r2i) ? 1u : 0u; });
   cin = __reduce_add_sync(FULL_MASK, cin);
@@ -285,6 +295,17 @@ __device__ __forceinline__ void serve_query(const KnnArgs& A, V& v, WarpScratch*
   for (int m = 0; m < 9; ++m)
     ms[m] = __reduce_add_sync(FULL_MASK, a[m]);
   cnt_out = (int)cnt;
+}
+
+// One query against the staged 27-cell block: K-row + hybrid moments.
+template <class V>
+__device__ __forceinline__ void serve_query(const KnnArgs& A, V& v, WarpScratch* ws, const int4& q, uint32_t qpos,
+                                            uint32_t M, const int3& org, int lane, int& cnt_out, int (&ms)[9])
+{
+  v.load(q);
+  if (!row_from_view(A, v, ws, qpos, M, lane))
+    push_unresolved(A, qpos, lane);
+  hybrid_from_view(A, v, org, cnt_out, ms);
 }
 
 // per-lane epilogue: relative integer moments -> absolute exact sums -> fp64 normal (+ curvature)
@@ -380,9 +401,13 @@ __global__ void __launch_bounds__(KTHREADS) knn_cells_kernel(KnnArgs A)
   const uint32_t qstart = __ldg(A.cell_start + cell);
   const uint32_t qlen = __ldg(A.cell_start + cell + 1) - qstart;
   if (M > CAP) {
-    if (lane == 0) {
-      uint32_t slot = atomicAdd(A.n_big, 1u);
-      A.big_cells[slot] = cell;
+    const uint32_t nbatch = (qlen + 31) / 32;
+    uint32_t slot = 0;
+    if (lane == 0) slot = atomicAdd(A.n_big, nbatch);
+    slot = __shfl_sync(FULL_MASK, slot, 0);
+    for (uint32_t b = lane; b < nbatch; b += 32) {
+      A.big_cells[2 * (slot + b)] = cell;
+      A.big_cells[2 * (slot + b) + 1] = b;
     }
     return;
   }
@@ -412,22 +437,151 @@ __global__ void __launch_bounds__(KTHREADS) knn_cells_kernel(KnnArgs A)
   }
 }
 
-// cells whose neighbourhood does not fit the staging buffer: stream candidates from global memory
+// ---- dense neighbourhoods (> CAP candidates) ------------------------------------------------------
+// Work item = (cell, batch of 32 queries).  Per query the warp streams the 27 ranges from global
+// memory (L1/L2 resident: every query of the batch reads the same ranges) only to COUNT, finds a
+// squared-distance threshold T that keeps between k and CAP candidates, compacts those into shared
+// memory and runs the same cached selection as the regular path on them.
+struct StreamCount {
+  uint32_t a, b;
+};
+
+// number of candidates with d2 < ta and d2 < tb (one streaming pass)
+__device__ __forceinline__ StreamCount stream_count(const GlobalView& gv, uint32_t ta, uint32_t tb)
+{
+  uint32_t ca = 0, cb = 0;
+  gv.for_each_d2([&](uint32_t d2) {
+    ca += (d2 < ta) ? 1u : 0u;
+    cb += (d2 < tb) ? 1u : 0u;
+  });
+  StreamCount r;
+  r.a = __reduce_add_sync(FULL_MASK, ca);
+  r.b = __reduce_add_sync(FULL_MASK, cb);
+  return r;
+}
+
+// Find T <= limit with  k <= #{d2 < T} <= CAP  (or T == limit when even that holds fewer than CAP).
+// c_limit = #{d2 < limit} is known.  Returns 0 when no such T exists (more than CAP-k ties at one
+// distance): the caller then falls back to the streaming selection.
+__device__ uint32_t find_threshold(const GlobalView& gv, uint32_t limit, uint32_t c_limit, uint32_t k, uint32_t& c_out)
+{
+  if (c_limit <= (uint32_t)CAP) {
+    c_out = c_limit;
+    return limit;
+  }
+  uint32_t lo = 0, hi = limit;  // #{d2 < lo} < k,  #{d2 < hi} > CAP
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const uint32_t c = stream_count(gv, mid, mid).a;
+    if (c < k) lo = mid;
+    else if (c > (uint32_t)CAP) hi = mid;
+    else {
+      c_out = c;
+      return mid;
+    }
+  }
+  return 0;
+}
+
+// compact the candidates with d2 < T into the warp's staging area; returns how many
+__device__ __forceinline__ uint32_t stream_compact(const GlobalView& gv, uint32_t T, int4* sp, uint32_t* spos, int lane)
+{
+  uint32_t base = 0;
+  for (int c = 0; c < 27; ++c) {
+    const uint32_t s = gv.rs[c], l = gv.rl[c];
+    for (uint32_t t0 = 0; t0 < l; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      int4 p = make_int4(0, 0, 0, 0);
+      bool in = false;
+      if (t < l) {
+        p = __ldg(gv.pts + s + t);
+        in = dist2(p, gv.q) < T;
+      }
+      const uint32_t b = __ballot_sync(FULL_MASK, in);
+      if (in) {
+        const uint32_t w = base + __popc(b & lanemask_lt());
+        sp[w] = p;
+        spos[w] = s + t;
+      }
+      base += __popc(b);
+    }
+  }
+  __syncwarp();
+  return base;
+}
+
 __global__ void __launch_bounds__(KTHREADS) knn_big_cells_kernel(KnnArgs A)
 {
-  __shared__ WarpScratch wss[KW];
+  extern __shared__ __align__(16) unsigned char smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t nbig = *A.n_big;
-  for (uint32_t i = blockIdx.x * KW + w; i < nbig; i += gridDim.x * KW) {
-    const uint32_t cell = A.big_cells[i];
-    WarpScratch* ws = &wss[w];
+  int4* sp = reinterpret_cast<int4*>(smem) + (size_t)w * CAP;
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem + (size_t)KW * CAP * 16) + (size_t)w * CAP;
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + (size_t)KW * CAP * 20) + w;
+  const uint32_t nitems = *A.n_big;
+  for (uint32_t it = blockIdx.x * KW + w; it < nitems; it += gridDim.x * KW) {
+    const uint32_t cell = A.big_cells[2 * it], batch = A.big_cells[2 * it + 1];
     int3 org;
     const uint32_t M = find_ranges(A, cell, ws, lane, org);
-    const uint32_t qstart = __ldg(A.cell_start + cell);
-    const uint32_t qlen = __ldg(A.cell_start + cell + 1) - qstart;
-    GlobalView v;
-    v.pts = A.pts; v.rs = ws->rs; v.rl = ws->rl; v.lane = lane;
-    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
+    const uint32_t cstart = __ldg(A.cell_start + cell);
+    const uint32_t clen = __ldg(A.cell_start + cell + 1) - cstart;
+    const uint32_t qstart = cstart + batch * 32;
+    const uint32_t nb = min(32u, clen - batch * 32);
+    GlobalView gv;
+    gv.pts = A.pts; gv.rs = ws->rs; gv.rl = ws->rl; gv.lane = lane;
+    int my_cnt = 0;
+    int my_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t qi = 0; qi < nb; ++qi) {
+      const uint32_t qpos = qstart + qi;
+      const int4 q = __ldg(A.pts + qpos);
+      gv.load(q);
+      int cnt;
+      int ms[9];
+      const StreamCount sc = stream_count(gv, A.r2i, A.guar2);
+      // ---- hybrid set: candidates with d2 < r2i, the max_nn nearest of them ----
+      uint32_t c1 = 0;
+      const uint32_t T1 = find_threshold(gv, A.r2i, sc.a, (uint32_t)A.max_nn, c1);
+      bool row_done = false;
+      if (T1) {
+        const uint32_t m1 = stream_compact(gv, T1, sp, spos, lane);
+        CachedView<16> v;
+        v.sp = sp; v.spos = spos; v.M = (int)m1; v.lane = lane;
+        v.load(q);
+        hybrid_from_view(A, v, org, cnt, ms);
+        if (m1 >= (uint32_t)A.K) {  // the K nearest overall are among them (T1 <= r2i <= guar2)
+          row_from_view(A, v, ws, qpos, m1, lane);
+          row_done = true;
+        }
+      } else {
+        hybrid_from_view(A, gv, org, cnt, ms);  // > CAP ties at one distance: exact streaming selection
+      }
+      // ---- K-row when fewer than K points lie inside the radius ----
+      if (!row_done) {
+        if (sc.b < (uint32_t)A.K) {
+          if (lane < A.K) A.nbr[(int64_t)qpos * A.K + lane] = -1;
+          push_unresolved(A, qpos, lane);  // the K-th neighbour may be outside the block
+        } else {
+          uint32_t c2 = 0;
+          const uint32_t T2 = find_threshold(gv, A.guar2, sc.b, (uint32_t)A.K, c2);
+          if (T2) {
+            const uint32_t m2 = stream_compact(gv, T2, sp, spos, lane);
+            CachedView<16> v;
+            v.sp = sp; v.spos = spos; v.M = (int)m2; v.lane = lane;
+            v.load(q);
+            row_from_view(A, v, ws, qpos, m2, lane);
+          } else if (!row_from_view(A, gv, ws, qpos, M, lane)) {
+            push_unresolved(A, qpos, lane);
+          }
+        }
+      }
+      __syncwarp();
+      if ((uint32_t)lane == qi) {
+        my_cnt = cnt;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) my_ms[m] = ms[m];
+      }
+    }
+    if ((uint32_t)lane < nb)
+      finish_normal(A, qstart + lane, my_cnt, my_ms, org);
     __syncwarp();
   }
 }
@@ -586,7 +740,8 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   RC_CHECK(dev_ensure(c, c->nbr, (size_t)n * p->K * 4));
   RC_CHECK(dev_ensure(c, c->nrm, (size_t)n * 24));
   RC_CHECK(dev_ensure(c, c->curv, (size_t)n * 8));
-  RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + (size_t)c->n_cells + 16) * 4));
+  const size_t max_items = (size_t)c->n_cells + (size_t)n / 32 + 8;
+  RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + 2 * max_items + 16) * 4));
   RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
 
   KnnArgs A;
@@ -617,7 +772,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   A.n_big = cnt;
   A.n_unres = cnt + 1;
   A.big_cells = dptr<uint32_t>(c->worklist);
-  A.unres = dptr<uint32_t>(c->worklist) + c->n_cells + 8;
+  A.unres = dptr<uint32_t>(c->worklist) + 2 * max_items;
   A.n = n;
 
   STAGE_BEGIN(c, EV_KNN);
@@ -625,7 +780,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   const size_t smem = (size_t)KW * CAP * 20 + KW * sizeof(WarpScratch);
   knn_cells_kernel<<<(unsigned)ceil_div64(c->n_cells, KW), KTHREADS, smem, c->stream>>>(A);
   KLAUNCH_CHECK(c);
-  knn_big_cells_kernel<<<c->num_sms * 8, KTHREADS, 0, c->stream>>>(A);
+  knn_big_cells_kernel<<<c->num_sms * 4, KTHREADS, smem, c->stream>>>(A);
   KLAUNCH_CHECK(c);
   STAGE_END(c, EV_KNN);
 
