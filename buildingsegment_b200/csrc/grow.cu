@@ -40,11 +40,14 @@ namespace {
 // ---- sequential engine -----------------------------------------------------------------------------
 // One warp.  Runs transactions in seed order starting at ctl[FRONTIER] until `max_tx` transactions
 // or `max_steps` Broad calls were executed (checked between transactions) or the cloud is done.
+// NOTIFY (head runner of the speculative engine): dooms in-flight transactions it overlaps, stops at
+// seeds that own a grower slot, and -- unless allow_growers -- at any depth-0 success, which is left
+// to a slot so that it grows concurrently with the others.
 template <bool NOTIFY>
-__global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long long max_tx, unsigned long long max_steps)
+__global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long long max_tx, unsigned long long max_steps,
+                                                     int allow_growers)
 {
   const int lane = threadIdx.x;
-  const int K = A.K;
   int64_t frontier = (int64_t)A.ctl[CTL_FRONTIER];
   int64_t pool_used = (int64_t)A.ctl[CTL_POOL];
   int64_t n_planes = (int64_t)A.ctl[CTL_PLANES];
@@ -78,102 +81,43 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
         stop = true;
         break;
       }
-      ++ntx;
       if (pool_used + A.n + 2 > A.pool_cap || n_planes >= A.planes_cap) {
         if (lane == 0) A.ctl[CTL_ERR] = 1;
         frontier = seed_i;
         stop = true;
         break;
       }
-      int32_t* list = A.pool + pool_used;
-      int64_t len = 1;
-      if (lane == 0) list[0] = (int32_t)seed_s;
-      Model m;
-      model_init(m, __ldg(A.pts + seed_s), A.nrm + 3 * (int64_t)seed_s);
-      int64_t sp = 0;           // frames below the register-cached top
-      int64_t top_cur = 0, top_end = 0;
-      bool have_top = false;
-      uint32_t node = seed_s;
-      bool depth0 = true, ok_tx = true;
-      for (;;) {
-        ++steps;
-        int32_t id = -1;
-        if (lane >= 1 && lane < K)
-          id = __ldg(A.nbr + (int64_t)node * K + lane);
-        bool ok = false;
-        int4 p = make_int4(0, 0, 0, 0);
-        double n0 = 0, n1 = 0, n2 = 0;
-        if (id >= 0 && __ldcg(A.state + id) == -1) {
-          p = __ldg(A.pts + id);
-          const double* nr = A.nrm + 3 * (int64_t)id;
-          n0 = nr[0]; n1 = nr[1]; n2 = nr[2];
-          ok = geo_test(m, p, n0, n1, n2, A.th_thick, A.th_dot);
-        }
-        ok = dedupe(ok, id);
-        const uint32_t acc = __ballot_sync(FULL_MASK, ok);
-        const int cnt = __popc(acc);
-        if (ok) {
-          list[len + __popc(acc & lanemask_lt())] = id;
-          A.state[id] = (int32_t)seed_i;
-          if (NOTIFY) {  // in-flight higher transactions that hold / are seeded at this point are void
-            uint32_t old = atomicMin(A.res + id, (uint32_t)seed_i);
-            if (old != RES_FREE && old > (uint32_t)seed_i) A.doom[old] = 1;
-            if (p.w > (int32_t)seed_i) A.doom[p.w] = 1;
-          }
-        }
-        __syncwarp();
-        if (depth0 && cnt < K - 1) {
-          ok_tx = false;  // :238-239 -- the marks stay (orphans)
-          break;
-        }
-        depth0 = false;
-        model_accumulate(m, acc, p, n0, n1, n2);
-        const int64_t s0 = len;
-        len += cnt;
-        model_update(m, len);
-        if (cnt > 0) {
-          if (have_top && top_cur < top_end) {
-            if (lane == 0) A.stack[sp] = make_int2((int)top_cur, (int)top_end);
-            ++sp;
-          }
-          top_cur = s0;
-          top_end = len;
-          have_top = true;
-        }
-        // next call in DFS pre-order
-        while (have_top && top_cur == top_end) {
-          if (sp > 0) {
-            --sp;
-            __syncwarp();
-            int2 f = A.stack[sp];
-            top_cur = f.x;
-            top_end = f.y;
-          } else {
-            have_top = false;
-          }
-        }
-        if (!have_top)
-          break;
-        node = (uint32_t)list[top_cur];
-        ++top_cur;
+      FlatStore st;
+      st.list = A.pool + pool_used;
+      st.stack = A.stack;
+      if (lane == 0) st.list[0] = (int32_t)seed_s;
+      TxState t;
+      tx_begin(t, A, seed_s);
+      const TxOutcome out = tx_run<NOTIFY ? MODE_SEQ_NOTIFY : MODE_SEQ>(A, st, t, seed_i, ~0ull,
+                                                                         NOTIFY && !allow_growers, lane, steps);
+      if (out == TX_IS_GROWER) {
+        frontier = seed_i;
+        stop = true;
+        break;
       }
-      if (!ok_tx)
-        continue;
-      if (len > A.th_count) {  // :199
+      ++ntx;
+      if (out == TX_FAILED)
+        continue;  // :238-239 -- the marks stay (orphans)
+      if (t.len > A.th_count) {  // :199
         if (lane == 0) {
           PlaneRec r;
           r.seed = (int32_t)seed_i; r.pad = 0;
-          r.off = pool_used; r.len = len;
-          r.nrm[0] = m.mn0; r.nrm[1] = m.mn1; r.nrm[2] = m.mn2;
-          r.ctr[0] = m.mc0; r.ctr[1] = m.mc1; r.ctr[2] = m.mc2; r.pad2 = 0;
+          r.off = pool_used; r.len = t.len;
+          r.nrm[0] = t.m.mn0; r.nrm[1] = t.m.mn1; r.nrm[2] = t.m.mn2;
+          r.ctr[0] = t.m.mc0; r.ctr[1] = t.m.mc1; r.ctr[2] = t.m.mc2; r.pad2 = 0;
           A.planes[n_planes] = r;
         }
-        pool_used += len;
+        pool_used += t.len;
         ++n_planes;
       } else {
-        for (int64_t t = lane; t < len; t += 32) {  // :203-209
-          A.state[list[t]] = -1;
-          if (NOTIFY) atomicCAS(A.res + list[t], (uint32_t)seed_i, RES_FREE);
+        for (int64_t e = lane; e < t.len; e += 32) {  // :203-209
+          A.state[st.list[e]] = -1;
+          if (NOTIFY) atomicCAS(A.res + st.list[e], (uint32_t)seed_i, RES_FREE);
         }
         __syncwarp();
       }
@@ -273,12 +217,13 @@ void grow_host_free(bseg_ctx* c)
 
 int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A);  // grow_spec.cu
 
-void launch_grow_seq(bseg_ctx* c, const GrowArgs& A, bool notify, unsigned long long max_tx, unsigned long long max_steps)
+void launch_grow_seq(bseg_ctx* c, const GrowArgs& A, bool notify, unsigned long long max_tx, unsigned long long max_steps,
+                     int allow_growers)
 {
   if (notify)
-    grow_seq_kernel<true><<<1, 32, 0, c->stream>>>(A, max_tx, max_steps);
+    grow_seq_kernel<true><<<1, 32, 0, c->stream>>>(A, max_tx, max_steps, allow_growers);
   else
-    grow_seq_kernel<false><<<1, 32, 0, c->stream>>>(A, max_tx, max_steps);
+    grow_seq_kernel<false><<<1, 32, 0, c->stream>>>(A, max_tx, max_steps, 1);
 }
 
 int stage_grow(bseg_ctx* c, const bseg_params* p)
@@ -328,7 +273,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 16 * sizeof(unsigned long long), c->stream));
   int64_t rounds = 0;
   if (p->grow_mode == 1) {
-    launch_grow_seq(c, A, false, ~0ull, ~0ull);
+    launch_grow_seq(c, A, false, ~0ull, ~0ull, 1);
     KLAUNCH_CHECK(c);
     rounds = 1;
   } else {

@@ -1,4 +1,4 @@
-// grow.cuh -- types and device helpers shared by the sequential (grow.cu) and speculative
+// grow.cuh -- the Broad() step engine shared by the sequential (grow.cu) and speculative
 // (grow_spec.cu) plane growers.  Reference semantics: my_function.cpp:180-258 (see grow.cu).
 #pragma once
 #include "common.cuh"
@@ -59,15 +59,22 @@ __device__ __forceinline__ bool geo_test(const Model& m, const int4& p, double n
   return dist <= th_thick && dot >= th_dot;
 }
 
+// cur_center /= size (my_function.cpp:250): the int32 sum is converted to size_t first (PCCMath.h:227-235)
+__device__ __forceinline__ int32_t center_div(uint32_t sc, uint32_t len)
+{
+  if ((int32_t)sc >= 0)
+    return (int32_t)(sc / len);  // same quotient as the 64-bit form, 32-bit divide
+  return (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)sc) / (uint64_t)len);
+}
+
 // my_function.cpp:241-250 after the accepted points were added to the running sums
 __device__ __forceinline__ void model_update(Model& m, int64_t len)
 {
   double nn = bseg_sqrt((m.sn0 * m.sn0) + (m.sn1 * m.sn1) + (m.sn2 * m.sn2));
   m.mn0 = m.sn0 / nn; m.mn1 = m.sn1 / nn; m.mn2 = m.sn2 / nn;
-  uint64_t dv = (uint64_t)len;
-  m.mc0 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc0) / dv);
-  m.mc1 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc1) / dv);
-  m.mc2 = (int32_t)(uint32_t)(((uint64_t)(int64_t)(int32_t)m.sc2) / dv);
+  m.mc0 = center_div(m.sc0, (uint32_t)len);
+  m.mc1 = center_div(m.sc1, (uint32_t)len);
+  m.mc2 = center_div(m.sc2, (uint32_t)len);
 }
 
 // add the accepted lanes' normals / positions to the running sums in neighbour order
@@ -93,3 +100,246 @@ __device__ __forceinline__ bool dedupe(bool ok, int32_t id)
   return ok && ((same & lanemask_lt()) == 0);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// ---- list / frame storage ---------------------------------------------------------------------------
+// flat: the sequential engine's region at the end of the committed pool
+struct FlatStore {
+  int32_t* list;
+  int2* stack;
+  __device__ __forceinline__ bool reserve(int64_t, int) { return true; }
+  __device__ __forceinline__ void put(int64_t e, int32_t id) { list[e] = id; }
+  __device__ __forceinline__ int32_t get(int64_t e) const { return list[e]; }
+  __device__ __forceinline__ void push(int64_t sp, int2 f) { stack[sp] = f; }
+  __device__ __forceinline__ int2 pop(int64_t sp) const { return stack[sp]; }
+};
+
+// paged: grower slots of the speculative engine share one page pool
+constexpr int PAGE_SHIFT = 11;
+constexpr int PAGE_SIZE = 1 << PAGE_SHIFT;  // entries per page
+constexpr int MAX_PAGES_PER_SLOT = 2048;    // 4 M entries per plane; larger planes run in the flat region
+
+struct PagePool {
+  int32_t* list_pages;   // [n_pages][PAGE_SIZE]
+  int2* stack_pages;     // [n_pages][PAGE_SIZE]
+  uint32_t* free_pages;  // stack of free page ids
+  unsigned long long* n_free;
+};
+
+struct PagedStore {
+  PagePool pool;
+  uint32_t* ptab;       // this slot's page table [MAX_PAGES_PER_SLOT]
+  int32_t* n_pages;     // pages currently owned by the slot
+  // make entries [0, upto) addressable; one lane allocates, the warp learns the result
+  __device__ __forceinline__ bool reserve(int64_t upto, int lane)
+  {
+    int have = *n_pages;
+    const int need = (int)((upto + PAGE_SIZE - 1) >> PAGE_SHIFT);
+    if (need <= have)
+      return true;
+    int ok = 1;
+    if (lane == 0) {
+      while (have < need) {
+        if (have >= MAX_PAGES_PER_SLOT) { ok = 0; break; }
+        unsigned long long nf = atomicAdd(pool.n_free, ~0ull);  // --n_free, returns old
+        if ((long long)nf <= 0) {
+          atomicAdd(pool.n_free, 1ull);
+          ok = 0;
+          break;
+        }
+        ptab[have++] = pool.free_pages[nf - 1];
+      }
+      *n_pages = have;
+    }
+    ok = __shfl_sync(FULL_MASK, ok, 0);
+    __syncwarp();
+    return ok != 0;
+  }
+  __device__ __forceinline__ size_t at(int64_t e) const
+  {
+    return ((size_t)ptab[e >> PAGE_SHIFT] << PAGE_SHIFT) + (size_t)(e & (PAGE_SIZE - 1));
+  }
+  __device__ __forceinline__ void put(int64_t e, int32_t id) { pool.list_pages[at(e)] = id; }
+  __device__ __forceinline__ int32_t get(int64_t e) const { return pool.list_pages[at(e)]; }
+  __device__ __forceinline__ void push(int64_t sp, int2 f) { pool.stack_pages[at(sp)] = f; }
+  __device__ __forceinline__ int2 pop(int64_t sp) const { return pool.stack_pages[at(sp)]; }
+};
+
+// ---- one transaction's DFS state -------------------------------------------------------------------
+struct TxState {
+  Model m;
+  int64_t len, sp, top_cur, top_end;
+  uint32_t node;
+  int have_top, depth0;
+};
+
+enum TxOutcome {
+  TX_RUNNING = 0,      // budget exhausted, resumable
+  TX_FINISHED = 1,     // DFS complete (commit or roll back by size)
+  TX_FAILED = 2,       // depth-0 failure: orphan marks stay, no plane
+  TX_DOOMED = 3,       // overlapped a lower in-flight transaction
+  TX_OVERFLOW = 4,     // storage exhausted
+  TX_IS_GROWER = 5     // sequential engine asked to leave growers alone: nothing was marked
+};
+
+enum { MODE_SEQ = 0, MODE_SEQ_NOTIFY = 1, MODE_SPEC = 2 };
+
+__device__ __forceinline__ void tx_begin(TxState& t, const GrowArgs& A, uint32_t seed_s)
+{
+  model_init(t.m, __ldg(A.pts + seed_s), A.nrm + 3 * (int64_t)seed_s);
+  t.len = 1;
+  t.sp = 0;
+  t.top_cur = 0;
+  t.top_end = 0;
+  t.node = seed_s;
+  t.have_top = 0;
+  t.depth0 = 1;
+}
+
+// Runs Broad() calls of transaction `seed_i` until it ends or `budget` calls were made.
+//   MODE_SEQ         committed state only; accepted points are marked in `state` at once
+//   MODE_SEQ_NOTIFY  same, and in-flight speculative transactions touching them are doomed
+//   MODE_SPEC        marks are reservations (atomicMin on res); lower reservations doom this one
+// Loads of step t+1 (neighbour row, then the neighbours' state / position / normal) are issued before the
+// fp64 model update of step t, so most of their latency hides behind it.
+template <int MODE, class Store>
+__device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, unsigned long long budget,
+                            bool leave_growers, int lane, unsigned long long& steps_out)
+{
+  const int K = A.K;
+  const uint32_t me = (uint32_t)seed_i;
+  unsigned long long steps = 0;
+  TxOutcome out = TX_RUNNING;
+  // neighbour `lane` of the node: id, and its state / reservation / position / normal
+  int32_t id = -1, stt = 0;
+  uint32_t rs = RES_FREE;
+  int4 p = make_int4(0, 0, 0, 0);
+  double n0 = 0, n1 = 0, n2 = 0;
+  if (lane >= 1 && lane < K)
+    id = __ldg(A.nbr + (int64_t)t.node * K + lane);
+  if (id >= 0) {
+    stt = __ldcg(A.state + id);
+    if (MODE == MODE_SPEC) rs = __ldcg(A.res + id);
+    p = __ldg(A.pts + id);
+    const double* nr = A.nrm + 3 * (int64_t)id;
+    n0 = __ldg(nr); n1 = __ldg(nr + 1); n2 = __ldg(nr + 2);
+  }
+  while (steps < budget) {
+    if (!st.reserve(t.len + 2 * K, lane)) {  // before anything is marked
+      out = TX_OVERFLOW;
+      break;
+    }
+    ++steps;
+    bool ok = id >= 0 && stt == -1 && (MODE != MODE_SPEC || rs != me) &&
+              geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
+    ok = dedupe(ok, id);
+    if (leave_growers && t.depth0) {
+      if (__popc(__ballot_sync(FULL_MASK, ok)) == K - 1) {
+        out = TX_IS_GROWER;
+        --steps;
+        break;
+      }
+    }
+    bool lost = false;
+    if (ok) {
+      if (MODE == MODE_SPEC) {
+        const uint32_t old = atomicMin(A.res + id, me);
+        if (old < me) lost = true;
+        else {
+          if (old != RES_FREE) A.doom[old] = 1;
+          if (p.w > (int32_t)me) A.doom[p.w] = 1;
+        }
+      } else {
+        A.state[id] = (int32_t)seed_i;
+        if (MODE == MODE_SEQ_NOTIFY) {
+          const uint32_t old = atomicMin(A.res + id, me);
+          if (old != RES_FREE && old > me) A.doom[old] = 1;
+          if (p.w > (int32_t)me) A.doom[p.w] = 1;
+        }
+      }
+    }
+    const uint32_t acc = __ballot_sync(FULL_MASK, ok);
+    const int cnt = __popc(acc);
+    if (ok)
+      st.put(t.len + __popc(acc & lanemask_lt()), id);  // recorded even when lost, so the release covers it
+    __syncwarp();
+    if (MODE == MODE_SPEC && __any_sync(FULL_MASK, lost)) {
+      t.len += cnt;
+      out = TX_DOOMED;
+      break;
+    }
+    if (t.depth0 && cnt < K - 1) {
+      t.len += cnt;
+      out = TX_FAILED;  // :238-239
+      break;
+    }
+    t.depth0 = 0;
+    // ---- DFS bookkeeping: which node is next (:252-255) ----
+    const int64_t s0 = t.len;
+    t.len += cnt;
+    uint32_t next = 0;
+    bool have_next = false;
+    if (cnt > 0) {
+      if (t.have_top && t.top_cur < t.top_end) {
+        if (lane == 0) st.push(t.sp, make_int2((int)t.top_cur, (int)t.top_end));
+        ++t.sp;
+      }
+      t.top_cur = s0 + 1;  // the first accepted point is visited right away
+      t.top_end = t.len;
+      t.have_top = 1;
+      next = (uint32_t)__shfl_sync(FULL_MASK, id, __ffs(acc) - 1);
+      have_next = true;
+      // every accepted point gets its own Broad() later: pull its row towards L2 now
+      if (ok) prefetch_l2(A.nbr + (int64_t)id * K);
+    } else {
+      while (t.have_top && t.top_cur == t.top_end) {
+        if (t.sp > 0) {
+          --t.sp;
+          __syncwarp();
+          const int2 f = st.pop(t.sp);
+          t.top_cur = f.x;
+          t.top_end = f.y;
+        } else {
+          t.have_top = 0;
+        }
+      }
+      if (t.have_top) {
+        next = (uint32_t)st.get(t.top_cur);
+        ++t.top_cur;
+        have_next = true;
+      }
+    }
+    // ---- software pipeline: next row, running sums, next gather, model update ----
+    int32_t nid = -1;
+    if (have_next && lane >= 1 && lane < K)
+      nid = __ldg(A.nbr + (int64_t)next * K + lane);
+    model_accumulate(t.m, acc, p, n0, n1, n2);
+    int32_t nstt = 0;
+    uint32_t nrs = RES_FREE;
+    int4 np = make_int4(0, 0, 0, 0);
+    double m0 = 0, m1 = 0, m2 = 0;
+    if (nid >= 0) {
+      nstt = __ldcg(A.state + nid);
+      if (MODE == MODE_SPEC) nrs = __ldcg(A.res + nid);
+      np = __ldg(A.pts + nid);
+      const double* nr = A.nrm + 3 * (int64_t)nid;
+      m0 = __ldg(nr); m1 = __ldg(nr + 1); m2 = __ldg(nr + 2);
+    }
+    model_update(t.m, t.len);
+    if (!have_next) {
+      out = TX_FINISHED;
+      break;
+    }
+    t.node = next;
+    id = nid; stt = nstt; rs = nrs; p = np; n0 = m0; n1 = m1; n2 = m2;
+    if (MODE == MODE_SPEC && (steps & 15) == 0 && ((volatile uint8_t*)A.doom)[seed_i]) {
+      out = TX_DOOMED;
+      break;
+    }
+  }
+  steps_out += steps;
+  return out;
+}

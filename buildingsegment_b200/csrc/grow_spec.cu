@@ -40,29 +40,35 @@ struct Slot {
   int32_t seed_i;
   uint32_t seed_s;
   int32_t status;
-  int32_t depth0;
   int32_t failed;    // depth-0 failure inside a slot: commits as orphan marks, no plane
-  int32_t have_top;
-  uint32_t node;
+  int32_t n_pages;   // pages of the pool this slot owns
   int32_t pad;
-  int64_t len, sp, top_cur, top_end;
   unsigned long long steps;
-  Model m;
+  TxState t;
 };
 
 struct SpecArgs {
   GrowArgs A;
   Slot* slots;
   int G;
-  int64_t capS;
-  int32_t* slist;
-  int2* sstack;
+  PagePool pool;
+  uint32_t* ptabs;  // [G][MAX_PAGES_PER_SLOT]
+  uint32_t n_pool_pages;
   uint32_t* kind;   // [C] window-relative
   uint32_t* mask;   // [C]
   uint32_t* flag;   // [C] candidate flags -> exclusive scan
   uint32_t* free_ids;
   unsigned long long* sc;
 };
+
+__device__ __forceinline__ PagedStore slot_store(const SpecArgs& S, int g)
+{
+  PagedStore st;
+  st.pool = S.pool;
+  st.ptab = S.ptabs + (size_t)g * MAX_PAGES_PER_SLOT;
+  st.n_pages = &S.slots[g].n_pages;
+  return st;
+}
 
 __global__ void __launch_bounds__(TPB) spec_prepare_kernel(SpecArgs S, int64_t F, int64_t C)
 {
@@ -166,8 +172,9 @@ __global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t F,
   sl.seed_s = __ldg(S.A.inv + F + t);
   sl.status = ST_NEW;
   sl.steps = 0;
-  sl.len = 0;
+  sl.t.len = 0;
   sl.failed = 0;
+  sl.n_pages = 0;
   S.A.hasslot[F + t] = 1;
   S.kind[t] = KIND_SLOT + g;
 }
@@ -191,132 +198,33 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   if (status != ST_NEW && status != ST_RUNNING)
     return;
   const int64_t seed_i = sl.seed_i;
-  const uint32_t me = (uint32_t)seed_i;
   if (A.doom[seed_i]) {
     __syncwarp();
-    if (lane == 0) {
-      if (status == ST_NEW) sl.len = 0;
-      sl.status = ST_DOOMED;
-    }
+    if (lane == 0) sl.status = ST_DOOMED;  // len stays 0 for a slot that never started
     return;
   }
-  const int K = A.K;
-  int32_t* list = S.slist + (int64_t)g * S.capS;
-  int2* stack = S.sstack + (int64_t)g * S.capS;
-  Model m;
-  int64_t len, sp, top_cur, top_end;
-  bool have_top, depth0;
-  uint32_t node;
+  PagedStore st = slot_store(S, g);
+  TxState t;
   if (status == ST_NEW) {
-    len = 1;
-    if (lane == 0) list[0] = (int32_t)sl.seed_s;
-    model_init(m, __ldg(A.pts + sl.seed_s), A.nrm + 3 * (int64_t)sl.seed_s);
-    sp = 0; top_cur = 0; top_end = 0; have_top = false; depth0 = true;
-    node = sl.seed_s;
+    tx_begin(t, A, sl.seed_s);
+    if (!st.reserve(1, lane)) {
+      if (lane == 0) sl.status = ST_DOOMED;
+      return;
+    }
+    if (lane == 0) st.put(0, (int32_t)sl.seed_s);
+    __syncwarp();
   } else {
-    m = sl.m;
-    len = sl.len; sp = sl.sp; top_cur = sl.top_cur; top_end = sl.top_end;
-    have_top = sl.have_top != 0; depth0 = sl.depth0 != 0;
-    node = sl.node;
+    t = sl.t;
   }
   __syncwarp();
   unsigned long long steps = 0;
-  int new_status = ST_RUNNING;
-  int failed = 0;
-  while (steps < budget) {
-    ++steps;
-    int32_t id = -1;
-    if (lane >= 1 && lane < K)
-      id = __ldg(A.nbr + (int64_t)node * K + lane);
-    bool ok = false;
-    int4 p = make_int4(0, 0, 0, 0);
-    double n0 = 0, n1 = 0, n2 = 0;
-    if (id >= 0 && __ldcg(A.state + id) == -1 && __ldcg(A.res + id) != me) {
-      p = __ldg(A.pts + id);
-      const double* nr = A.nrm + 3 * (int64_t)id;
-      n0 = nr[0]; n1 = nr[1]; n2 = nr[2];
-      ok = geo_test(m, p, n0, n1, n2, A.th_thick, A.th_dot);
-    }
-    ok = dedupe(ok, id);
-    bool lost = false;
-    if (ok) {
-      const uint32_t old = atomicMin(A.res + id, me);
-      if (old < me) {
-        lost = true;
-      } else {
-        if (old != RES_FREE) A.doom[old] = 1;
-        if (p.w > (int32_t)me) A.doom[p.w] = 1;
-      }
-    }
-    const uint32_t acc = __ballot_sync(FULL_MASK, ok);
-    const bool any_lost = __any_sync(FULL_MASK, lost);
-    const int cnt = __popc(acc);
-    if (ok)
-      list[len + __popc(acc & lanemask_lt())] = id;  // recorded even when lost, so the release covers it
-    __syncwarp();
-    if (any_lost) {
-      len += cnt;
-      new_status = ST_DOOMED;
-      break;
-    }
-    if (depth0 && cnt < K - 1) {
-      len += cnt;
-      failed = 1;
-      new_status = ST_FINISHED;
-      break;
-    }
-    depth0 = false;
-    model_accumulate(m, acc, p, n0, n1, n2);
-    const int64_t s0 = len;
-    len += cnt;
-    model_update(m, len);
-    if (cnt > 0) {
-      if (have_top && top_cur < top_end) {
-        if (lane == 0) stack[sp] = make_int2((int)top_cur, (int)top_end);
-        ++sp;
-      }
-      top_cur = s0;
-      top_end = len;
-      have_top = true;
-    }
-    while (have_top && top_cur == top_end) {
-      if (sp > 0) {
-        --sp;
-        __syncwarp();
-        int2 f = stack[sp];
-        top_cur = f.x;
-        top_end = f.y;
-      } else {
-        have_top = false;
-      }
-    }
-    if (!have_top) {
-      new_status = ST_FINISHED;
-      break;
-    }
-    if (len + K > S.capS) {  // does not fit a slot: the head runner will grow it in the big region
-      new_status = ST_DOOMED;
-      break;
-    }
-    node = (uint32_t)list[top_cur];
-    ++top_cur;
-    if ((steps & 15) == 0 && ((volatile uint8_t*)A.doom)[seed_i]) {
-      // put the fetched node back so a (never happening) resume would be consistent
-      --top_cur;
-      new_status = ST_DOOMED;
-      break;
-    }
-  }
+  const TxOutcome out = tx_run<MODE_SPEC>(A, st, t, seed_i, budget, false, lane, steps);
   __syncwarp();
   if (lane == 0) {
-    sl.m = m;
-    sl.len = len; sl.sp = sp; sl.top_cur = top_cur; sl.top_end = top_end;
-    sl.have_top = have_top ? 1 : 0;
-    sl.depth0 = depth0 ? 1 : 0;
-    sl.node = node;
-    sl.failed = failed;
+    sl.t = t;
     sl.steps += steps;
-    sl.status = new_status;
+    sl.failed = out == TX_FAILED ? 1 : 0;
+    sl.status = out == TX_RUNNING ? ST_RUNNING : ((out == TX_FINISHED || out == TX_FAILED) ? ST_FINISHED : ST_DOOMED);
   }
 }
 
@@ -379,13 +287,13 @@ __global__ void __launch_bounds__(GW * 32) spec_commit_slots_kernel(SpecArgs S, 
   const int64_t first_bad = fbu > (unsigned long long)C ? C : (int64_t)fbu;  // slots beyond the window were not validated
   const int64_t i = sl.seed_i;
   const int64_t t = i - F;
-  const int32_t* list = S.slist + (int64_t)g * S.capS;
-  const int64_t len = sl.len;
+  const PagedStore st = slot_store(S, g);
+  const int64_t len = sl.t.len;
   bool release = false, free_slot = false;
   if (t < first_bad) {  // finished and clean
     free_slot = true;
     if (sl.failed) {
-      for (int64_t e = 1 + lane; e < len; e += 32) A.state[list[e]] = (int32_t)i;
+      for (int64_t e = 1 + lane; e < len; e += 32) A.state[st.get(e)] = (int32_t)i;
     } else if (len > A.th_count) {
       unsigned long long off = 0, pl = 0;
       if (lane == 0) {
@@ -398,7 +306,7 @@ __global__ void __launch_bounds__(GW * 32) spec_commit_slots_kernel(SpecArgs S, 
         if (lane == 0) A.ctl[CTL_ERR] = 2;
       } else {
         for (int64_t e = lane; e < len; e += 32) {
-          const int32_t id = list[e];
+          const int32_t id = st.get(e);
           A.pool[off + e] = id;
           if (e >= 1) A.state[id] = (int32_t)i;
         }
@@ -406,8 +314,8 @@ __global__ void __launch_bounds__(GW * 32) spec_commit_slots_kernel(SpecArgs S, 
           PlaneRec r;
           r.seed = (int32_t)i; r.pad = 0;
           r.off = (int64_t)off; r.len = len;
-          r.nrm[0] = sl.m.mn0; r.nrm[1] = sl.m.mn1; r.nrm[2] = sl.m.mn2;
-          r.ctr[0] = sl.m.mc0; r.ctr[1] = sl.m.mc1; r.ctr[2] = sl.m.mc2; r.pad2 = 0;
+          r.nrm[0] = sl.t.m.mn0; r.nrm[1] = sl.t.m.mn1; r.nrm[2] = sl.t.m.mn2;
+          r.ctr[0] = sl.t.m.mc0; r.ctr[1] = sl.t.m.mc1; r.ctr[2] = sl.t.m.mc2; r.pad2 = 0;
           A.planes[pl] = r;
         }
       }
@@ -424,9 +332,16 @@ __global__ void __launch_bounds__(GW * 32) spec_commit_slots_kernel(SpecArgs S, 
     if (lane == 0) atomicAdd(&S.sc[SC_SLOT_STEPS], sl.steps);
   }
   if (release)
-    for (int64_t e = lane; e < len; e += 32) atomicCAS(A.res + list[e], (uint32_t)i, RES_FREE);
+    for (int64_t e = lane; e < len; e += 32) atomicCAS(A.res + st.get(e), (uint32_t)i, RES_FREE);
   __syncwarp();
   if (free_slot && lane == 0) {
+    // pages back to the pool
+    const int np = sl.n_pages;
+    if (np > 0) {
+      const unsigned long long pos = atomicAdd(S.pool.n_free, (unsigned long long)np);
+      for (int k = 0; k < np; ++k) S.pool.free_pages[pos + k] = st.ptab[k];
+    }
+    sl.n_pages = 0;
     sl.status = ST_FREE;
     A.hasslot[i] = 0;
     const unsigned long long pos = atomicAdd(&S.sc[SC_NFREE], 1ull);
@@ -438,23 +353,31 @@ __global__ void spec_advance_kernel(SpecArgs S, int64_t F, int64_t C)
 {
   unsigned long long fb = S.sc[SC_FIRST_BAD];
   if (fb > (unsigned long long)C) fb = (unsigned long long)C;
-  S.A.ctl[CTL_FRONTIER] = (unsigned long long)F + fb;
+  const unsigned long long Fn = (unsigned long long)F + fb;
+  S.A.ctl[CTL_FRONTIER] = Fn;
   S.sc[5] = fb;  // reported to the host
+  S.sc[6] = (Fn < (unsigned long long)S.A.n && S.A.hasslot[Fn]) ? 1ull : 0ull;  // a live slot sits at the head
 }
 
 __global__ void spec_init_kernel(SpecArgs S)
 {
-  int g = blockIdx.x * TPB + threadIdx.x;
-  if (g < S.G) {
+  uint32_t g = blockIdx.x * TPB + threadIdx.x;
+  if (g < (uint32_t)S.G) {
     S.slots[g].status = ST_FREE;
+    S.slots[g].n_pages = 0;
     S.free_ids[g] = (uint32_t)(S.G - 1 - g);
   }
-  if (g == 0) S.sc[SC_NFREE] = (unsigned long long)S.G;
+  if (g < S.n_pool_pages) S.pool.free_pages[g] = g;
+  if (g == 0) {
+    S.sc[SC_NFREE] = (unsigned long long)S.G;
+    *S.pool.n_free = (unsigned long long)S.n_pool_pages;
+  }
 }
 
 }  // namespace
 
-void launch_grow_seq(bseg_ctx* c, const GrowArgs& A, bool notify, unsigned long long max_tx, unsigned long long max_steps);
+void launch_grow_seq(bseg_ctx* c, const GrowArgs& A, bool notify, unsigned long long max_tx, unsigned long long max_steps,
+                     int allow_growers);
 
 int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
 {
@@ -462,28 +385,39 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   const int64_t n = A.n;
   const int64_t CMAX = 1 << 20, CMIN = 4096;
   SpecArgs S;
-  S.G = 2048;
-  S.capS = n + 2 < 16384 ? n + 2 + A.K : 16384;
-  RC_CHECK(dev_ensure(c, c->g_tx, (size_t)S.G * sizeof(Slot) + (size_t)S.G * 4 + 256));
+  S.G = 1024;
+  // page pool: room for every point once plus one page per slot, capped at 64 Mi entries
+  int64_t pages = (3 * n) / PAGE_SIZE + 2 * S.G;
+  if (pages > 32768) pages = 32768;
+  S.n_pool_pages = (uint32_t)pages;
+  const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 4 + 256;
+  RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + 64));
   RC_CHECK(dev_ensure(c, c->g_spec, (size_t)CMAX * 12 + (size_t)n * 2 + 256));
-  RC_CHECK(dev_ensure(c, c->g_queue, (size_t)S.G * S.capS * 12 + 256));
+  RC_CHECK(dev_ensure(c, c->g_queue, (size_t)pages * PAGE_SIZE * 12 + 256));
   S.slots = dptr<Slot>(c->g_tx);
   S.free_ids = reinterpret_cast<uint32_t*>(S.slots + S.G);
+  S.ptabs = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(c->g_tx.p) + slot_bytes);
+  S.pool.free_pages = S.ptabs + (size_t)S.G * MAX_PAGES_PER_SLOT;
+  S.pool.stack_pages = dptr<int2>(c->g_queue);
+  S.pool.list_pages = reinterpret_cast<int32_t*>(S.pool.stack_pages + (size_t)pages * PAGE_SIZE);
   S.kind = dptr<uint32_t>(c->g_spec);
   S.mask = S.kind + CMAX;
   S.flag = S.mask + CMAX;
   A.doom = reinterpret_cast<uint8_t*>(S.flag + CMAX);
   A.hasslot = A.doom + n;
-  S.sstack = dptr<int2>(c->g_queue);
-  S.slist = reinterpret_cast<int32_t*>(S.sstack + (size_t)S.G * S.capS);
   S.sc = A.ctl + 8;
+  S.pool.n_free = &S.sc[7];
   S.A = A;
   CU_CHECK(c, cudaMemsetAsync(A.doom, 0, (size_t)n * 2, c->stream));
-  spec_init_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
-  KLAUNCH_CHECK(c);
+  {
+    const int64_t m = pages > S.G ? pages : S.G;
+    spec_init_kernel<<<(unsigned)ceil_div64(m, TPB), TPB, 0, c->stream>>>(S);
+    KLAUNCH_CHECK(c);
+  }
 
   int64_t F = 0, C = 16384, rounds = 0;
   unsigned long long head_tx = 64;
+  int64_t seq_growers = 0;
   uint32_t* d_ncand = reinterpret_cast<uint32_t*>(&S.sc[SC_NCAND]);
   while (F < n) {
     if (C > n - F) C = n - F;
@@ -512,7 +446,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     KLAUNCH_CHECK(c);
     spec_advance_kernel<<<1, 1, 0, c->stream>>>(S, F, C);
     KLAUNCH_CHECK(c);
-    launch_grow_seq(c, S.A, true, head_tx, 1ull << 40);
+    launch_grow_seq(c, S.A, true, head_tx, 1ull << 40, 0);
     KLAUNCH_CHECK(c);
     ++rounds;
     unsigned long long ctl[16];
@@ -520,9 +454,21 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     if (ctl[CTL_ERR])
       break;
     const int64_t committed = (int64_t)ctl[8 + 5];
-    const int64_t Fn = (int64_t)ctl[CTL_FRONTIER];
+    const bool head_live = ctl[8 + 6] != 0;
+    int64_t Fn = (int64_t)ctl[CTL_FRONTIER];
     if (Fn < F)
       return bseg_fail(c, BSEG_E_STATE, "speculative grower: frontier moved backwards");
+    if (Fn == F && !head_live) {
+      // the head is a depth-0 success without a slot (no slot / no pages left, or a plane too large for
+      // the page table): the head runner grows it in the flat region, alone
+      launch_grow_seq(c, S.A, true, 1, 1ull << 40, 1);
+      KLAUNCH_CHECK(c);
+      RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
+      if (ctl[CTL_ERR])
+        break;
+      Fn = (int64_t)ctl[CTL_FRONTIER];
+      ++seq_growers;
+    }
     F = Fn;
     // window: wide when the clean prefix is long, never below CMIN (speculation is cheap)
     if (committed >= C) C = C * 2 < CMAX ? C * 2 : CMAX;
@@ -536,5 +482,6 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       return bseg_fail(c, BSEG_E_STATE, "speculative grower: no progress");
   }
   c->tm.grow_rounds = rounds;
+  (void)seq_growers;
   return 0;
 }

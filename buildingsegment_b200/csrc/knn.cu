@@ -137,18 +137,37 @@ __device__ __forceinline__ uint32_t count_le(const V& v, uint32_t t)
   return __reduce_add_sync(FULL_MASK, c);
 }
 
-// k smallest by (d2, idx) among candidates with d2 <= hi; precondition count_le(hi) >= k, hi < 2^32-1
+// k smallest by (d2, idx) among candidates with d2 <= hi; precondition count_le(hi) >= k, hi < 2^32-1.
+// Finds t* = min{t : #{d2 <= t} >= k} by a bracketed search that alternates an interpolation probe
+// (#{d2 <= t} grows about linearly in t on a surface: area ~ r^2 = t) with a bisection probe; a probe
+// that lands between the k-th and (k+1)-th distance ends the search at once.
 template <class V>
 __device__ Sel select_k(const V& v, uint32_t k, uint32_t hi, uint32_t idx_hi)
 {
   uint32_t lo = 0;
+  uint32_t flo = 0;            // #{d2 <= lo - 1}  (< k)
+  uint32_t fhi = 0xffffffffu;  // #{d2 <= hi}, unknown until probed
+  bool interp = false;
   while (lo < hi) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    uint32_t c = count_le(v, mid);
+    uint32_t mid;
+    if (interp && fhi != 0xffffffffu && fhi > flo) {
+      const uint64_t span = (uint64_t)(hi - lo);
+      mid = lo + (uint32_t)((span * (uint64_t)(k - flo)) / (uint64_t)(fhi - flo));
+      if (mid >= hi) mid = hi - 1;
+    } else {
+      mid = lo + ((hi - lo) >> 1);
+    }
+    interp = !interp;
+    const uint32_t c = count_le(v, mid);
     if (c == k)
       return Sel{mid + 1, 0, 0};
-    if (c > k) hi = mid;
-    else lo = mid + 1;
+    if (c > k) {
+      hi = mid;
+      fhi = c;
+    } else {
+      lo = mid + 1;
+      flo = c;
+    }
   }
   const uint32_t t = lo;
   uint32_t less = 0, ties = 0;
