@@ -317,7 +317,7 @@ def run_ours(args):
                                    f"(K=15, r=100 mm, max_nn=50, 300 mm, 0.88, 400)" if world == 1 else
                                    f"C5-style city tile, one 500 m block-slab of {n} points per GPU, reference defaults",
                        "points_per_gpu": n, "l2": "inputs larger than L2 (cloud + neighbour rows >> 126 MB)",
-                       "grow_engine": "speculative (grow_mode 0)", "planes": int(npl)},
+                       "grow_engine": "sweeper + speculative growers (grow_mode 0)", "planes": int(npl)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -325,7 +325,11 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "grow": {"steps": int(last_t["grow_steps"]), "rounds": int(last_t["grow_rounds"]),
-                     "n_unresolved_knn": int(last_t["n_unresolved"]), "n_big_items": int(last_t["n_big_cells"])},
+                     "n_unresolved_knn": int(last_t["n_unresolved"]), "n_big_items": int(last_t["n_big_cells"]),
+                     "wasted_steps": int(last_t["grow_wasted_steps"]), "sweep_iters": int(last_t["grow_sweep_iters"]),
+                     "tiny_tx": int(last_t["grow_tiny_tx"]), "seq_fallbacks": int(last_t["grow_seq_fallbacks"]),
+                     "head_steps": int(last_t["grow_head_steps"]), "head_ms": round(last_t["grow_head_ns"] / 1e6, 3),
+                     "sweep_ms": round(last_t["grow_sweep_ns"] / 1e6, 3)},
         }
         print(json.dumps(out))
     ctx.close()

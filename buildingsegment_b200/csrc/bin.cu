@@ -236,7 +236,7 @@ int stage_bin(bseg_ctx* c, const bseg_params* p)
   RC_CHECK(dev_ensure(c, c->pts, (size_t)n * 16));
   RC_CHECK(dev_ensure(c, c->inv, (size_t)n * 4));
   RC_CHECK(dev_ensure(c, c->flags, (size_t)(n + 4) * 4));
-  RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
+  RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
 
   uint32_t ext[3];
   int maxbits = 0;

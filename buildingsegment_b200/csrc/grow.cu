@@ -31,6 +31,7 @@
 // state[s] = -1 free, else ORIGINAL index of the seed whose transaction marked it; plane ids are
 // assigned at the end: id(owner) = 1 + #committed plane seeds below owner (cur_planeId at that time).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "grow.cuh"
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
       const uint32_t seed_s = __shfl_sync(FULL_MASK, s_l, b);
       if (__ldcg(A.state + seed_s) != -1)
         continue;  // taken by a transaction of this very batch
-      if (NOTIFY && A.hasslot[seed_i]) {  // a speculative grower owns this seed: leave it to the window
+      if (NOTIFY && A.slotof[seed_i] >= 0) {  // a speculative grower owns this seed: leave it to the window
         frontier = seed_i;
         stop = true;
         break;
@@ -243,7 +244,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   RC_CHECK(dev_ensure(c, c->g_planes, (size_t)planes_cap * sizeof(PlaneRec)));
   RC_CHECK(dev_ensure(c, c->g_label, (size_t)n * 4));
   RC_CHECK(dev_ensure(c, c->g_pidx, (size_t)n * 4));
-  RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
+  RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
   c->pool_cap = pool_cap;
 
   GrowArgs A;
@@ -263,14 +264,20 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.stack = dptr<int2>(c->g_stack);
   A.planes = dptr<PlaneRec>(c->g_planes);
   A.planes_cap = planes_cap;
-  A.ctl = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 40;
+  A.ctl = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 64;  // [64, 128): grower control block
   A.doom = nullptr;
-  A.hasslot = nullptr;
+  A.slotof = nullptr;
+  A.stop_flag = nullptr;
+  A.frontier = 0;
+  {
+    const char* gf = getenv("BSEG_GROW_FLAGS");  // tuning switches of the step engine (grow.cuh GF_*)
+    A.flags = gf ? atoi(gf) : (GF_ROW_L2);
+  }
 
   STAGE_BEGIN(c, EV_GROW);
   CU_CHECK(c, cudaMemsetAsync(A.state, 0xff, (size_t)n * 4, c->stream));
   CU_CHECK(c, cudaMemsetAsync(A.res, 0xff, (size_t)n * 4, c->stream));
-  CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 16 * sizeof(unsigned long long), c->stream));
+  CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 64 * sizeof(unsigned long long), c->stream));
   int64_t rounds = 0;
   if (p->grow_mode == 1) {
     launch_grow_seq(c, A, false, ~0ull, ~0ull, 1);

@@ -25,8 +25,33 @@ struct GrowArgs {
   // control block: [0] next seed (frontier), [1] pool used, [2] planes, [3] steps, [4] error, [5] transactions
   unsigned long long* ctl;
   // speculative engine only (NULL otherwise): per ORIGINAL index
-  uint8_t* doom;     // 1 = the transaction seeded here overlapped a lower one, or lost its seed
-  uint8_t* hasslot;  // 1 = a grower slot is attached to this seed
+  uint8_t* doom;     // 1 = a lower transaction took a point this one holds, or its seed
+  int32_t* slotof;   // grower slot attached to this seed, -1 = none
+  // speculative slices: set by the head slot when it finishes, polled by the others
+  unsigned long long* stop_flag;
+  int64_t frontier;  // first unresolved seed at slice start (everything below is committed)
+  int flags;         // tuning switches (BSEG_GROW_FLAGS): see GF_*
+};
+enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8 };
+
+// ---- "assumed taken" record of a speculative transaction ----------------------------------------------
+// A point that is free in the committed state and passes the geometric tests, but is reserved by a LOWER
+// in-flight transaction, is treated as taken (the lower one gets it when it commits).  The transaction
+// remembers WHOM it relied on; if one of them is released without committing (doomed, rolled back), the
+// dependants are doomed too (grow_spec.cu: cascade), so a slot that reaches the sweeper clean has only
+// ever relied on planes that were committed with those points.
+constexpr int ASSUME_MAX = 16;
+struct AssumeSet {
+  int32_t id[ASSUME_MAX];
+  int32_t n;      // entries used
+  int32_t over;   // more than ASSUME_MAX distinct transactions: depends on "everyone lower"
+  __device__ __forceinline__ void add(int32_t a)
+  {
+    for (int k = 0; k < n; ++k)
+      if (id[k] == a) return;
+    if (n < ASSUME_MAX) id[n++] = a;
+    else over = 1;
+  }
 };
 
 enum { CTL_FRONTIER = 0, CTL_POOL = 1, CTL_PLANES = 2, CTL_STEPS = 3, CTL_ERR = 4, CTL_TX = 5 };
@@ -103,6 +128,10 @@ __device__ __forceinline__ bool dedupe(bool ok, int32_t id)
 __device__ __forceinline__ void prefetch_l2(const void* p)
 {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 // ---- list / frame storage ---------------------------------------------------------------------------
@@ -202,30 +231,41 @@ __device__ __forceinline__ void tx_begin(TxState& t, const GrowArgs& A, uint32_t
 // Runs Broad() calls of transaction `seed_i` until it ends or `budget` calls were made.
 //   MODE_SEQ         committed state only; accepted points are marked in `state` at once
 //   MODE_SEQ_NOTIFY  same, and in-flight speculative transactions touching them are doomed
-//   MODE_SPEC        marks are reservations (atomicMin on res); lower reservations doom this one
-// Loads of step t+1 (neighbour row, then the neighbours' state / position / normal) are issued before the
-// fp64 model update of step t, so most of their latency hides behind it.
+//   MODE_SPEC        marks are reservations (atomicMin on res); a lower reservation = "assume taken"
+// Latency chain of one step (the grower is latency-bound): row of the next node (L1: every neighbour's
+// row is prefetched when the neighbour is gathered) -> gather of its neighbours' state / reservation /
+// position / normal (L2) -> tests.  The reservation atomics are NOT on the chain in MODE_SPEC: the
+// decision uses the reservation value that was gathered, the atomic's result is inspected one step later
+// and only matters when a lower transaction slipped in between (then this one gives up and is re-run).
 template <int MODE, class Store>
 __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, unsigned long long budget,
-                            bool leave_growers, int lane, unsigned long long& steps_out)
+                            bool leave_growers, int lane, unsigned long long& steps_out, AssumeSet* as = nullptr)
 {
   const int K = A.K;
   const uint32_t me = (uint32_t)seed_i;
+  const bool row_l1 = (A.flags & GF_ROW_L1) != 0, row_l2 = (A.flags & GF_ROW_L2) != 0;
+  const bool early_pop = (A.flags & GF_EARLY_POP) != 0, state_nc = (A.flags & GF_STATE_NC) != 0;
   unsigned long long steps = 0;
   TxOutcome out = TX_RUNNING;
   // neighbour `lane` of the node: id, and its state / reservation / position / normal
   int32_t id = -1, stt = 0;
   uint32_t rs = RES_FREE;
+  bool mine = false;  // accepted by this transaction in the previous step (its reservation may still be in flight)
   int4 p = make_int4(0, 0, 0, 0);
   double n0 = 0, n1 = 0, n2 = 0;
   if (lane >= 1 && lane < K)
     id = __ldg(A.nbr + (int64_t)t.node * K + lane);
   if (id >= 0) {
-    stt = __ldcg(A.state + id);
+    // inside a speculative slice nobody writes `state` (the sweeper is a different kernel): L1 may keep it
+    stt = (MODE == MODE_SPEC && state_nc) ? __ldg(A.state + id) : __ldcg(A.state + id);
     if (MODE == MODE_SPEC) rs = __ldcg(A.res + id);
     p = __ldg(A.pts + id);
     const double* nr = A.nrm + 3 * (int64_t)id;
     n0 = __ldg(nr); n1 = __ldg(nr + 1); n2 = __ldg(nr + 2);
+    if (row_l1) {
+      prefetch_l1(A.nbr + (int64_t)id * K);
+      prefetch_l1(A.nbr + (int64_t)id * K + (K - 1));
+    }
   }
   while (steps < budget) {
     if (!st.reserve(t.len + 2 * K, lane)) {  // before anything is marked
@@ -233,7 +273,11 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
       break;
     }
     ++steps;
-    bool ok = id >= 0 && stt == -1 && (MODE != MODE_SPEC || rs != me) &&
+    // the node visited if nothing is accepted now: fetch it early, it is two dependent loads away
+    int32_t pop_id = -1;
+    const int64_t pop_at = t.top_cur;
+    if (early_pop && t.have_top && t.top_cur < t.top_end) pop_id = st.get(t.top_cur);
+    bool ok = id >= 0 && stt == -1 && (MODE != MODE_SPEC || (rs != me && !mine)) &&
               geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
     ok = dedupe(ok, id);
     if (leave_growers && t.depth0) {
@@ -243,34 +287,40 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
         break;
       }
     }
-    bool lost = false;
+    int32_t relied = -1;  // lower in-flight transaction whose reservation made this lane decline
+    uint32_t old = RES_FREE;
+    bool fired = false;
     if (ok) {
       if (MODE == MODE_SPEC) {
-        const uint32_t old = atomicMin(A.res + id, me);
-        if (old < me) lost = true;
-        else {
-          if (old != RES_FREE) A.doom[old] = 1;
-          if (p.w > (int32_t)me) A.doom[p.w] = 1;
+        if (rs < me) {  // reserved by a lower transaction: assume taken
+          ok = false;
+          relied = (int32_t)rs;
+        } else {
+          old = atomicMin(A.res + id, me);  // result looked at after the next gather is on its way
+          fired = true;
         }
       } else {
         A.state[id] = (int32_t)seed_i;
         if (MODE == MODE_SEQ_NOTIFY) {
-          const uint32_t old = atomicMin(A.res + id, me);
-          if (old != RES_FREE && old > me) A.doom[old] = 1;
+          const uint32_t o = atomicMin(A.res + id, me);
+          if (o != RES_FREE && o > me) A.doom[o] = 1;
           if (p.w > (int32_t)me) A.doom[p.w] = 1;
         }
+      }
+    }
+    if (MODE == MODE_SPEC) {
+      uint32_t rel = __ballot_sync(FULL_MASK, relied >= 0);
+      while (rel) {  // every lane keeps the same record (the slot stores lane 0's copy)
+        const int b = __ffs(rel) - 1;
+        rel &= rel - 1;
+        as->add(__shfl_sync(FULL_MASK, relied, b));
       }
     }
     const uint32_t acc = __ballot_sync(FULL_MASK, ok);
     const int cnt = __popc(acc);
     if (ok)
-      st.put(t.len + __popc(acc & lanemask_lt()), id);  // recorded even when lost, so the release covers it
+      st.put(t.len + __popc(acc & lanemask_lt()), id);
     __syncwarp();
-    if (MODE == MODE_SPEC && __any_sync(FULL_MASK, lost)) {
-      t.len += cnt;
-      out = TX_DOOMED;
-      break;
-    }
     if (t.depth0 && cnt < K - 1) {
       t.len += cnt;
       out = TX_FAILED;  // :238-239
@@ -293,7 +343,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
       next = (uint32_t)__shfl_sync(FULL_MASK, id, __ffs(acc) - 1);
       have_next = true;
       // every accepted point gets its own Broad() later: pull its row towards L2 now
-      if (ok) prefetch_l2(A.nbr + (int64_t)id * K);
+      if (row_l2 && ok) prefetch_l2(A.nbr + (int64_t)id * K);
     } else {
       while (t.have_top && t.top_cur == t.top_end) {
         if (t.sp > 0) {
@@ -307,7 +357,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
         }
       }
       if (t.have_top) {
-        next = (uint32_t)st.get(t.top_cur);
+        next = (uint32_t)((pop_id >= 0 && t.top_cur == pop_at) ? pop_id : st.get(t.top_cur));
         ++t.top_cur;
         have_next = true;
       }
@@ -319,25 +369,53 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     model_accumulate(t.m, acc, p, n0, n1, n2);
     int32_t nstt = 0;
     uint32_t nrs = RES_FREE;
+    bool nmine = false;
     int4 np = make_int4(0, 0, 0, 0);
     double m0 = 0, m1 = 0, m2 = 0;
     if (nid >= 0) {
-      nstt = __ldcg(A.state + nid);
+      nstt = (MODE == MODE_SPEC && state_nc) ? __ldg(A.state + nid) : __ldcg(A.state + nid);
       if (MODE == MODE_SPEC) nrs = __ldcg(A.res + nid);
       np = __ldg(A.pts + nid);
       const double* nr = A.nrm + 3 * (int64_t)nid;
       m0 = __ldg(nr); m1 = __ldg(nr + 1); m2 = __ldg(nr + 2);
+      if (row_l1) {
+        prefetch_l1(A.nbr + (int64_t)nid * K);
+        prefetch_l1(A.nbr + (int64_t)nid * K + (K - 1));
+      }
+    }
+    if (MODE == MODE_SPEC) {  // points accepted a moment ago are ours whatever the gathered reservation says
+      uint32_t a = acc;
+      while (a) {
+        const int b = __ffs(a) - 1;
+        a &= a - 1;
+        nmine |= nid == __shfl_sync(FULL_MASK, id, b);
+      }
     }
     model_update(t.m, t.len);
+    if (MODE == MODE_SPEC) {
+      bool race = false;
+      if (fired) {
+        if (old < me) race = true;                      // a lower transaction reserved it in between
+        else if (old != RES_FREE) A.doom[old] = 1;      // stolen from a higher transaction: it is void
+        if (p.w > (int32_t)me) A.doom[p.w] = 1;         // the transaction seeded at this point lost its seed
+      }
+      if (__any_sync(FULL_MASK, race)) {
+        out = TX_DOOMED;
+        break;
+      }
+    }
     if (!have_next) {
       out = TX_FINISHED;
       break;
     }
     t.node = next;
-    id = nid; stt = nstt; rs = nrs; p = np; n0 = m0; n1 = m1; n2 = m2;
-    if (MODE == MODE_SPEC && (steps & 15) == 0 && ((volatile uint8_t*)A.doom)[seed_i]) {
-      out = TX_DOOMED;
-      break;
+    id = nid; stt = nstt; rs = nrs; mine = nmine; p = np; n0 = m0; n1 = m1; n2 = m2;
+    if (MODE == MODE_SPEC && (steps & 7) == 0) {
+      if (((volatile uint8_t*)A.doom)[seed_i]) {
+        out = TX_DOOMED;
+        break;
+      }
+      if (*(volatile unsigned long long*)A.stop_flag) break;  // the head finished: let the sweeper commit
     }
   }
   steps_out += steps;

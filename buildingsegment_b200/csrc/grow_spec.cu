@@ -1,49 +1,79 @@
-// grow_spec.cu -- the speculative, order-faithful plane grower (grow_mode 0).
+// grow_spec.cu -- the parallel, order-faithful plane grower (grow_mode 0): a sequential SWEEPER that is
+// the only writer of the committed state, fed by growers that run AHEAD of it speculatively.
 //
-// The reference (my_function.cpp:180-258) is a sequential greedy algorithm: seeds in index order,
-// each transaction TX(i) = "if point i is still free, run Broad(i,0) and its DFS, then commit or
-// roll back".  A transaction's decisions depend on other transactions only through the free/taken
-// state of the points it ACCEPTS (a geometric rejection does not look at the state, and a taken
-// point stays taken), so TX(i) computed against a snapshot equals its sequential outcome iff no
-// lower-index transaction that was still in flight accepted one of the same points or TX(i)'s seed.
-//
-// Engine (rounds over a window [F, F+C) of original indices, F = first unresolved seed):
-//   depth0   one thread per window index: skip taken seeds; run the depth-0 tests; tiny
-//            transactions (depth-0 failure: <= K-2 orphan marks) reserve their accepted points with
-//            atomicMin(res[pt], i); depth-0 successes become grower candidates
-//   assign   the LOWEST candidates get the free grower slots (scan over the window)
-//   grow     one warp per slot runs Broad steps for a time slice, reserving every accepted point;
-//            slots persist across rounds (a plane may need many slices)
-//   overlap detection is symmetric: whoever comes second at a point sees the other's reservation
-//            (atomicMin result): the lower index keeps the point, the higher one is doomed
-//   validate first_bad = lowest window index whose transaction is doomed, blocked or unfinished
-//   commit   everything below first_bad commits in parallel (disjoint point sets by construction);
-//            everything at/after it releases its reservations, except slots still running clean
-//   head     the sequential engine (grow.cu) then runs transactions from F in order -- this clears
-//            the doomed head and gives at least sequential-GPU speed on dependent chains
-// Only a PREFIX ever commits, and a waiting transaction is doomed as soon as any lower one touches
-// its points, so the final state is exactly the sequential one.  Plane ids are ordinal in seed order
-// and are assigned after the fact (grow.cu finalize).
+// The reference (my_function.cpp:180-258) is a sequential greedy algorithm: seeds in index order, each
+// transaction TX(i) = "if point i is still free, run Broad(i,0) and its DFS, then commit or roll back".
+// Two facts make it parallel without changing a single label:
+//   (1) Whether a neighbour passes the depth-0 geometric tests depends only on the seed's own normal and
+//       position (my_function.cpp:189-190,227-230), never on the state.  gmask[s] (one bit per neighbour
+//       column, duplicates removed) is therefore computed for ALL points up front, and a seed whose
+//       transaction fails at depth 0 (:238-239, the overwhelming majority: "tiny" transactions that only
+//       leave orphan marks) costs the sweeper one state gather.  The sweeper is ONE thread block that walks
+//       the seeds in index order, 1024 at a time: every thread evaluates its seed against the committed
+//       state, a shared-memory hash table finds the seeds that a lower seed of the same batch is about to
+//       mark, and the conflict-free prefix of the batch commits in parallel (atomicMin keeps the lower owner
+//       where two tiny transactions want the same point).
+//   (2) A transaction's decisions depend on other transactions only through the free/taken state of the
+//       points it ACCEPTS (a geometric rejection does not look at the state, a taken point stays taken).
+//       Depth-0 successes ("growers") therefore run ahead of the sweeper in slots, one warp each, against
+//       the committed state, reserving every accepted point with atomicMin(res[pt], seed index):
+//         - the point is reserved by a LOWER in-flight grower: treat it as taken and remember whom we
+//           relied on (AssumeSet);
+//         - it is reserved by a HIGHER one: take it, the higher one is doomed;
+//         - the sweeper marks a reserved point for a lower tiny transaction: the holder is doomed.
+//       A doomed / rolled-back grower releases its reservations and dooms whoever relied on it (cascade).
+//       When the sweeper reaches a seed that is a grower at its turn, a finished, un-doomed slot holds
+//       exactly the sequential result (every lower transaction has been committed by then, and every point
+//       it saw as taken is taken); it is committed (or rolled back, :203-209) in place.  Otherwise the
+//       sweeper stops, the seed gets a slot as the lowest candidate and -- with nothing lower in flight --
+//       runs clean: progress is guaranteed.
+// Round = release doomed slots -> scout (lowest candidates of the window take the free slots) -> one slice
+// of Broad steps for every running slot (ends when the head slot finishes) -> sweep.  Plane ids are ordinal
+// in seed order and are assigned after the fact (grow.cu finalize).
 #include "grow.cuh"
 
 namespace {
 
 constexpr int TPB = 256;
-constexpr int GW = 4;  // warps per block in slot kernels
+constexpr int GW = 4;          // warps per block in slot kernels
+constexpr int SWEEP_T = 1024;  // seeds per sweeper batch == threads of the sweeper block
+constexpr int HT = 16384;      // sweeper hash table slots (keys + vals = 128 KB of shared memory)
 
-enum { KIND_NONE = 0, KIND_SKIP = 1, KIND_TINY = 2, KIND_TINY_BAD = 3, KIND_CAND = 4, KIND_BLOCKED = 5, KIND_SLOT = 8 };
-enum { ST_FREE = 0, ST_NEW = 1, ST_RUNNING = 2, ST_FINISHED = 3, ST_DOOMED = 4 };
+enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3 };
 // spec control block (A.ctl + 8)
-enum { SC_FIRST_BAD = 0, SC_NFREE = 1, SC_TX_COMMIT = 2, SC_NCAND = 3, SC_SLOT_STEPS = 4 };
+enum {
+  SC_NFREE = 0,       // free slots
+  SC_NCAND = 1,       // candidates of the window (scan total)
+  SC_STOP = 2,        // head finished: slices end
+  SC_HEAD_SLOT = 3,   // slot of the seed at the frontier + 1 (0 = none)
+  SC_WASTED = 4,      // Broad steps of released slots
+  SC_SWEEP_ITERS = 5,
+  SC_TINY = 6,        // tiny transactions committed
+  SC_POOLFREE = 7,    // free pages
+  SC_NREL = 8,        // released seeds of this round
+  SC_STUCK = 9,       // sweeper stopped at a grower that has no slot
+  SC_NASSIGN = 10,    // slots handed out by this round's scout
+  SC_HEAD_STEPS = 11, // Broad steps of the head slot (the critical path) ...
+  SC_HEAD_NS = 12,    // ... and the time they took (globaltimer)
+  SC_SWEEP_NS = 13,   // time inside the sweeper
+};
+
+__device__ __forceinline__ unsigned long long gtimer()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct Slot {
   int32_t seed_i;
   uint32_t seed_s;
   int32_t status;
-  int32_t failed;    // depth-0 failure inside a slot: commits as orphan marks, no plane
+  int32_t started;   // 0 = tx_begin still to be done
   int32_t n_pages;   // pages of the pool this slot owns
   int32_t pad;
   unsigned long long steps;
+  AssumeSet as;
   TxState t;
 };
 
@@ -54,10 +84,11 @@ struct SpecArgs {
   PagePool pool;
   uint32_t* ptabs;  // [G][MAX_PAGES_PER_SLOT]
   uint32_t n_pool_pages;
-  uint32_t* kind;   // [C] window-relative
-  uint32_t* mask;   // [C]
+  const uint32_t* gmask;  // [n] ORIGINAL index space (the sweeper and the scout walk seeds in index order)
   uint32_t* flag;   // [C] candidate flags -> exclusive scan
   uint32_t* free_ids;
+  int32_t* released;  // seeds released this round
+  uint8_t* gone;      // [n] original index space: released this round
   unsigned long long* sc;
 };
 
@@ -70,56 +101,24 @@ __device__ __forceinline__ PagedStore slot_store(const SpecArgs& S, int g)
   return st;
 }
 
-__global__ void __launch_bounds__(TPB) spec_prepare_kernel(SpecArgs S, int64_t F, int64_t C)
+// ---- depth-0 geometry of every point (state-independent) -------------------------------------------------
+// bit j of gmask[s]: neighbour column j of s is a valid point, passes the tests of Broad(s, 0) with the
+// seed's own model (my_function.cpp:189-190,227-230) and is the first such occurrence of that point in the
+// row (a repeated id finds planeIdx already set, :226).
+__global__ void __launch_bounds__(TPB) gmask_kernel(GrowArgs A, uint32_t* __restrict__ gmask)
 {
-  int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
-  if (t >= C)
+  const int64_t s = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (s >= A.n)
     return;
-  S.kind[t] = KIND_NONE;
-  S.flag[t] = 0;
-  if (!S.A.hasslot[F + t])
-    S.A.doom[F + t] = 0;
-}
-
-__global__ void __launch_bounds__(TPB) spec_mark_slots_kernel(SpecArgs S, int64_t F, int64_t C)
-{
-  int g = blockIdx.x * TPB + threadIdx.x;
-  if (g >= S.G)
-    return;
-  const Slot& sl = S.slots[g];
-  if (sl.status == ST_FREE)
-    return;
-  int64_t t = (int64_t)sl.seed_i - F;
-  if (t >= 0 && t < C)
-    S.kind[t] = KIND_SLOT + (uint32_t)g;
-}
-
-// one thread per window index: Broad(i, 0) against the committed state (my_function.cpp:221-239)
-__global__ void __launch_bounds__(TPB) spec_depth0_kernel(SpecArgs S, int64_t F, int64_t C)
-{
-  const GrowArgs& A = S.A;
-  int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
-  if (t >= C || S.kind[t] != KIND_NONE)
-    return;
-  const int64_t i = F + t;
-  const uint32_t s = __ldg(A.inv + i);
-  if (__ldcg(A.state + s) != -1) {
-    S.kind[t] = KIND_SKIP;
-    return;
-  }
-  if (__ldcg(A.res + s) < (uint32_t)i) {  // a lower in-flight transaction accepted this seed
-    S.kind[t] = KIND_BLOCKED;
-    return;
-  }
   Model m;
-  model_init(m, __ldg(A.pts + s), A.nrm + 3 * (int64_t)s);
+  const int4 self = __ldg(A.pts + s);
+  model_init(m, self, A.nrm + 3 * s);
   const int K = A.K;
-  const int32_t* row = A.nbr + (int64_t)s * K;
+  const int32_t* row = A.nbr + s * K;
   uint32_t mask = 0;
-  int cnt = 0;
   for (int j = 1; j < K; ++j) {
     const int32_t id = __ldg(row + j);
-    if (id < 0 || __ldcg(A.state + id) != -1)
+    if (id < 0)
       continue;
     bool dup = false;
     for (int j2 = 1; j2 < j; ++j2)
@@ -128,64 +127,172 @@ __global__ void __launch_bounds__(TPB) spec_depth0_kernel(SpecArgs S, int64_t F,
       continue;
     const int4 p = __ldg(A.pts + id);
     const double* nr = A.nrm + 3 * (int64_t)id;
-    if (geo_test(m, p, nr[0], nr[1], nr[2], A.th_thick, A.th_dot)) {
-      mask |= 1u << j;
-      ++cnt;
-    }
+    if (geo_test(m, p, __ldg(nr), __ldg(nr + 1), __ldg(nr + 2), A.th_thick, A.th_dot)) mask |= 1u << j;
   }
-  if (cnt == K - 1) {
-    S.kind[t] = KIND_CAND;
-    S.flag[t] = 1;
+  gmask[self.w] = mask;
+}
+
+// ---- slot bookkeeping shared by the release kernel and the sweeper ----------------------------------------
+// give the slot's pages and the slot itself back (one thread)
+__device__ __forceinline__ void slot_free(const SpecArgs& S, int g)
+{
+  Slot& sl = S.slots[g];
+  const PagedStore st = slot_store(S, g);
+  const int np = sl.n_pages;
+  if (np > 0) {
+    const unsigned long long pos = atomicAdd(S.pool.n_free, (unsigned long long)np);
+    for (int k = 0; k < np; ++k) S.pool.free_pages[pos + k] = st.ptab[k];
+  }
+  sl.n_pages = 0;
+  sl.status = ST_FREE;
+  S.A.slotof[sl.seed_i] = -1;
+  const unsigned long long pos = atomicAdd(&S.sc[SC_NFREE], 1ull);
+  S.free_ids[pos] = (uint32_t)g;
+}
+
+__device__ __forceinline__ bool relies_on(const Slot& d, int32_t a)
+{
+  if (d.as.over)
+    return true;
+  for (int k = 0; k < d.as.n; ++k)
+    if (d.as.id[k] == a) return true;
+  return false;
+}
+
+// ---- K0: release doomed / dead slots ahead of the sweeper, then doom whoever relied on them -----------------
+// A doomed plane can hold 10^5 reservations: RCH blocks per slot walk its list.
+constexpr int RCH = 16;
+__global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
+{
+  const GrowArgs& A = S.A;
+  const int g = blockIdx.y;
+  const Slot& sl = S.slots[g];
+  if (sl.status == ST_FREE)
     return;
+  const int32_t i = sl.seed_i;
+  if (!(sl.status == ST_DEAD || A.doom[i]))
+    return;
+  const PagedStore st = slot_store(S, g);
+  const int64_t len = sl.started ? sl.t.len : 0;
+  for (int64_t e = 1 + (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB)
+    atomicCAS(A.res + st.get(e), (uint32_t)i, RES_FREE);
+}
+
+__global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
+{
+  const GrowArgs& A = S.A;
+  const int g = blockIdx.x * TPB + threadIdx.x;
+  if (g >= S.G)
+    return;
+  Slot& sl = S.slots[g];
+  if (sl.status == ST_FREE)
+    return;
+  const int32_t i = sl.seed_i;
+  if (!(sl.status == ST_DEAD || A.doom[i]))
+    return;
+  atomicAdd(&S.sc[SC_WASTED], sl.steps);
+  S.released[atomicAdd(&S.sc[SC_NREL], 1ull)] = i;
+  S.gone[i] = 1;
+  slot_free(S, g);
+}
+
+__global__ void __launch_bounds__(TPB) spec_cascade_kernel(SpecArgs S)
+{
+  const int g = blockIdx.x * TPB + threadIdx.x;
+  if (g >= S.G || S.sc[SC_NREL] == 0)
+    return;
+  const Slot& d = S.slots[g];
+  if (d.status == ST_FREE)
+    return;
+  bool hit = false;
+  if (d.as.over) {
+    const int nrel = (int)S.sc[SC_NREL];
+    for (int k = 0; k < nrel && !hit; ++k) hit = S.released[k] < d.seed_i;
+  } else {
+    for (int k = 0; k < d.as.n; ++k) hit |= S.gone[d.as.id[k]] != 0;
   }
-  bool lost = false;
-  for (int j = 1; j < K; ++j)
-    if ((mask >> j) & 1u) {
-      const int32_t id = __ldg(row + j);
-      const uint32_t old = atomicMin(A.res + id, (uint32_t)i);
-      if (old < (uint32_t)i) lost = true;
-      else {
-        if (old != RES_FREE && old != (uint32_t)i) A.doom[old] = 1;
-        const int32_t o = __ldg(A.pts + id).w;
-        if (o > (int32_t)i) A.doom[o] = 1;
+  if (hit) S.A.doom[d.seed_i] = 1;
+}
+
+__global__ void __launch_bounds__(TPB) spec_cascade_done_kernel(SpecArgs S)
+{
+  const int k = blockIdx.x * TPB + threadIdx.x;
+  const int nrel = (int)S.sc[SC_NREL];
+  if (k < nrel) S.gone[S.released[k]] = 0;
+}
+
+// ---- K1: scout -- candidates of the window [F, F+C) ----------------------------------------------------------
+// candidate: free seed without a slot whose K-1 neighbours all pass depth 0 and are all free and not
+// reserved by a lower in-flight grower (relying on one would make it a tiny transaction: the sweeper's job)
+__global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, int64_t C)
+{
+  const GrowArgs& A = S.A;
+  const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (t == 0) {
+    S.sc[SC_STOP] = 0;
+    S.sc[SC_NREL] = 0;
+    S.sc[SC_NCAND] = 0;
+    S.sc[SC_NASSIGN] = 0;
+  }
+  if (t >= C)
+    return;
+  const int64_t i = F + t;
+  uint32_t cand = 0;
+  if (__ldcg(A.slotof + i) < 0) {
+    const uint32_t s = __ldg(A.inv + i);
+    const int K = A.K;
+    if (__ldcg(A.state + s) == -1 && __ldcg(A.res + s) >= (uint32_t)i && __popc(__ldg(S.gmask + i)) == K - 1) {
+      const int32_t* row = A.nbr + (int64_t)s * K;
+      cand = 1;
+      for (int j = 1; j < K; ++j) {
+        const int32_t id = __ldg(row + j);
+        if (__ldcg(A.state + id) != -1 || __ldcg(A.res + id) < (uint32_t)i) {
+          cand = 0;
+          break;
+        }
       }
     }
-  S.mask[t] = mask;
-  S.kind[t] = lost ? KIND_TINY_BAD : KIND_TINY;
+  }
+  S.flag[t] = cand;
 }
 
 // flag[] holds the exclusive scan of the candidate flags; the lowest candidates take the free slots
 __global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t F, int64_t C)
 {
-  int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
-  if (t >= C || S.kind[t] != KIND_CAND)
+  const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (t >= C)
     return;
   const uint32_t r = S.flag[t];
+  const uint32_t next = t + 1 < C ? S.flag[t + 1] : (uint32_t)S.sc[SC_NCAND];
+  if (next == r)
+    return;  // not a candidate
+  // the last free slot is kept for the seed at the frontier: the head can always grow
   const uint32_t nfree = (uint32_t)S.sc[SC_NFREE];
-  if (r >= nfree) {
-    S.kind[t] = KIND_BLOCKED;
+  if (t == 0 ? r >= nfree : r + 1 >= nfree)
     return;
-  }
+  atomicAdd(&S.sc[SC_NASSIGN], 1ull);
   const uint32_t g = S.free_ids[nfree - 1 - r];
   Slot& sl = S.slots[g];
   sl.seed_i = (int32_t)(F + t);
   sl.seed_s = __ldg(S.A.inv + F + t);
-  sl.status = ST_NEW;
+  sl.status = ST_RUNNING;
+  sl.started = 0;
   sl.steps = 0;
-  sl.t.len = 0;
-  sl.failed = 0;
   sl.n_pages = 0;
-  S.A.hasslot[F + t] = 1;
-  S.kind[t] = KIND_SLOT + g;
+  sl.as.n = 0;
+  sl.as.over = 0;
+  S.A.slotof[F + t] = (int32_t)g;
+  S.A.doom[F + t] = 0;
 }
 
-__global__ void spec_pop_free_kernel(SpecArgs S)
+__global__ void spec_pop_free_kernel(SpecArgs S, int64_t F)
 {
-  const unsigned long long nc = S.sc[SC_NCAND] & 0xffffffffull, nf = S.sc[SC_NFREE];
-  S.sc[SC_NFREE] = nf - (nc < nf ? nc : nf);
+  S.sc[SC_NFREE] -= S.sc[SC_NASSIGN];
+  const int32_t g = F < S.A.n ? S.A.slotof[F] : -1;
+  S.sc[SC_HEAD_SLOT] = (unsigned long long)(g + 1);
 }
 
-// one warp per slot: a time slice of Broad steps with reservations
+// ---- K2: one warp per slot, a time slice of Broad steps with reservations ----------------------------------
 __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned long long budget)
 {
   const GrowArgs& A = S.A;
@@ -194,21 +301,21 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   if (g >= S.G)
     return;
   Slot& sl = S.slots[g];
-  const int status = sl.status;
-  if (status != ST_NEW && status != ST_RUNNING)
+  if (sl.status != ST_RUNNING)
     return;
   const int64_t seed_i = sl.seed_i;
-  if (A.doom[seed_i]) {
+  if (((volatile uint8_t*)A.doom)[seed_i]) {
     __syncwarp();
-    if (lane == 0) sl.status = ST_DOOMED;  // len stays 0 for a slot that never started
+    if (lane == 0) sl.status = ST_DEAD;
     return;
   }
   PagedStore st = slot_store(S, g);
   TxState t;
-  if (status == ST_NEW) {
+  AssumeSet as = sl.as;
+  if (!sl.started) {
     tx_begin(t, A, sl.seed_s);
     if (!st.reserve(1, lane)) {
-      if (lane == 0) sl.status = ST_DOOMED;
+      if (lane == 0) sl.status = ST_DEAD;
       return;
     }
     if (lane == 0) st.put(0, (int32_t)sl.seed_s);
@@ -218,145 +325,297 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   }
   __syncwarp();
   unsigned long long steps = 0;
-  const TxOutcome out = tx_run<MODE_SPEC>(A, st, t, seed_i, budget, false, lane, steps);
+  const bool is_head = (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT];
+  const unsigned long long t0 = is_head ? gtimer() : 0ull;
+  const TxOutcome out = tx_run<MODE_SPEC>(A, st, t, seed_i, budget, false, lane, steps, &as);
   __syncwarp();
+  if (lane == 0 && is_head) {
+    S.sc[SC_HEAD_STEPS] += steps;
+    S.sc[SC_HEAD_NS] += gtimer() - t0;
+  }
   if (lane == 0) {
     sl.t = t;
+    sl.as = as;
+    sl.started = 1;
     sl.steps += steps;
-    sl.failed = out == TX_FAILED ? 1 : 0;
-    sl.status = out == TX_RUNNING ? ST_RUNNING : ((out == TX_FINISHED || out == TX_FAILED) ? ST_FINISHED : ST_DOOMED);
+    // a depth-0 failure under assumptions is a tiny transaction: the sweeper's job
+    sl.status = out == TX_RUNNING ? ST_RUNNING : (out == TX_FINISHED ? ST_FINISHED : ST_DEAD);
+    if (out == TX_FINISHED && (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT]) {
+      *(volatile unsigned long long*)&S.sc[SC_STOP] = 1ull;
+    }
   }
 }
 
-__global__ void __launch_bounds__(TPB) spec_validate_kernel(SpecArgs S, int64_t F, int64_t C)
-{
-  int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
-  bool bad = false;
-  if (t < C) {
-    const uint32_t k = S.kind[t];
-    if (k == KIND_SKIP) bad = false;
-    else if (k == KIND_TINY) bad = S.A.doom[F + t] != 0;
-    else if (k >= KIND_SLOT) bad = S.slots[k - KIND_SLOT].status != ST_FINISHED || S.A.doom[F + t] != 0;
-    else bad = true;
-  }
-  // lowest bad index of the block -> one atomic
-  __shared__ unsigned long long blk;
-  if (threadIdx.x == 0) blk = ~0ull;
-  __syncthreads();
-  if (bad) atomicMin(&blk, (unsigned long long)t);
-  __syncthreads();
-  if (threadIdx.x == 0 && blk != ~0ull) atomicMin(&S.sc[SC_FIRST_BAD], blk);
-}
+// ---- K3: the sweeper ------------------------------------------------------------------------------------------
+struct SweepShared {
+  int first_special;  // lowest thread whose seed needs the slow path (or lies beyond the cloud)
+  int first_over;     // lowest thread beyond the hash-table budget
+  int first_conf;     // lowest thread whose seed a lower seed of the batch wants
+  int n_used;         // hash slots claimed by this batch
+  int stop;
+  int sp_slot, sp_live, sp_grower;
+  unsigned long long c_off, c_pl;
+  int warp_sum[32];
+  uint16_t used[HT / 2 + 64];
+};
 
-__global__ void __launch_bounds__(TPB) spec_commit_tiny_kernel(SpecArgs S, int64_t F, int64_t C)
+__device__ __forceinline__ uint32_t sweep_hash(uint32_t p) { return (p * 2654435761u) >> 18; }  // 14 bits
+
+// the sequential authority: walks the seeds from the frontier in index order
+template <int KM>
+__global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
 {
+  extern __shared__ uint32_t smem_u32[];
+  uint32_t* hkeys = smem_u32;        // [HT] point, 0xffffffff = empty
+  uint32_t* hvals = smem_u32 + HT;   // [HT] lowest thread of the batch that wants it
+  __shared__ SweepShared sh;
   const GrowArgs& A = S.A;
-  int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
-  if (t >= C)
-    return;
-  const uint32_t k = S.kind[t];
-  if (k != KIND_TINY && k != KIND_TINY_BAD)
-    return;
-  const unsigned long long fbu = S.sc[SC_FIRST_BAD];
-  const int64_t first_bad = fbu > (unsigned long long)C ? C : (int64_t)fbu;
-  const int64_t i = F + t;
-  const uint32_t s = __ldg(A.inv + i);
-  const int32_t* row = A.nbr + (int64_t)s * A.K;
-  const uint32_t mask = S.mask[t];
-  if (t < first_bad) {
-    for (int j = 1; j < A.K; ++j)
-      if ((mask >> j) & 1u) A.state[__ldg(row + j)] = (int32_t)i;  // orphan marks, :233 then :238-239
-    atomicAdd(&S.sc[SC_TX_COMMIT], 1ull);
-  } else {
-    for (int j = 1; j < A.K; ++j)
-      if ((mask >> j) & 1u) atomicCAS(A.res + __ldg(row + j), (uint32_t)i, RES_FREE);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int K = A.K;
+  int64_t F = (int64_t)A.ctl[CTL_FRONTIER];
+  unsigned long long iters = 0, ntiny = 0;
+  const unsigned long long t_begin = gtimer();
+  for (int k = tid; k < HT; k += SWEEP_T) {
+    hkeys[k] = 0xffffffffu;
+    hvals[k] = 0xffffffffu;
   }
-}
+  if (tid == 0) sh.stop = 0;
+  __syncthreads();
 
-__global__ void __launch_bounds__(GW * 32) spec_commit_slots_kernel(SpecArgs S, int64_t F, int64_t C)
-{
-  const GrowArgs& A = S.A;
-  const int lane = threadIdx.x & 31;
-  const int g = blockIdx.x * GW + (threadIdx.x >> 5);
-  if (g >= S.G)
-    return;
-  Slot& sl = S.slots[g];
-  if (sl.status == ST_FREE)
-    return;
-  const unsigned long long fbu = S.sc[SC_FIRST_BAD];
-  const int64_t first_bad = fbu > (unsigned long long)C ? C : (int64_t)fbu;  // slots beyond the window were not validated
-  const int64_t i = sl.seed_i;
-  const int64_t t = i - F;
-  const PagedStore st = slot_store(S, g);
-  const int64_t len = sl.t.len;
-  bool release = false, free_slot = false;
-  if (t < first_bad) {  // finished and clean
-    free_slot = true;
-    if (sl.failed) {
-      for (int64_t e = 1 + lane; e < len; e += 32) A.state[st.get(e)] = (int32_t)i;
-    } else if (len > A.th_count) {
-      unsigned long long off = 0, pl = 0;
-      if (lane == 0) {
-        off = atomicAdd(&A.ctl[CTL_POOL], (unsigned long long)len);
-        pl = atomicAdd(&A.ctl[CTL_PLANES], 1ull);
+  while (F < A.n) {
+    ++iters;
+    // ---- evaluate SWEEP_T seeds against the committed state ----
+    const int64_t i = F + tid;
+    const bool valid = i < A.n;
+    uint32_t s = 0, want = 0;
+    int32_t slot = -1;
+    bool live = false, grower = false, hasres = false;
+    int32_t ids[KM];  // neighbour columns that pass depth 0 (registers: every loop over them is unrolled)
+#pragma unroll
+    for (int j = 1; j < KM; ++j) ids[j] = -1;
+    if (valid) {
+      // three dependent levels of loads, everything inside a level is issued back to back
+      s = __ldg(A.inv + i);
+      const uint32_t m = __ldg(S.gmask + i);
+      slot = __ldcg(A.slotof + i);
+      const int32_t* row = A.nbr + (int64_t)s * K;
+      const int32_t st_s = __ldcg(A.state + s);
+#pragma unroll
+      for (int j = 1; j < KM; ++j)
+        if ((m >> j) & 1u) ids[j] = __ldg(row + j);
+      int32_t stj[KM];
+      uint32_t rsj[KM];
+#pragma unroll
+      for (int j = 1; j < KM; ++j) {
+        stj[j] = 0;
+        rsj[j] = RES_FREE;
+        if (ids[j] >= 0) {
+          stj[j] = __ldcg(A.state + ids[j]);
+          rsj[j] = __ldcg(A.res + ids[j]);
+        }
       }
-      off = __shfl_sync(FULL_MASK, off, 0);
-      pl = __shfl_sync(FULL_MASK, pl, 0);
-      if ((int64_t)(off + len) > A.pool_cap - A.n - 2 || (int64_t)pl >= A.planes_cap) {
-        if (lane == 0) A.ctl[CTL_ERR] = 2;
-      } else {
-        for (int64_t e = lane; e < len; e += 32) {
+      live = st_s == -1;
+      if (live) {
+#pragma unroll
+        for (int j = 1; j < KM; ++j)
+          if (ids[j] >= 0 && stj[j] == -1) {
+            want |= 1u << j;
+            hasres |= rsj[j] != RES_FREE;
+          }
+        grower = __popc(want) == K - 1;  // :238 -- every neighbour accepted
+      }
+    }
+    if (tid == 0) {
+      sh.first_special = SWEEP_T;
+      sh.first_over = SWEEP_T;
+      sh.first_conf = SWEEP_T;
+      sh.n_used = 0;
+    }
+    __syncthreads();
+    if (!valid || slot >= 0 || grower) atomicMin(&sh.first_special, tid);
+    __syncthreads();
+    const int first_special = sh.first_special;
+
+    if (first_special == 0) {
+      // ---- slow path: the seed at the frontier owns a slot and / or is a grower at its turn ----
+      if (tid == 0) {
+        sh.sp_slot = slot;
+        sh.sp_live = live ? 1 : 0;
+        sh.sp_grower = grower ? 1 : 0;
+      }
+      __syncthreads();
+      const int g = sh.sp_slot;
+      const bool grower_now = sh.sp_live && sh.sp_grower;
+      if (g < 0) {  // a grower without a slot: the scout gives it one
+        if (tid == 0) S.sc[SC_STUCK] = 1;
+        break;
+      }
+      Slot& sl = S.slots[g];
+      const int status = sl.status;
+      const bool doomed = ((volatile uint8_t*)A.doom)[F] != 0;
+      const PagedStore st = slot_store(S, g);
+      const int64_t len = sl.started ? sl.t.len : 0;
+      if (grower_now && status == ST_RUNNING && !doomed)  // the head is still growing
+        break;
+      const bool commit = grower_now && status == ST_FINISHED && !doomed;
+      bool cascade = true;
+      if (commit && len > A.th_count) {  // :199-202
+        cascade = false;
+        if (tid == 0) {
+          sh.c_off = A.ctl[CTL_POOL];
+          sh.c_pl = A.ctl[CTL_PLANES];
+        }
+        __syncthreads();
+        const unsigned long long off = sh.c_off, pl = sh.c_pl;
+        if ((int64_t)(off + len) > A.pool_cap - A.n - 2 || (int64_t)pl >= A.planes_cap) {
+          if (tid == 0) A.ctl[CTL_ERR] = 2;
+          break;
+        }
+        for (int64_t e = tid; e < len; e += SWEEP_T) {
           const int32_t id = st.get(e);
           A.pool[off + e] = id;
-          if (e >= 1) A.state[id] = (int32_t)i;
+          if (e >= 1) {
+            A.state[id] = (int32_t)F;
+            A.res[id] = RES_FREE;
+          }
         }
-        if (lane == 0) {
+        if (tid == 0) {
           PlaneRec r;
-          r.seed = (int32_t)i; r.pad = 0;
+          r.seed = (int32_t)F; r.pad = 0;
           r.off = (int64_t)off; r.len = len;
           r.nrm[0] = sl.t.m.mn0; r.nrm[1] = sl.t.m.mn1; r.nrm[2] = sl.t.m.mn2;
           r.ctr[0] = sl.t.m.mc0; r.ctr[1] = sl.t.m.mc1; r.ctr[2] = sl.t.m.mc2; r.pad2 = 0;
           A.planes[pl] = r;
+          A.ctl[CTL_POOL] = off + (unsigned long long)len;
+          A.ctl[CTL_PLANES] = pl + 1;
+          A.ctl[CTL_STEPS] += sl.steps;
+          A.ctl[CTL_TX] += 1;
+        }
+      } else {
+        // roll back (:203-209), or drop a slot that is doomed / dead / no longer a grower at its turn
+        for (int64_t e = 1 + tid; e < len; e += SWEEP_T) atomicCAS(A.res + st.get(e), (uint32_t)F, RES_FREE);
+        if (tid == 0) {
+          if (commit) {
+            A.ctl[CTL_STEPS] += sl.steps;
+            A.ctl[CTL_TX] += 1;
+          } else {
+            atomicAdd(&S.sc[SC_WASTED], sl.steps);
+          }
         }
       }
-    } else {
-      release = true;  // :203-209 roll back: nothing persists
+      if (cascade) {  // whoever treated these points as taken is void
+        for (int g2 = tid; g2 < S.G; g2 += SWEEP_T) {
+          const Slot& d = S.slots[g2];
+          if (g2 != g && d.status != ST_FREE && d.seed_i > (int32_t)F && relies_on(d, (int32_t)F)) A.doom[d.seed_i] = 1;
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) slot_free(S, g);
+      __threadfence();
+      __syncthreads();
+      if (commit) {
+        F += 1;  // the seed is done (its own point stays unmarked, :191)
+      } else if (grower_now) {  // needs to be grown again: the scout re-assigns it
+        if (tid == 0) S.sc[SC_STUCK] = 1;
+        break;
+      }
+      continue;  // dropped, and not a grower any more: re-evaluated as an ordinary seed
     }
-    if (lane == 0) {
-      atomicAdd(&S.sc[SC_TX_COMMIT], 1ull);
-      atomicAdd(&A.ctl[CTL_STEPS], sl.steps);
-    }
-  } else if (sl.status == ST_DOOMED || A.doom[i]) {
-    release = true;
-    free_slot = true;
-    if (lane == 0) atomicAdd(&S.sc[SC_SLOT_STEPS], sl.steps);
-  }
-  if (release)
-    for (int64_t e = lane; e < len; e += 32) atomicCAS(A.res + st.get(e), (uint32_t)i, RES_FREE);
-  __syncwarp();
-  if (free_slot && lane == 0) {
-    // pages back to the pool
-    const int np = sl.n_pages;
-    if (np > 0) {
-      const unsigned long long pos = atomicAdd(S.pool.n_free, (unsigned long long)np);
-      for (int k = 0; k < np; ++k) S.pool.free_pages[pos + k] = st.ptab[k];
-    }
-    sl.n_pages = 0;
-    sl.status = ST_FREE;
-    A.hasslot[i] = 0;
-    const unsigned long long pos = atomicAdd(&S.sc[SC_NFREE], 1ull);
-    S.free_ids[pos] = (uint32_t)g;
-  }
-}
 
-__global__ void spec_advance_kernel(SpecArgs S, int64_t F, int64_t C)
-{
-  unsigned long long fb = S.sc[SC_FIRST_BAD];
-  if (fb > (unsigned long long)C) fb = (unsigned long long)C;
-  const unsigned long long Fn = (unsigned long long)F + fb;
-  S.A.ctl[CTL_FRONTIER] = Fn;
-  S.sc[5] = fb;  // reported to the host
-  S.sc[6] = (Fn < (unsigned long long)S.A.n && S.A.hasslot[Fn]) ? 1ull : 0ull;  // a live slot sits at the head
+    // ---- fast path: seeds [F, F + first_special) are dead or tiny ----
+    const bool cand = tid < first_special && live;
+    // cap the batch so that the hash table stays at most half full
+    int wsum = cand ? __popc(want) : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL_MASK, wsum, o);
+      if (lane >= o) wsum += v;
+    }
+    if (lane == 31) sh.warp_sum[tid >> 5] = wsum;
+    __syncthreads();
+    int incl = wsum;  // inclusive prefix of wants in index order
+    for (int w = 0; w < (tid >> 5); ++w) incl += sh.warp_sum[w];
+    if (cand && incl > HT / 2) atomicMin(&sh.first_over, tid);
+    __syncthreads();
+    const int seg_hi = sh.first_over < first_special ? sh.first_over : first_special;  // >= 1
+    const bool in_seg = cand && tid < seg_hi;
+    // which seeds are about to be marked by a LOWER seed of this batch?
+    if (in_seg && want) {
+#pragma unroll
+      for (int j = 1; j < KM; ++j) {
+        if (!((want >> j) & 1u))
+          continue;
+        const uint32_t id = (uint32_t)ids[j];
+        uint32_t h = sweep_hash(id);
+        for (;;) {
+          const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
+          if (old == 0xffffffffu) sh.used[atomicAdd(&sh.n_used, 1)] = (uint16_t)h;
+          if (old == 0xffffffffu || old == id) {
+            atomicMin(hvals + h, (uint32_t)tid);
+            break;
+          }
+          h = (h + 1) & (HT - 1);
+        }
+      }
+    }
+    __syncthreads();
+    if (in_seg) {
+      uint32_t h = sweep_hash(s);
+      for (;;) {
+        const uint32_t k = hkeys[h];
+        if (k == 0xffffffffu)
+          break;
+        if (k == s) {
+          if (hvals[h] < (uint32_t)tid) atomicMin(&sh.first_conf, tid);
+          break;
+        }
+        h = (h + 1) & (HT - 1);
+      }
+    }
+    __syncthreads();
+    const int seg_end = sh.first_conf < seg_hi ? sh.first_conf : seg_hi;  // >= 1: thread 0 has nobody below it
+    // ---- commit the conflict-free prefix: orphan marks of the tiny transactions (:233 then :238-239) ----
+    if (in_seg && tid < seg_end) {
+      ++ntiny;
+      if (want) {
+#pragma unroll
+        for (int j = 1; j < KM; ++j) {
+          if (!((want >> j) & 1u))
+            continue;
+          const int32_t id = ids[j];
+          atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, (uint32_t)i);  // the lower seed owns a shared point
+          if (hasres) {
+            const uint32_t r = __ldcg(A.res + id);
+            if (r != RES_FREE) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
+          }
+        }
+      }
+    }
+    // wipe the table entries of this batch
+    const int n_used = sh.n_used;
+    for (int k = tid; k < n_used; k += SWEEP_T) {
+      const int h = sh.used[k];
+      hkeys[h] = 0xffffffffu;
+      hvals[h] = 0xffffffffu;
+    }
+    __threadfence();
+    F += seg_end;
+    __syncthreads();
+  }
+
+  if (tid == 0) {
+    A.ctl[CTL_FRONTIER] = (unsigned long long)F;
+    S.sc[SC_SWEEP_ITERS] += iters;
+    S.sc[SC_SWEEP_NS] += gtimer() - t_begin;
+  }
+  // tiny transactions committed: one atomic per warp
+  for (int o = 16; o; o >>= 1) ntiny += __shfl_down_sync(FULL_MASK, ntiny, o);
+  if (lane == 0 && ntiny) {
+    atomicAdd(&S.sc[SC_TINY], ntiny);
+    atomicAdd(&A.ctl[CTL_TX], ntiny);
+    atomicAdd(&A.ctl[CTL_STEPS], ntiny);
+  }
 }
 
 __global__ void spec_init_kernel(SpecArgs S)
@@ -369,6 +628,7 @@ __global__ void spec_init_kernel(SpecArgs S)
   }
   if (g < S.n_pool_pages) S.pool.free_pages[g] = g;
   if (g == 0) {
+    for (int k = 0; k < 16; ++k) S.sc[k] = 0;
     S.sc[SC_NFREE] = (unsigned long long)S.G;
     *S.pool.n_free = (unsigned long long)S.n_pool_pages;
   }
@@ -383,105 +643,121 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
 {
   (void)p;
   const int64_t n = A.n;
-  const int64_t CMAX = 1 << 20, CMIN = 4096;
+  const int64_t CMAX = 1 << 16;
   SpecArgs S;
   S.G = 1024;
   // page pool: room for every point once plus one page per slot, capped at 64 Mi entries
   int64_t pages = (3 * n) / PAGE_SIZE + 2 * S.G;
   if (pages > 32768) pages = 32768;
   S.n_pool_pages = (uint32_t)pages;
-  const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 4 + 256;
+  const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 8 + 256;
   RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + 64));
-  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)CMAX * 12 + (size_t)n * 2 + 256));
+  // flag[CMAX+1] | gmask[n] | slotof[n] | doom[n] | gone[n]
+  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 10 + 256));
   RC_CHECK(dev_ensure(c, c->g_queue, (size_t)pages * PAGE_SIZE * 12 + 256));
   S.slots = dptr<Slot>(c->g_tx);
   S.free_ids = reinterpret_cast<uint32_t*>(S.slots + S.G);
+  S.released = reinterpret_cast<int32_t*>(S.free_ids + S.G);
   S.ptabs = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(c->g_tx.p) + slot_bytes);
   S.pool.free_pages = S.ptabs + (size_t)S.G * MAX_PAGES_PER_SLOT;
   S.pool.stack_pages = dptr<int2>(c->g_queue);
   S.pool.list_pages = reinterpret_cast<int32_t*>(S.pool.stack_pages + (size_t)pages * PAGE_SIZE);
-  S.kind = dptr<uint32_t>(c->g_spec);
-  S.mask = S.kind + CMAX;
-  S.flag = S.mask + CMAX;
-  A.doom = reinterpret_cast<uint8_t*>(S.flag + CMAX);
-  A.hasslot = A.doom + n;
+  S.flag = dptr<uint32_t>(c->g_spec);
+  uint32_t* gmask = S.flag + CMAX + 4;
+  S.gmask = gmask;
+  A.slotof = reinterpret_cast<int32_t*>(gmask + n);
+  A.doom = reinterpret_cast<uint8_t*>(A.slotof + n);
+  S.gone = A.doom + n;
   S.sc = A.ctl + 8;
-  S.pool.n_free = &S.sc[7];
+  S.pool.n_free = &S.sc[SC_POOLFREE];
+  A.stop_flag = &S.sc[SC_STOP];
+  A.frontier = 0;
   S.A = A;
+  CU_CHECK(c, cudaMemsetAsync(A.slotof, 0xff, (size_t)n * 4, c->stream));
   CU_CHECK(c, cudaMemsetAsync(A.doom, 0, (size_t)n * 2, c->stream));
   {
     const int64_t m = pages > S.G ? pages : S.G;
     spec_init_kernel<<<(unsigned)ceil_div64(m, TPB), TPB, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
+    gmask_kernel<<<(unsigned)ceil_div64(n, TPB), TPB, 0, c->stream>>>(A, gmask);
+    KLAUNCH_CHECK(c);
+  }
+  static bool attr_set = false;
+  const size_t sweep_smem = (size_t)HT * 8;
+  if (!attr_set) {
+    CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
+    CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
+    attr_set = true;
   }
 
-  int64_t F = 0, C = 16384, rounds = 0;
-  unsigned long long head_tx = 64;
-  int64_t seq_growers = 0;
+  int64_t F = 0, rounds = 0, stalls = 0, fallbacks = 0;
+  unsigned long long ctl[32] = {0};
   uint32_t* d_ncand = reinterpret_cast<uint32_t*>(&S.sc[SC_NCAND]);
+  const unsigned sb = (unsigned)((S.G + GW - 1) / GW);
+  const unsigned long long budget = 4096;
+  // the first pass of the sweeper runs before anything is in flight: it stops at the first grower
   while (F < n) {
-    if (C > n - F) C = n - F;
+    const int64_t C = n - F < CMAX ? n - F : CMAX;
     const unsigned gb = (unsigned)ceil_div64(C, TPB);
-    const unsigned sb = (unsigned)((S.G + GW - 1) / GW);
-    CU_CHECK(c, cudaMemsetAsync(&S.sc[SC_FIRST_BAD], 0xff, sizeof(unsigned long long), c->stream));
-    spec_prepare_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    spec_mark_slots_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    spec_depth0_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    CU_CHECK(c, cudaMemsetAsync(&S.sc[SC_NCAND], 0, sizeof(unsigned long long), c->stream));
-    RC_CHECK(bseg_exclusive_scan_u32(c, S.flag, C, d_ncand));
-    spec_assign_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    spec_pop_free_kernel<<<1, 1, 0, c->stream>>>(S);
-    KLAUNCH_CHECK(c);
-    spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, 4096ull);
-    KLAUNCH_CHECK(c);
-    spec_validate_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    spec_commit_tiny_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    spec_commit_slots_kernel<<<sb, GW * 32, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    spec_advance_kernel<<<1, 1, 0, c->stream>>>(S, F, C);
-    KLAUNCH_CHECK(c);
-    launch_grow_seq(c, S.A, true, head_tx, 1ull << 40, 0);
+    S.A.frontier = F;
+    if (rounds > 0) {
+      spec_release_entries_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
+      spec_release_slots_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
+      spec_cascade_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
+      spec_cascade_done_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
+      spec_scout_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
+      KLAUNCH_CHECK(c);
+      RC_CHECK(bseg_exclusive_scan_u32(c, S.flag, C, d_ncand));
+      spec_assign_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
+      KLAUNCH_CHECK(c);
+      spec_pop_free_kernel<<<1, 1, 0, c->stream>>>(S, F);
+      KLAUNCH_CHECK(c);
+      spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget);
+      KLAUNCH_CHECK(c);
+    }
+    if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
+    else spec_sweep_kernel<32><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     ++rounds;
-    unsigned long long ctl[16];
     RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
     if (ctl[CTL_ERR])
       break;
-    const int64_t committed = (int64_t)ctl[8 + 5];
-    const bool head_live = ctl[8 + 6] != 0;
-    int64_t Fn = (int64_t)ctl[CTL_FRONTIER];
+    const int64_t Fn = (int64_t)ctl[CTL_FRONTIER];
     if (Fn < F)
-      return bseg_fail(c, BSEG_E_STATE, "speculative grower: frontier moved backwards");
-    if (Fn == F && !head_live) {
-      // the head is a depth-0 success without a slot (no slot / no pages left, or a plane too large for
-      // the page table): the head runner grows it in the flat region, alone
-      launch_grow_seq(c, S.A, true, 1, 1ull << 40, 1);
-      KLAUNCH_CHECK(c);
-      RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
-      if (ctl[CTL_ERR])
-        break;
-      Fn = (int64_t)ctl[CTL_FRONTIER];
-      ++seq_growers;
+      return bseg_fail(c, BSEG_E_STATE, "plane grower: frontier moved backwards");
+    // no progress and nothing growing at the head for several rounds: the head cannot get a slot (no pages
+    // left, or a plane too large for the page table) -- grow it alone in the flat region
+    const bool head_has_slot = ctl[8 + SC_HEAD_SLOT] != 0;
+    if (Fn == F && rounds > 1 && !head_has_slot) {
+      if (++stalls >= 2) {
+        launch_grow_seq(c, S.A, true, 1, 1ull << 40, 1);
+        KLAUNCH_CHECK(c);
+        RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
+        if (ctl[CTL_ERR])
+          break;
+        stalls = 0;
+        ++fallbacks;
+        F = (int64_t)ctl[CTL_FRONTIER];
+        continue;
+      }
+    } else {
+      stalls = 0;
     }
     F = Fn;
-    // window: wide when the clean prefix is long, never below CMIN (speculation is cheap)
-    if (committed >= C) C = C * 2 < CMAX ? C * 2 : CMAX;
-    else {
-      int64_t want = committed * 4;
-      C = want < CMIN ? CMIN : (want > CMAX ? CMAX : want);
-    }
-    // head runner: long sequential runs where the window keeps colliding, a single step otherwise
-    head_tx = committed < 256 ? 2048 : (committed < 4096 ? 128 : 8);
-    if (rounds > (int64_t)4 * n + 1024)
-      return bseg_fail(c, BSEG_E_STATE, "speculative grower: no progress");
+    if (rounds > 8 * n + 1024)
+      return bseg_fail(c, BSEG_E_STATE, "plane grower: no progress");
   }
   c->tm.grow_rounds = rounds;
-  (void)seq_growers;
+  c->tm.grow_wasted_steps = (int64_t)ctl[8 + SC_WASTED];
+  c->tm.grow_sweep_iters = (int64_t)ctl[8 + SC_SWEEP_ITERS];
+  c->tm.grow_tiny_tx = (int64_t)ctl[8 + SC_TINY];
+  c->tm.grow_seq_fallbacks = fallbacks;
+  c->tm.grow_head_steps = (int64_t)ctl[8 + SC_HEAD_STEPS];
+  c->tm.grow_head_ns = (int64_t)ctl[8 + SC_HEAD_NS];
+  c->tm.grow_sweep_ns = (int64_t)ctl[8 + SC_SWEEP_NS];
   return 0;
 }

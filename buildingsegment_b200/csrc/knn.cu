@@ -761,7 +761,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   RC_CHECK(dev_ensure(c, c->curv, (size_t)n * 8));
   const size_t max_items = (size_t)c->n_cells + (size_t)n / 32 + 8;
   RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + 2 * max_items + 16) * 4));
-  RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
+  RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
 
   KnnArgs A;
   A.pts = dptr<int4>(c->pts);

@@ -246,7 +246,7 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
   // ---- ordered accumulation + finalisation ----
   RC_CHECK(dev_ensure(c, c->r_image, (size_t)npx * 24));
   RC_CHECK(dev_ensure(c, c->r_png, (size_t)npx * 9 + 64));
-  RC_CHECK(dev_ensure(c, c->counters, 64 * sizeof(uint64_t)));
+  RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
   unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 56;
   CU_CHECK(c, cudaMemsetAsync(maxbits, 0, 2 * sizeof(unsigned long long), c->stream));
   accumulate_kernel<<<(unsigned)ceil_div64(npx, TPB), TPB, 0, c->stream>>>(

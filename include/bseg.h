@@ -69,6 +69,13 @@ typedef struct bseg_timings {
   int64_t grow_rounds;    /* rounds of the speculative engine                 */
   int64_t kernel_launches;/* kernels launched since bseg_reset_counters       */
   int64_t n_big_cells;    /* cells whose 27-neighbourhood did not fit the shared-memory stage */
+  int64_t grow_wasted_steps; /* Broad() calls of speculative growers that were released (parallel engine) */
+  int64_t grow_sweep_iters;  /* batches of the sweeper                                                  */
+  int64_t grow_tiny_tx;      /* depth-0 failures committed by the sweeper                               */
+  int64_t grow_seq_fallbacks;/* planes grown alone by the sequential engine (slot storage exhausted)    */
+  int64_t grow_head_steps;   /* Broad() calls of the head slot: the critical path of the parallel engine */
+  int64_t grow_head_ns;      /* device time of those calls, ns                                          */
+  int64_t grow_sweep_ns;     /* device time inside the sweeper, ns                                      */
 } bseg_timings;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
