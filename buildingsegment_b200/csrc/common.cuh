@@ -102,6 +102,7 @@ struct bseg_ctx {
   DevBuf g_tx;        // grower transaction slots
   DevBuf g_queue;     // u32 grower queue
   DevBuf g_stack;     // int2 DFS frames of grower slots
+  DevBuf g_rowdup;    // u8 [n]: neighbour row names a point twice
   DevBuf g_label;     // int32 [n] label in original order
   DevBuf g_pidx;      // int32 [n] planeIdx in original order
   // raster

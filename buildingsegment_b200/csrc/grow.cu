@@ -135,6 +135,23 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
   }
 }
 
+// rowdup[s] = 1 when columns 1..K-1 of row s name some point twice (only then the per-step dedupe is needed)
+__global__ void rowdup_kernel(const int32_t* __restrict__ nbr, int K, int64_t n, uint8_t* __restrict__ rowdup)
+{
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n)
+    return;
+  const int32_t* row = nbr + s * K;
+  bool dup = false;
+  for (int j = 2; j < K; ++j) {
+    const int32_t id = __ldg(row + j);
+    if (id < 0)
+      continue;
+    for (int j2 = 1; j2 < j; ++j2) dup |= __ldg(row + j2) == id;
+  }
+  rowdup[s] = dup ? 1 : 0;
+}
+
 // ---- finalize: plane ids, planeIdx and label in original order ------------------------------------------
 // id(owner) = 1 + #plane seeds < owner; label = id when the owner IS a plane seed, else the id of the
 // plane seeded at the point itself (a seed is in its own pointIdx without being marked), else 0.
@@ -271,10 +288,14 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.frontier = 0;
   {
     const char* gf = getenv("BSEG_GROW_FLAGS");  // tuning switches of the step engine (grow.cuh GF_*)
-    A.flags = gf ? atoi(gf) : (GF_ROW_L2);
+    A.flags = gf ? atoi(gf) : (GF_ROWDUP | GF_FASTDIV);
   }
+  RC_CHECK(dev_ensure(c, c->g_rowdup, (size_t)n + 64));
+  A.rowdup = dptr<uint8_t>(c->g_rowdup);
 
   STAGE_BEGIN(c, EV_GROW);
+  rowdup_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(A.nbr, A.K, n, dptr<uint8_t>(c->g_rowdup));
+  KLAUNCH_CHECK(c);
   CU_CHECK(c, cudaMemsetAsync(A.state, 0xff, (size_t)n * 4, c->stream));
   CU_CHECK(c, cudaMemsetAsync(A.res, 0xff, (size_t)n * 4, c->stream));
   CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 64 * sizeof(unsigned long long), c->stream));

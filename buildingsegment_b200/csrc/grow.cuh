@@ -31,8 +31,9 @@ struct GrowArgs {
   unsigned long long* stop_flag;
   int64_t frontier;  // first unresolved seed at slice start (everything below is committed)
   int flags;         // tuning switches (BSEG_GROW_FLAGS): see GF_*
+  const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
 };
-enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8 };
+enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32 };
 
 // ---- "assumed taken" record of a speculative transaction ----------------------------------------------
 // A point that is free in the committed state and passes the geometric tests, but is reserved by a LOWER
@@ -100,6 +101,47 @@ __device__ __forceinline__ void model_update(Model& m, int64_t len)
   m.mc0 = center_div(m.sc0, (uint32_t)len);
   m.mc1 = center_div(m.sc1, (uint32_t)len);
   m.mc2 = center_div(m.sc2, (uint32_t)len);
+}
+
+// The same update with the three quotients sharing one reciprocal -- bit-identical results:
+//   fp64: Markstein's theorem -- r = RN(1/b), q0 = RN(a*r), rem = a - b*q0 (exact, FMA), RN(q0 + rem*r) is the
+//         correctly rounded a/b unless b's mantissa is all ones; operands outside a safe exponent window
+//         (zero, subnormal, inf, NaN: Q9) take the true division;
+//   u32:  floor(a/b) from trunc(a * RN(1/b)) is off by at most one; the remainder tells which way.
+__device__ __forceinline__ bool div_safe_operand(double x)
+{
+  const int e = (int)((bseg_d2u(x) >> 52) & 0x7ffu);
+  return e > 523 && e < 1523;
+}
+__device__ __forceinline__ void model_update_fast(Model& m, int64_t len)
+{
+  const double nn = bseg_sqrt((m.sn0 * m.sn0) + (m.sn1 * m.sn1) + (m.sn2 * m.sn2));
+  const bool all_ones = (bseg_d2u(nn) & 0xfffffffffffffULL) == 0xfffffffffffffULL;
+  if (div_safe_operand(nn) && !all_ones && div_safe_operand(m.sn0) && div_safe_operand(m.sn1) &&
+      div_safe_operand(m.sn2)) {
+    const double r = __drcp_rn(nn);
+    const double q0 = __dmul_rn(m.sn0, r), q1 = __dmul_rn(m.sn1, r), q2 = __dmul_rn(m.sn2, r);
+    m.mn0 = __fma_rn(__fma_rn(-q0, nn, m.sn0), r, q0);
+    m.mn1 = __fma_rn(__fma_rn(-q1, nn, m.sn1), r, q1);
+    m.mn2 = __fma_rn(__fma_rn(-q2, nn, m.sn2), r, q2);
+  } else {
+    m.mn0 = m.sn0 / nn; m.mn1 = m.sn1 / nn; m.mn2 = m.sn2 / nn;
+  }
+  const uint32_t l = (uint32_t)len;
+  if ((int32_t)(m.sc0 | m.sc1 | m.sc2) >= 0) {  // all three sums below 2^31 (always, before Q6 strikes)
+    const double rl = __drcp_rn((double)l);
+    uint32_t q, rem;
+    q = (uint32_t)__dmul_rn((double)m.sc0, rl); rem = m.sc0 - q * l;
+    m.mc0 = (int32_t)((int32_t)rem < 0 ? q - 1 : (rem >= l ? q + 1 : q));
+    q = (uint32_t)__dmul_rn((double)m.sc1, rl); rem = m.sc1 - q * l;
+    m.mc1 = (int32_t)((int32_t)rem < 0 ? q - 1 : (rem >= l ? q + 1 : q));
+    q = (uint32_t)__dmul_rn((double)m.sc2, rl); rem = m.sc2 - q * l;
+    m.mc2 = (int32_t)((int32_t)rem < 0 ? q - 1 : (rem >= l ? q + 1 : q));
+  } else {
+    m.mc0 = center_div(m.sc0, l);
+    m.mc1 = center_div(m.sc1, l);
+    m.mc2 = center_div(m.sc2, l);
+  }
 }
 
 // add the accepted lanes' normals / positions to the running sums in neighbour order
@@ -245,6 +287,9 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
   const uint32_t me = (uint32_t)seed_i;
   const bool row_l1 = (A.flags & GF_ROW_L1) != 0, row_l2 = (A.flags & GF_ROW_L2) != 0;
   const bool early_pop = (A.flags & GF_EARLY_POP) != 0, state_nc = (A.flags & GF_STATE_NC) != 0;
+  const bool use_rowdup = (A.flags & GF_ROWDUP) != 0, fastdiv = (A.flags & GF_FASTDIV) != 0;
+  bool has_dup = true;  // of the row being tested
+  if (use_rowdup) has_dup = __ldg(A.rowdup + t.node) != 0;
   unsigned long long steps = 0;
   TxOutcome out = TX_RUNNING;
   // neighbour `lane` of the node: id, and its state / reservation / position / normal
@@ -279,7 +324,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     if (early_pop && t.have_top && t.top_cur < t.top_end) pop_id = st.get(t.top_cur);
     bool ok = id >= 0 && stt == -1 && (MODE != MODE_SPEC || (rs != me && !mine)) &&
               geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
-    ok = dedupe(ok, id);
+    if (has_dup) ok = dedupe(ok, id);
     if (leave_growers && t.depth0) {
       if (__popc(__ballot_sync(FULL_MASK, ok)) == K - 1) {
         out = TX_IS_GROWER;
@@ -366,6 +411,8 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     int32_t nid = -1;
     if (have_next && lane >= 1 && lane < K)
       nid = __ldg(A.nbr + (int64_t)next * K + lane);
+    bool ndup = true;
+    if (use_rowdup && have_next) ndup = __ldg(A.rowdup + next) != 0;
     model_accumulate(t.m, acc, p, n0, n1, n2);
     int32_t nstt = 0;
     uint32_t nrs = RES_FREE;
@@ -391,7 +438,8 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
         nmine |= nid == __shfl_sync(FULL_MASK, id, b);
       }
     }
-    model_update(t.m, t.len);
+    if (fastdiv) model_update_fast(t.m, t.len);
+    else model_update(t.m, t.len);
     if (MODE == MODE_SPEC) {
       bool race = false;
       if (fired) {
@@ -410,6 +458,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     }
     t.node = next;
     id = nid; stt = nstt; rs = nrs; mine = nmine; p = np; n0 = m0; n1 = m1; n2 = m2;
+    has_dup = ndup;
     if (MODE == MODE_SPEC && (steps & 7) == 0) {
       if (((volatile uint8_t*)A.doom)[seed_i]) {
         out = TX_DOOMED;

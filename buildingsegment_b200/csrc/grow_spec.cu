@@ -178,47 +178,50 @@ __global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
     atomicCAS(A.res + st.get(e), (uint32_t)i, RES_FREE);
 }
 
-__global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
+// one block, one thread per slot: bookkeeping of the released slots, then the cascade
+__global__ void __launch_bounds__(1024) spec_release_slots_kernel(SpecArgs S)
 {
   const GrowArgs& A = S.A;
-  const int g = blockIdx.x * TPB + threadIdx.x;
-  if (g >= S.G)
-    return;
-  Slot& sl = S.slots[g];
-  if (sl.status == ST_FREE)
-    return;
-  const int32_t i = sl.seed_i;
-  if (!(sl.status == ST_DEAD || A.doom[i]))
-    return;
-  atomicAdd(&S.sc[SC_WASTED], sl.steps);
-  S.released[atomicAdd(&S.sc[SC_NREL], 1ull)] = i;
-  S.gone[i] = 1;
-  slot_free(S, g);
-}
-
-__global__ void __launch_bounds__(TPB) spec_cascade_kernel(SpecArgs S)
-{
-  const int g = blockIdx.x * TPB + threadIdx.x;
-  if (g >= S.G || S.sc[SC_NREL] == 0)
-    return;
-  const Slot& d = S.slots[g];
-  if (d.status == ST_FREE)
-    return;
-  bool hit = false;
-  if (d.as.over) {
-    const int nrel = (int)S.sc[SC_NREL];
-    for (int k = 0; k < nrel && !hit; ++k) hit = S.released[k] < d.seed_i;
-  } else {
-    for (int k = 0; k < d.as.n; ++k) hit |= S.gone[d.as.id[k]] != 0;
+  __shared__ int n_rel, min_rel;
+  __shared__ int32_t rel[1024];
+  const int g = threadIdx.x;
+  if (g == 0) {
+    n_rel = 0;
+    min_rel = 0x7fffffff;
   }
-  if (hit) S.A.doom[d.seed_i] = 1;
-}
-
-__global__ void __launch_bounds__(TPB) spec_cascade_done_kernel(SpecArgs S)
-{
-  const int k = blockIdx.x * TPB + threadIdx.x;
-  const int nrel = (int)S.sc[SC_NREL];
-  if (k < nrel) S.gone[S.released[k]] = 0;
+  __syncthreads();
+  bool active = false;
+  if (g < S.G) {
+    Slot& sl = S.slots[g];
+    if (sl.status != ST_FREE) {
+      const int32_t i = sl.seed_i;
+      if (sl.status == ST_DEAD || A.doom[i]) {
+        atomicAdd(&S.sc[SC_WASTED], sl.steps);
+        rel[atomicAdd(&n_rel, 1)] = i;
+        atomicMin(&min_rel, i);
+        S.gone[i] = 1;
+        slot_free(S, g);
+      } else {
+        active = true;
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (n_rel == 0)
+    return;
+  if (active) {  // whoever treated a released slot's points as taken is void
+    const Slot& d = S.slots[g];
+    bool hit = false;
+    if (d.as.over) {
+      hit = min_rel < d.seed_i;
+    } else {
+      for (int k = 0; k < d.as.n; ++k) hit |= S.gone[d.as.id[k]] != 0;
+    }
+    if (hit) A.doom[d.seed_i] = 1;
+  }
+  __syncthreads();
+  for (int k = g; k < n_rel; k += 1024) S.gone[rel[k]] = 0;
 }
 
 // ---- K1: scout -- candidates of the window [F, F+C) ----------------------------------------------------------
@@ -353,7 +356,7 @@ struct SweepShared {
   int first_conf;     // lowest thread whose seed a lower seed of the batch wants
   int n_used;         // hash slots claimed by this batch
   int stop;
-  int sp_slot, sp_live, sp_grower;
+  int sp_slot, sp_live, sp_grower, sp_np;
   unsigned long long c_off, c_pl;
   int warp_sum[32];
   uint16_t used[HT / 2 + 64];
@@ -390,39 +393,36 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
     const bool valid = i < A.n;
     uint32_t s = 0, want = 0;
     int32_t slot = -1;
-    bool live = false, grower = false, hasres = false;
+    bool live = false, grower = false;
     int32_t ids[KM];  // neighbour columns that pass depth 0 (registers: every loop over them is unrolled)
 #pragma unroll
     for (int j = 1; j < KM; ++j) ids[j] = -1;
     if (valid) {
-      // three dependent levels of loads, everything inside a level is issued back to back
+      // dependent levels of loads: (inv, gmask, slot) -> state of the seed -> [live seeds only] row -> states.
+      // One SM gathers ~1 sector per clock, so dead seeds (most of them, late in the sweep) must not gather.
       s = __ldg(A.inv + i);
       const uint32_t m = __ldg(S.gmask + i);
       slot = __ldcg(A.slotof + i);
-      const int32_t* row = A.nbr + (int64_t)s * K;
-      const int32_t st_s = __ldcg(A.state + s);
-#pragma unroll
-      for (int j = 1; j < KM; ++j)
-        if ((m >> j) & 1u) ids[j] = __ldg(row + j);
-      int32_t stj[KM];
-      uint32_t rsj[KM];
-#pragma unroll
-      for (int j = 1; j < KM; ++j) {
-        stj[j] = 0;
-        rsj[j] = RES_FREE;
-        if (ids[j] >= 0) {
-          stj[j] = __ldcg(A.state + ids[j]);
-          rsj[j] = __ldcg(A.res + ids[j]);
-        }
+      if (i + SWEEP_T < A.n) {  // the next batch usually starts SWEEP_T seeds further: pull its lines into L2
+        const uint32_t s2 = __ldg(A.inv + i + SWEEP_T);
+        prefetch_l2(A.state + s2);
+        prefetch_l2(A.nbr + (int64_t)s2 * K);
       }
-      live = st_s == -1;
+      live = __ldcg(A.state + s) == -1;
       if (live) {
+        const int32_t* row = A.nbr + (int64_t)s * K;
 #pragma unroll
         for (int j = 1; j < KM; ++j)
-          if (ids[j] >= 0 && stj[j] == -1) {
-            want |= 1u << j;
-            hasres |= rsj[j] != RES_FREE;
-          }
+          if ((m >> j) & 1u) ids[j] = __ldg(row + j);
+        int32_t stj[KM];
+#pragma unroll
+        for (int j = 1; j < KM; ++j) {
+          stj[j] = 0;
+          if (ids[j] >= 0) stj[j] = __ldcg(A.state + ids[j]);
+        }
+#pragma unroll
+        for (int j = 1; j < KM; ++j)
+          if (ids[j] >= 0 && stj[j] == -1) want |= 1u << j;
         grower = __popc(want) == K - 1;  // :238 -- every neighbour accepted
       }
     }
@@ -512,7 +512,19 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       }
       __threadfence();
       __syncthreads();
-      if (tid == 0) slot_free(S, g);
+      // give the slot back; its pages are returned by the whole block
+      if (tid == 0) {
+        const int np = sl.n_pages;
+        sh.sp_np = np;
+        sh.c_off = np > 0 ? atomicAdd(S.pool.n_free, (unsigned long long)np) : 0ull;
+      }
+      __syncthreads();
+      for (int k = tid; k < sh.sp_np; k += SWEEP_T) S.pool.free_pages[sh.c_off + k] = st.ptab[k];
+      __syncthreads();
+      if (tid == 0) {
+        sl.n_pages = 0;
+        slot_free(S, g);
+      }
       __threadfence();
       __syncthreads();
       if (commit) {
@@ -585,10 +597,8 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
             continue;
           const int32_t id = ids[j];
           atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, (uint32_t)i);  // the lower seed owns a shared point
-          if (hasres) {
-            const uint32_t r = __ldcg(A.res + id);
-            if (r != RES_FREE) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
-          }
+          const uint32_t r = __ldcg(A.res + id);
+          if (r != RES_FREE) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
         }
       }
     }
@@ -703,11 +713,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     if (rounds > 0) {
       spec_release_entries_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
-      spec_release_slots_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
-      KLAUNCH_CHECK(c);
-      spec_cascade_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
-      KLAUNCH_CHECK(c);
-      spec_cascade_done_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
+      spec_release_slots_kernel<<<1, 1024, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
       spec_scout_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
       KLAUNCH_CHECK(c);
@@ -718,6 +724,14 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       KLAUNCH_CHECK(c);
       spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget);
       KLAUNCH_CHECK(c);
+      // slots doomed during the slice are released by the whole GPU here, so that the sweeper (one block)
+      // meets few of them; two passes settle most cascades, the sweeper handles what is left in place
+      for (int pass = 0; pass < 2; ++pass) {
+        spec_release_entries_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
+        KLAUNCH_CHECK(c);
+        spec_release_slots_kernel<<<1, 1024, 0, c->stream>>>(S);
+        KLAUNCH_CHECK(c);
+      }
     }
     if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     else spec_sweep_kernel<32><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
