@@ -329,7 +329,7 @@ def run_ours(args):
                      "wasted_steps": int(last_t["grow_wasted_steps"]), "sweep_iters": int(last_t["grow_sweep_iters"]),
                      "tiny_tx": int(last_t["grow_tiny_tx"]), "seq_fallbacks": int(last_t["grow_seq_fallbacks"]),
                      "head_steps": int(last_t["grow_head_steps"]), "head_ms": round(last_t["grow_head_ns"] / 1e6, 3),
-                     "sweep_ms": round(last_t["grow_sweep_ns"] / 1e6, 3)},
+                     "sweep_ms": round(last_t["grow_sweep_ns"] / 1e6, 3), "at_fails": int(last_t["grow_at_fails"])},
         }
         print(json.dumps(out))
     ctx.close()

@@ -35,25 +35,14 @@ struct GrowArgs {
 };
 enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32 };
 
-// ---- "assumed taken" record of a speculative transaction ----------------------------------------------
+// ---- "assumed taken" list of a speculative transaction --------------------------------------------------
 // A point that is free in the committed state and passes the geometric tests, but is reserved by a LOWER
-// in-flight transaction, is treated as taken (the lower one gets it when it commits).  The transaction
-// remembers WHOM it relied on; if one of them is released without committing (doomed, rolled back), the
-// dependants are doomed too (grow_spec.cu: cascade), so a slot that reaches the sweeper clean has only
-// ever relied on planes that were committed with those points.
-constexpr int ASSUME_MAX = 16;
-struct AssumeSet {
-  int32_t id[ASSUME_MAX];
-  int32_t n;      // entries used
-  int32_t over;   // more than ASSUME_MAX distinct transactions: depends on "everyone lower"
-  __device__ __forceinline__ void add(int32_t a)
-  {
-    for (int k = 0; k < n; ++k)
-      if (id[k] == a) return;
-    if (n < ASSUME_MAX) id[n++] = a;
-    else over = 1;
-  }
-};
+// in-flight transaction (a grower, or a tiny transaction that published its orphan marks ahead of the
+// sweeper), is treated as taken and appended to the slot's AT list.  When the sweeper reaches the
+// transaction every lower one has been committed, so the result is the sequential one iff every AT point
+// is taken by then -- that is what the sweeper verifies before committing (grow_spec.cu).
+// Reservations below the slice's frontier belong to transactions the sweeper has passed: they are stale
+// (a dead tiny transaction never clears its hints) and count as free.
 
 enum { CTL_FRONTIER = 0, CTL_POOL = 1, CTL_PLANES = 2, CTL_STEPS = 3, CTL_ERR = 4, CTL_TX = 5 };
 
@@ -186,6 +175,7 @@ struct FlatStore {
   __device__ __forceinline__ int32_t get(int64_t e) const { return list[e]; }
   __device__ __forceinline__ void push(int64_t sp, int2 f) { stack[sp] = f; }
   __device__ __forceinline__ int2 pop(int64_t sp) const { return stack[sp]; }
+  __device__ __forceinline__ void put_at(int64_t, int32_t) {}
 };
 
 // paged: grower slots of the speculative engine share one page pool
@@ -196,6 +186,7 @@ constexpr int MAX_PAGES_PER_SLOT = 2048;    // 4 M entries per plane; larger pla
 struct PagePool {
   int32_t* list_pages;   // [n_pages][PAGE_SIZE]
   int2* stack_pages;     // [n_pages][PAGE_SIZE]
+  int32_t* at_pages;     // [n_pages][PAGE_SIZE] assumed-taken points
   uint32_t* free_pages;  // stack of free page ids
   unsigned long long* n_free;
 };
@@ -237,12 +228,15 @@ struct PagedStore {
   __device__ __forceinline__ int32_t get(int64_t e) const { return pool.list_pages[at(e)]; }
   __device__ __forceinline__ void push(int64_t sp, int2 f) { pool.stack_pages[at(sp)] = f; }
   __device__ __forceinline__ int2 pop(int64_t sp) const { return pool.stack_pages[at(sp)]; }
+  __device__ __forceinline__ void put_at(int64_t k, int32_t id) { pool.at_pages[at(k)] = id; }
+  __device__ __forceinline__ int32_t get_at(int64_t k) const { return pool.at_pages[at(k)]; }
 };
 
 // ---- one transaction's DFS state -------------------------------------------------------------------
 struct TxState {
   Model m;
   int64_t len, sp, top_cur, top_end;
+  int64_t n_at;  // entries of the assumed-taken list (speculative engine)
   uint32_t node;
   int have_top, depth0;
 };
@@ -262,6 +256,7 @@ __device__ __forceinline__ void tx_begin(TxState& t, const GrowArgs& A, uint32_t
 {
   model_init(t.m, __ldg(A.pts + seed_s), A.nrm + 3 * (int64_t)seed_s);
   t.len = 1;
+  t.n_at = 0;
   t.sp = 0;
   t.top_cur = 0;
   t.top_end = 0;
@@ -281,13 +276,14 @@ __device__ __forceinline__ void tx_begin(TxState& t, const GrowArgs& A, uint32_t
 // and only matters when a lower transaction slipped in between (then this one gives up and is re-run).
 template <int MODE, class Store>
 __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, unsigned long long budget,
-                            bool leave_growers, int lane, unsigned long long& steps_out, AssumeSet* as = nullptr)
+                            bool leave_growers, int lane, unsigned long long& steps_out)
 {
   const int K = A.K;
   const uint32_t me = (uint32_t)seed_i;
   const bool row_l1 = (A.flags & GF_ROW_L1) != 0, row_l2 = (A.flags & GF_ROW_L2) != 0;
   const bool early_pop = (A.flags & GF_EARLY_POP) != 0, state_nc = (A.flags & GF_STATE_NC) != 0;
   const bool use_rowdup = (A.flags & GF_ROWDUP) != 0, fastdiv = (A.flags & GF_FASTDIV) != 0;
+  const uint32_t fr = MODE == MODE_SPEC ? (uint32_t)A.frontier : 0u;
   bool has_dup = true;  // of the row being tested
   if (use_rowdup) has_dup = __ldg(A.rowdup + t.node) != 0;
   unsigned long long steps = 0;
@@ -313,7 +309,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     }
   }
   while (steps < budget) {
-    if (!st.reserve(t.len + 2 * K, lane)) {  // before anything is marked
+    if (!st.reserve((t.len > t.n_at ? t.len : t.n_at) + 2 * K, lane)) {  // before anything is marked
       out = TX_OVERFLOW;
       break;
     }
@@ -332,14 +328,38 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
         break;
       }
     }
-    int32_t relied = -1;  // lower in-flight transaction whose reservation made this lane decline
+    bool relied = false;  // a lower in-flight transaction holds the point: assume taken
     uint32_t old = RES_FREE;
     bool fired = false;
     if (ok) {
       if (MODE == MODE_SPEC) {
-        if (rs < me) {  // reserved by a lower transaction: assume taken
+        if (rs < fr) {  // stale reservation of a transaction the sweeper has passed: free; replace it (rare)
+          uint32_t cur = rs;
+          for (;;) {
+            if (cur < fr) {
+              const uint32_t seen = atomicCAS(A.res + id, cur, me);
+              if (seen == cur) {
+                old = RES_FREE;
+                break;
+              }
+              cur = seen;
+            } else {
+              old = atomicMin(A.res + id, me);
+              if (old >= fr)
+                break;
+              cur = old;
+            }
+          }
+          if (old < me) {
+            ok = false;
+            relied = true;
+          } else {
+            if (old != RES_FREE) A.doom[old] = 1;
+            if (p.w > (int32_t)me) A.doom[p.w] = 1;
+          }
+        } else if (rs < me) {
           ok = false;
-          relied = (int32_t)rs;
+          relied = true;
         } else {
           old = atomicMin(A.res + id, me);  // result looked at after the next gather is on its way
           fired = true;
@@ -354,11 +374,10 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
       }
     }
     if (MODE == MODE_SPEC) {
-      uint32_t rel = __ballot_sync(FULL_MASK, relied >= 0);
-      while (rel) {  // every lane keeps the same record (the slot stores lane 0's copy)
-        const int b = __ffs(rel) - 1;
-        rel &= rel - 1;
-        as->add(__shfl_sync(FULL_MASK, relied, b));
+      const uint32_t rel = __ballot_sync(FULL_MASK, relied);
+      if (rel) {
+        if (relied) st.put_at(t.n_at + __popc(rel & lanemask_lt()), id);
+        t.n_at += __popc(rel);
       }
     }
     const uint32_t acc = __ballot_sync(FULL_MASK, ok);
@@ -443,8 +462,8 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     if (MODE == MODE_SPEC) {
       bool race = false;
       if (fired) {
-        if (old < me) race = true;                      // a lower transaction reserved it in between
-        else if (old != RES_FREE) A.doom[old] = 1;      // stolen from a higher transaction: it is void
+        if (old < me && old >= fr) race = true;         // a lower transaction reserved it in between
+        else if (old != RES_FREE && old >= fr) A.doom[old] = 1;  // stolen from a higher transaction: it is void
         if (p.w > (int32_t)me) A.doom[p.w] = 1;         // the transaction seeded at this point lost its seed
       }
       if (__any_sync(FULL_MASK, race)) {

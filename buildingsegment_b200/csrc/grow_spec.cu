@@ -16,17 +16,18 @@
 //   (2) A transaction's decisions depend on other transactions only through the free/taken state of the
 //       points it ACCEPTS (a geometric rejection does not look at the state, a taken point stays taken).
 //       Depth-0 successes ("growers") therefore run ahead of the sweeper in slots, one warp each, against
-//       the committed state, reserving every accepted point with atomicMin(res[pt], seed index):
-//         - the point is reserved by a LOWER in-flight grower: treat it as taken and remember whom we
-//           relied on (AssumeSet);
-//         - it is reserved by a HIGHER one: take it, the higher one is doomed;
-//         - the sweeper marks a reserved point for a lower tiny transaction: the holder is doomed.
-//       A doomed / rolled-back grower releases its reservations and dooms whoever relied on it (cascade).
-//       When the sweeper reaches a seed that is a grower at its turn, a finished, un-doomed slot holds
-//       exactly the sequential result (every lower transaction has been committed by then, and every point
-//       it saw as taken is taken); it is committed (or rolled back, :203-209) in place.  Otherwise the
-//       sweeper stops, the seed gets a slot as the lowest candidate and -- with nothing lower in flight --
-//       runs clean: progress is guaranteed.
+//       the committed state, reserving every accepted point with atomicMin(res[pt], seed index); tiny
+//       transactions of the window ahead of the sweeper publish the marks they are going to make the same
+//       way (hints, re-evaluated and retracted every round).  A point that is
+//         - reserved by a LOWER in-flight transaction is treated as taken and appended to the grower's
+//           assumed-taken (AT) list;
+//         - reserved by a HIGHER one is taken, and a higher grower that held it is doomed;
+//         - marked by the sweeper while a grower holds it: the grower is doomed.
+//       When the sweeper reaches a seed that is a grower at its turn, every lower transaction has been
+//       committed; a finished, un-doomed slot whose AT points are all taken by then holds exactly the
+//       sequential result and is committed (or rolled back, :203-209) in place.  Otherwise the sweeper
+//       stops, the seed gets a slot as the lowest candidate (one slot is kept for it) and -- with nothing
+//       lower in flight -- runs clean: progress is guaranteed.
 // Round = release doomed slots -> scout (lowest candidates of the window take the free slots) -> one slice
 // of Broad steps for every running slot (ends when the head slot finishes) -> sweep.  Plane ids are ordinal
 // in seed order and are assigned after the fact (grow.cu finalize).
@@ -56,6 +57,7 @@ enum {
   SC_HEAD_STEPS = 11, // Broad steps of the head slot (the critical path) ...
   SC_HEAD_NS = 12,    // ... and the time they took (globaltimer)
   SC_SWEEP_NS = 13,   // time inside the sweeper
+  SC_ATFAIL = 14,     // finished slots whose assumed-taken points were not all taken
 };
 
 __device__ __forceinline__ unsigned long long gtimer()
@@ -73,7 +75,6 @@ struct Slot {
   int32_t n_pages;   // pages of the pool this slot owns
   int32_t pad;
   unsigned long long steps;
-  AssumeSet as;
   TxState t;
 };
 
@@ -87,8 +88,7 @@ struct SpecArgs {
   const uint32_t* gmask;  // [n] ORIGINAL index space (the sweeper and the scout walk seeds in index order)
   uint32_t* flag;   // [C] candidate flags -> exclusive scan
   uint32_t* free_ids;
-  int32_t* released;  // seeds released this round
-  uint8_t* gone;      // [n] original index space: released this round
+  uint8_t* hinted;    // [n] original index space: this tiny transaction has published hints
   unsigned long long* sc;
 };
 
@@ -150,15 +150,6 @@ __device__ __forceinline__ void slot_free(const SpecArgs& S, int g)
   S.free_ids[pos] = (uint32_t)g;
 }
 
-__device__ __forceinline__ bool relies_on(const Slot& d, int32_t a)
-{
-  if (d.as.over)
-    return true;
-  for (int k = 0; k < d.as.n; ++k)
-    if (d.as.id[k] == a) return true;
-  return false;
-}
-
 // ---- K0: release doomed / dead slots ahead of the sweeper, then doom whoever relied on them -----------------
 // A doomed plane can hold 10^5 reservations: RCH blocks per slot walk its list.
 constexpr int RCH = 16;
@@ -178,82 +169,105 @@ __global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
     atomicCAS(A.res + st.get(e), (uint32_t)i, RES_FREE);
 }
 
-// one block, one thread per slot: bookkeeping of the released slots, then the cascade
-__global__ void __launch_bounds__(1024) spec_release_slots_kernel(SpecArgs S)
+__global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
 {
   const GrowArgs& A = S.A;
-  __shared__ int n_rel, min_rel;
-  __shared__ int32_t rel[1024];
-  const int g = threadIdx.x;
-  if (g == 0) {
-    n_rel = 0;
-    min_rel = 0x7fffffff;
-  }
-  __syncthreads();
-  bool active = false;
-  if (g < S.G) {
-    Slot& sl = S.slots[g];
-    if (sl.status != ST_FREE) {
-      const int32_t i = sl.seed_i;
-      if (sl.status == ST_DEAD || A.doom[i]) {
-        atomicAdd(&S.sc[SC_WASTED], sl.steps);
-        rel[atomicAdd(&n_rel, 1)] = i;
-        atomicMin(&min_rel, i);
-        S.gone[i] = 1;
-        slot_free(S, g);
-      } else {
-        active = true;
-      }
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (n_rel == 0)
+  const int g = blockIdx.x * TPB + threadIdx.x;
+  if (g >= S.G)
     return;
-  if (active) {  // whoever treated a released slot's points as taken is void
-    const Slot& d = S.slots[g];
-    bool hit = false;
-    if (d.as.over) {
-      hit = min_rel < d.seed_i;
-    } else {
-      for (int k = 0; k < d.as.n; ++k) hit |= S.gone[d.as.id[k]] != 0;
-    }
-    if (hit) A.doom[d.seed_i] = 1;
-  }
-  __syncthreads();
-  for (int k = g; k < n_rel; k += 1024) S.gone[rel[k]] = 0;
+  Slot& sl = S.slots[g];
+  if (sl.status == ST_FREE)
+    return;
+  if (!(sl.status == ST_DEAD || A.doom[sl.seed_i]))
+    return;
+  atomicAdd(&S.sc[SC_WASTED], sl.steps);
+  slot_free(S, g);
 }
 
-// ---- K1: scout -- candidates of the window [F, F+C) ----------------------------------------------------------
-// candidate: free seed without a slot whose K-1 neighbours all pass depth 0 and are all free and not
-// reserved by a lower in-flight grower (relying on one would make it a tiny transaction: the sweeper's job)
+// ---- K1: scout -- the window [F, F+C) ahead of the sweeper -------------------------------------------------
+// Every seed of the window without a slot is evaluated against the committed state plus the reservations
+// of LOWER in-flight transactions (reservations below F are stale and count as free):
+//   dead (seed taken, or reserved by a lower transaction): retract the hints it may have published;
+//   grower-looking (all K-1 neighbours pass depth 0, free and unreserved by anything lower): candidate;
+//   tiny-looking: publish the marks it is going to make, atomicMin(res[pt], i) -- a higher grower that
+//     held the point is doomed.
+__device__ __forceinline__ uint32_t eff_res(uint32_t r, uint32_t F) { return r < F ? RES_FREE : r; }
+
 __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, int64_t C)
 {
   const GrowArgs& A = S.A;
   const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
   if (t == 0) {
     S.sc[SC_STOP] = 0;
-    S.sc[SC_NREL] = 0;
     S.sc[SC_NCAND] = 0;
     S.sc[SC_NASSIGN] = 0;
   }
   if (t >= C)
     return;
   const int64_t i = F + t;
+  const uint32_t me = (uint32_t)i, fr = (uint32_t)F;
   uint32_t cand = 0;
   if (__ldcg(A.slotof + i) < 0) {
     const uint32_t s = __ldg(A.inv + i);
     const int K = A.K;
-    if (__ldcg(A.state + s) == -1 && __ldcg(A.res + s) >= (uint32_t)i && __popc(__ldg(S.gmask + i)) == K - 1) {
-      const int32_t* row = A.nbr + (int64_t)s * K;
-      cand = 1;
-      for (int j = 1; j < K; ++j) {
+    const uint32_t m = __ldg(S.gmask + i);
+    const int32_t* row = A.nbr + (int64_t)s * K;
+    const bool hinted = S.hinted[i] != 0;
+    const bool dead = __ldcg(A.state + s) != -1 || eff_res(__ldcg(A.res + s), fr) < me;
+    uint32_t want = 0;
+    bool lower = false;
+    if (!dead) {
+      uint32_t mm = m;
+      while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
         const int32_t id = __ldg(row + j);
-        if (__ldcg(A.state + id) != -1 || __ldcg(A.res + id) < (uint32_t)i) {
-          cand = 0;
+        if (__ldcg(A.state + id) == -1) {
+          want |= 1u << j;
+          lower |= eff_res(__ldcg(A.res + id), fr) < me;
+        }
+      }
+      cand = (__popc(m) == K - 1 && __popc(want) == K - 1 && !lower) ? 1u : 0u;
+    }
+    if (dead || cand) {
+      if (hinted) {  // retract: a grower must not find its own stale hints, a dead seed marks nothing
+        uint32_t mm = m;
+        while (mm) {
+          const int j = __ffs(mm) - 1;
+          mm &= mm - 1;
+          atomicCAS(A.res + __ldg(row + j), me, RES_FREE);
+        }
+        S.hinted[i] = 0;
+      }
+    } else if (want) {
+      uint32_t mm = want;
+      while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int32_t id = __ldg(row + j);
+        uint32_t cur = __ldcg(A.res + id);
+        for (;;) {
+          if (cur != RES_FREE && cur >= fr && cur <= me)
+            break;  // ours already, or a lower transaction's
+          uint32_t prev;
+          if (cur < fr) {  // stale: replace
+            prev = atomicCAS(A.res + id, cur, me);
+            if (prev != cur) {
+              cur = prev;
+              continue;
+            }
+          } else {
+            prev = atomicMin(A.res + id, me);
+            if (prev < fr) {  // cannot happen inside this kernel (nobody writes stale values); be safe
+              cur = prev;
+              continue;
+            }
+            if (prev != RES_FREE && prev > me && __ldcg(A.slotof + prev) >= 0) A.doom[prev] = 1;
+          }
           break;
         }
       }
+      S.hinted[i] = 1;
     }
   }
   S.flag[t] = cand;
@@ -282,8 +296,6 @@ __global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t F,
   sl.started = 0;
   sl.steps = 0;
   sl.n_pages = 0;
-  sl.as.n = 0;
-  sl.as.over = 0;
   S.A.slotof[F + t] = (int32_t)g;
   S.A.doom[F + t] = 0;
 }
@@ -314,7 +326,6 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   }
   PagedStore st = slot_store(S, g);
   TxState t;
-  AssumeSet as = sl.as;
   if (!sl.started) {
     tx_begin(t, A, sl.seed_s);
     if (!st.reserve(1, lane)) {
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   unsigned long long steps = 0;
   const bool is_head = (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT];
   const unsigned long long t0 = is_head ? gtimer() : 0ull;
-  const TxOutcome out = tx_run<MODE_SPEC>(A, st, t, seed_i, budget, false, lane, steps, &as);
+  const TxOutcome out = tx_run<MODE_SPEC>(A, st, t, seed_i, budget, false, lane, steps);
   __syncwarp();
   if (lane == 0 && is_head) {
     S.sc[SC_HEAD_STEPS] += steps;
@@ -338,7 +349,6 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   }
   if (lane == 0) {
     sl.t = t;
-    sl.as = as;
     sl.started = 1;
     sl.steps += steps;
     // a depth-0 failure under assumptions is a tiny transaction: the sweeper's job
@@ -356,7 +366,7 @@ struct SweepShared {
   int first_conf;     // lowest thread whose seed a lower seed of the batch wants
   int n_used;         // hash slots claimed by this batch
   int stop;
-  int sp_slot, sp_live, sp_grower, sp_np;
+  int sp_slot, sp_np, sp_bad;
   unsigned long long c_off, c_pl;
   int warp_sum[32];
   uint16_t used[HT / 2 + 64];
@@ -433,35 +443,48 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       sh.n_used = 0;
     }
     __syncthreads();
-    if (!valid || slot >= 0 || grower) atomicMin(&sh.first_special, tid);
+    if (!valid || grower) atomicMin(&sh.first_special, tid);
+    // a slot whose seed is not a grower at its turn is void (the state only gets more taken: it never will be)
+    if (valid && slot >= 0 && !grower) A.doom[i] = 1;
     __syncthreads();
     const int first_special = sh.first_special;
 
     if (first_special == 0) {
-      // ---- slow path: the seed at the frontier owns a slot and / or is a grower at its turn ----
+      // ---- slow path: the seed at the frontier is a grower at its turn ----
       if (tid == 0) {
         sh.sp_slot = slot;
-        sh.sp_live = live ? 1 : 0;
-        sh.sp_grower = grower ? 1 : 0;
+        sh.sp_bad = 0;
       }
       __syncthreads();
       const int g = sh.sp_slot;
-      const bool grower_now = sh.sp_live && sh.sp_grower;
-      if (g < 0) {  // a grower without a slot: the scout gives it one
+      if (g < 0) {  // no slot: the scout gives it one
         if (tid == 0) S.sc[SC_STUCK] = 1;
         break;
       }
       Slot& sl = S.slots[g];
       const int status = sl.status;
       const bool doomed = ((volatile uint8_t*)A.doom)[F] != 0;
-      const PagedStore st = slot_store(S, g);
-      const int64_t len = sl.started ? sl.t.len : 0;
-      if (grower_now && status == ST_RUNNING && !doomed)  // the head is still growing
+      if (status != ST_FINISHED || doomed) {
+        // still growing (the head), or void: released next round, then the scout re-assigns it
+        if (tid == 0 && status != ST_RUNNING) S.sc[SC_STUCK] = 1;
         break;
-      const bool commit = grower_now && status == ST_FINISHED && !doomed;
-      bool cascade = true;
-      if (commit && len > A.th_count) {  // :199-202
-        cascade = false;
+      }
+      const PagedStore st = slot_store(S, g);
+      const int64_t len = sl.t.len, n_at = sl.t.n_at;
+      // every point it treated as taken (reserved by a lower transaction at the time) must be taken now
+      bool bad = false;
+      for (int64_t k = tid; k < n_at; k += SWEEP_T) bad |= __ldcg(A.state + st.get_at(k)) == -1;
+      if (bad) sh.sp_bad = 1;
+      __syncthreads();
+      if (sh.sp_bad) {
+        if (tid == 0) {
+          A.doom[F] = 1;
+          S.sc[SC_STUCK] = 1;
+          atomicAdd(&S.sc[SC_ATFAIL], 1ull);
+        }
+        break;
+      }
+      if (len > A.th_count) {  // :199-202
         if (tid == 0) {
           sh.c_off = A.ctl[CTL_POOL];
           sh.c_pl = A.ctl[CTL_PLANES];
@@ -489,26 +512,13 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           A.planes[pl] = r;
           A.ctl[CTL_POOL] = off + (unsigned long long)len;
           A.ctl[CTL_PLANES] = pl + 1;
-          A.ctl[CTL_STEPS] += sl.steps;
-          A.ctl[CTL_TX] += 1;
         }
-      } else {
-        // roll back (:203-209), or drop a slot that is doomed / dead / no longer a grower at its turn
+      } else {  // roll back (:203-209): nothing persists
         for (int64_t e = 1 + tid; e < len; e += SWEEP_T) atomicCAS(A.res + st.get(e), (uint32_t)F, RES_FREE);
-        if (tid == 0) {
-          if (commit) {
-            A.ctl[CTL_STEPS] += sl.steps;
-            A.ctl[CTL_TX] += 1;
-          } else {
-            atomicAdd(&S.sc[SC_WASTED], sl.steps);
-          }
-        }
       }
-      if (cascade) {  // whoever treated these points as taken is void
-        for (int g2 = tid; g2 < S.G; g2 += SWEEP_T) {
-          const Slot& d = S.slots[g2];
-          if (g2 != g && d.status != ST_FREE && d.seed_i > (int32_t)F && relies_on(d, (int32_t)F)) A.doom[d.seed_i] = 1;
-        }
+      if (tid == 0) {
+        A.ctl[CTL_STEPS] += sl.steps;
+        A.ctl[CTL_TX] += 1;
       }
       __threadfence();
       __syncthreads();
@@ -527,13 +537,8 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       }
       __threadfence();
       __syncthreads();
-      if (commit) {
-        F += 1;  // the seed is done (its own point stays unmarked, :191)
-      } else if (grower_now) {  // needs to be grown again: the scout re-assigns it
-        if (tid == 0) S.sc[SC_STUCK] = 1;
-        break;
-      }
-      continue;  // dropped, and not a grower any more: re-evaluated as an ordinary seed
+      F += 1;  // the seed is done (its own point stays unmarked, :191)
+      continue;
     }
 
     // ---- fast path: seeds [F, F + first_special) are dead or tiny ----
@@ -598,7 +603,10 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           const int32_t id = ids[j];
           atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, (uint32_t)i);  // the lower seed owns a shared point
           const uint32_t r = __ldcg(A.res + id);
-          if (r != RES_FREE) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
+          if (r != RES_FREE) {
+            if (r != (uint32_t)i) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
+            A.res[id] = RES_FREE;                 // (a hint of this or a higher tiny transaction: obsolete)
+          }
         }
       }
     }
@@ -662,22 +670,22 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.n_pool_pages = (uint32_t)pages;
   const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 8 + 256;
   RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + 64));
-  // flag[CMAX+1] | gmask[n] | slotof[n] | doom[n] | gone[n]
+  // flag[CMAX+4] | gmask[n] | slotof[n] | doom[n] | hinted[n]
   RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 10 + 256));
-  RC_CHECK(dev_ensure(c, c->g_queue, (size_t)pages * PAGE_SIZE * 12 + 256));
+  RC_CHECK(dev_ensure(c, c->g_queue, (size_t)pages * PAGE_SIZE * 16 + 256));
   S.slots = dptr<Slot>(c->g_tx);
   S.free_ids = reinterpret_cast<uint32_t*>(S.slots + S.G);
-  S.released = reinterpret_cast<int32_t*>(S.free_ids + S.G);
   S.ptabs = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(c->g_tx.p) + slot_bytes);
   S.pool.free_pages = S.ptabs + (size_t)S.G * MAX_PAGES_PER_SLOT;
   S.pool.stack_pages = dptr<int2>(c->g_queue);
   S.pool.list_pages = reinterpret_cast<int32_t*>(S.pool.stack_pages + (size_t)pages * PAGE_SIZE);
+  S.pool.at_pages = S.pool.list_pages + (size_t)pages * PAGE_SIZE;
   S.flag = dptr<uint32_t>(c->g_spec);
   uint32_t* gmask = S.flag + CMAX + 4;
   S.gmask = gmask;
   A.slotof = reinterpret_cast<int32_t*>(gmask + n);
   A.doom = reinterpret_cast<uint8_t*>(A.slotof + n);
-  S.gone = A.doom + n;
+  S.hinted = A.doom + n;
   S.sc = A.ctl + 8;
   S.pool.n_free = &S.sc[SC_POOLFREE];
   A.stop_flag = &S.sc[SC_STOP];
@@ -713,7 +721,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     if (rounds > 0) {
       spec_release_entries_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
-      spec_release_slots_kernel<<<1, 1024, 0, c->stream>>>(S);
+      spec_release_slots_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
       spec_scout_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
       KLAUNCH_CHECK(c);
@@ -724,14 +732,6 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       KLAUNCH_CHECK(c);
       spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget);
       KLAUNCH_CHECK(c);
-      // slots doomed during the slice are released by the whole GPU here, so that the sweeper (one block)
-      // meets few of them; two passes settle most cascades, the sweeper handles what is left in place
-      for (int pass = 0; pass < 2; ++pass) {
-        spec_release_entries_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
-        KLAUNCH_CHECK(c);
-        spec_release_slots_kernel<<<1, 1024, 0, c->stream>>>(S);
-        KLAUNCH_CHECK(c);
-      }
     }
     if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     else spec_sweep_kernel<32><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
@@ -770,6 +770,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   c->tm.grow_sweep_iters = (int64_t)ctl[8 + SC_SWEEP_ITERS];
   c->tm.grow_tiny_tx = (int64_t)ctl[8 + SC_TINY];
   c->tm.grow_seq_fallbacks = fallbacks;
+  c->tm.grow_at_fails = (int64_t)ctl[8 + SC_ATFAIL];
   c->tm.grow_head_steps = (int64_t)ctl[8 + SC_HEAD_STEPS];
   c->tm.grow_head_ns = (int64_t)ctl[8 + SC_HEAD_NS];
   c->tm.grow_sweep_ns = (int64_t)ctl[8 + SC_SWEEP_NS];

@@ -40,7 +40,7 @@ class Timings(C.Structure):
                [(k, C.c_int64) for k in ("n_unresolved", "grow_steps", "grow_rounds", "kernel_launches",
                                          "n_big_cells", "grow_wasted_steps", "grow_sweep_iters",
                                          "grow_tiny_tx", "grow_seq_fallbacks", "grow_head_steps", "grow_head_ns",
-                                         "grow_sweep_ns")]
+                                         "grow_sweep_ns", "grow_at_fails")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -76,6 +76,7 @@ typedef struct bseg_timings {
   int64_t grow_head_steps;   /* Broad() calls of the head slot: the critical path of the parallel engine */
   int64_t grow_head_ns;      /* device time of those calls, ns                                          */
   int64_t grow_sweep_ns;     /* device time inside the sweeper, ns                                      */
+  int64_t grow_at_fails;     /* finished growers re-run because an assumed-taken point was free after all */
 } bseg_timings;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
