@@ -284,6 +284,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.ctl = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 64;  // [64, 128): grower control block
   A.doom = nullptr;
   A.slotof = nullptr;
+  A.atby = nullptr;
   A.stop_flag = nullptr;
   A.frontier = 0;
   {

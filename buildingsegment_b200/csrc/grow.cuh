@@ -32,6 +32,7 @@ struct GrowArgs {
   int64_t frontier;  // first unresolved seed at slice start (everything below is committed)
   int flags;         // tuning switches (BSEG_GROW_FLAGS): see GF_*
   const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
+  uint32_t* atby;    // [n] lowest in-flight transaction that assumed the point taken (early notification)
 };
 enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32 };
 
@@ -43,6 +44,16 @@ enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDU
 // is taken by then -- that is what the sweeper verifies before committing (grow_spec.cu).
 // Reservations below the slice's frontier belong to transactions the sweeper has passed: they are stale
 // (a dead tiny transaction never clears its hints) and count as free.
+// Early notification: atby[pt] names the lowest transaction that assumed pt taken; a reservation that is
+// dropped WITHOUT the point being taken (retracted hint, released or rolled-back grower) dooms it right
+// away, so it re-runs ahead of the sweeper instead of failing the verification at the head.
+__device__ __forceinline__ void unreserve_notify(uint32_t* atby, const int32_t* slotof, uint8_t* doom, int64_t p)
+{
+  if (__ldcg(atby + p) == 0xffffffffu)
+    return;
+  const uint32_t a = atomicExch(atby + p, 0xffffffffu);
+  if (a != 0xffffffffu && __ldcg(slotof + a) >= 0) doom[a] = 1;
+}
 
 enum { CTL_FRONTIER = 0, CTL_POOL = 1, CTL_PLANES = 2, CTL_STEPS = 3, CTL_ERR = 4, CTL_TX = 5 };
 
@@ -376,7 +387,10 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     if (MODE == MODE_SPEC) {
       const uint32_t rel = __ballot_sync(FULL_MASK, relied);
       if (rel) {
-        if (relied) st.put_at(t.n_at + __popc(rel & lanemask_lt()), id);
+        if (relied) {
+          st.put_at(t.n_at + __popc(rel & lanemask_lt()), id);
+          atomicMin(A.atby + id, me);  // whoever un-reserves the point without taking it tells us at once
+        }
         t.n_at += __popc(rel);
       }
     }

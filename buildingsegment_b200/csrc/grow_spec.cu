@@ -40,7 +40,7 @@ constexpr int GW = 4;          // warps per block in slot kernels
 constexpr int SWEEP_T = 1024;  // seeds per sweeper batch == threads of the sweeper block
 constexpr int HT = 16384;      // sweeper hash table slots (keys + vals = 128 KB of shared memory)
 
-enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3 };
+enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING = 4 };
 // spec control block (A.ctl + 8)
 enum {
   SC_NFREE = 0,       // free slots
@@ -153,32 +153,42 @@ __device__ __forceinline__ void slot_free(const SpecArgs& S, int g)
 // ---- K0: release doomed / dead slots ahead of the sweeper, then doom whoever relied on them -----------------
 // A doomed plane can hold 10^5 reservations: RCH blocks per slot walk its list.
 constexpr int RCH = 16;
-__global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
+// which slots go: decided ONCE (releasing a slot can doom others through the early notification, and the
+// three kernels must agree)
+__global__ void __launch_bounds__(TPB) spec_mark_release_kernel(SpecArgs S)
 {
-  const GrowArgs& A = S.A;
-  const int g = blockIdx.y;
-  const Slot& sl = S.slots[g];
-  if (sl.status == ST_FREE)
-    return;
-  const int32_t i = sl.seed_i;
-  if (!(sl.status == ST_DEAD || A.doom[i]))
-    return;
-  const PagedStore st = slot_store(S, g);
-  const int64_t len = sl.started ? sl.t.len : 0;
-  for (int64_t e = 1 + (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB)
-    atomicCAS(A.res + st.get(e), (uint32_t)i, RES_FREE);
-}
-
-__global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
-{
-  const GrowArgs& A = S.A;
   const int g = blockIdx.x * TPB + threadIdx.x;
   if (g >= S.G)
     return;
   Slot& sl = S.slots[g];
   if (sl.status == ST_FREE)
     return;
-  if (!(sl.status == ST_DEAD || A.doom[sl.seed_i]))
+  if (sl.status == ST_DEAD || S.A.doom[sl.seed_i]) sl.status = ST_RELEASING;
+}
+
+__global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
+{
+  const GrowArgs& A = S.A;
+  const int g = blockIdx.y;
+  const Slot& sl = S.slots[g];
+  if (sl.status != ST_RELEASING)
+    return;
+  const int32_t i = sl.seed_i;
+  const PagedStore st = slot_store(S, g);
+  const int64_t len = sl.started ? sl.t.len : 0;
+  for (int64_t e = 1 + (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB) {
+    const int32_t pt = st.get(e);
+    if (atomicCAS(A.res + pt, (uint32_t)i, RES_FREE) == (uint32_t)i) unreserve_notify(A.atby, A.slotof, A.doom, pt);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
+{
+  const int g = blockIdx.x * TPB + threadIdx.x;
+  if (g >= S.G)
+    return;
+  Slot& sl = S.slots[g];
+  if (sl.status != ST_RELEASING)
     return;
   atomicAdd(&S.sc[SC_WASTED], sl.steps);
   slot_free(S, g);
@@ -235,7 +245,8 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, 
         while (mm) {
           const int j = __ffs(mm) - 1;
           mm &= mm - 1;
-          atomicCAS(A.res + __ldg(row + j), me, RES_FREE);
+          const int32_t pt = __ldg(row + j);
+          if (atomicCAS(A.res + pt, me, RES_FREE) == me) unreserve_notify(A.atby, A.slotof, A.doom, pt);
         }
         S.hinted[i] = 0;
       }
@@ -514,7 +525,10 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           A.ctl[CTL_PLANES] = pl + 1;
         }
       } else {  // roll back (:203-209): nothing persists
-        for (int64_t e = 1 + tid; e < len; e += SWEEP_T) atomicCAS(A.res + st.get(e), (uint32_t)F, RES_FREE);
+        for (int64_t e = 1 + tid; e < len; e += SWEEP_T) {
+          const int32_t pt = st.get(e);
+          if (atomicCAS(A.res + pt, (uint32_t)F, RES_FREE) == (uint32_t)F) unreserve_notify(A.atby, A.slotof, A.doom, pt);
+        }
       }
       if (tid == 0) {
         A.ctl[CTL_STEPS] += sl.steps;
@@ -670,8 +684,8 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.n_pool_pages = (uint32_t)pages;
   const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 8 + 256;
   RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + 64));
-  // flag[CMAX+4] | gmask[n] | slotof[n] | doom[n] | hinted[n]
-  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 10 + 256));
+  // flag[CMAX+4] | gmask[n] | slotof[n] | atby[n] | doom[n] | hinted[n]
+  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 14 + 256));
   RC_CHECK(dev_ensure(c, c->g_queue, (size_t)pages * PAGE_SIZE * 16 + 256));
   S.slots = dptr<Slot>(c->g_tx);
   S.free_ids = reinterpret_cast<uint32_t*>(S.slots + S.G);
@@ -684,14 +698,15 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   uint32_t* gmask = S.flag + CMAX + 4;
   S.gmask = gmask;
   A.slotof = reinterpret_cast<int32_t*>(gmask + n);
-  A.doom = reinterpret_cast<uint8_t*>(A.slotof + n);
+  A.atby = reinterpret_cast<uint32_t*>(A.slotof + n);
+  A.doom = reinterpret_cast<uint8_t*>(A.atby + n);
   S.hinted = A.doom + n;
   S.sc = A.ctl + 8;
   S.pool.n_free = &S.sc[SC_POOLFREE];
   A.stop_flag = &S.sc[SC_STOP];
   A.frontier = 0;
   S.A = A;
-  CU_CHECK(c, cudaMemsetAsync(A.slotof, 0xff, (size_t)n * 4, c->stream));
+  CU_CHECK(c, cudaMemsetAsync(A.slotof, 0xff, (size_t)n * 8, c->stream));  // slotof = -1, atby = none
   CU_CHECK(c, cudaMemsetAsync(A.doom, 0, (size_t)n * 2, c->stream));
   {
     const int64_t m = pages > S.G ? pages : S.G;
@@ -719,6 +734,8 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     const unsigned gb = (unsigned)ceil_div64(C, TPB);
     S.A.frontier = F;
     if (rounds > 0) {
+      spec_mark_release_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
       spec_release_entries_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
       spec_release_slots_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
