@@ -103,6 +103,7 @@ struct bseg_ctx {
   DevBuf g_queue;     // u32 grower queue
   DevBuf g_stack;     // int2 DFS frames of grower slots
   DevBuf g_rowdup;    // u8 [n]: neighbour row names a point twice
+  DevBuf g_marklog;   // uint2 [n]: orphan marks of the current sweep (point, seed)
   DevBuf g_label;     // int32 [n] label in original order
   DevBuf g_pidx;      // int32 [n] planeIdx in original order
   // raster

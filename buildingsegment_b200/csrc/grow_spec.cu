@@ -31,6 +31,8 @@
 // Round = release doomed slots -> scout (lowest candidates of the window take the free slots) -> one slice
 // of Broad steps for every running slot (ends when the head slot finishes) -> sweep.  Plane ids are ordinal
 // in seed order and are assigned after the fact (grow.cu finalize).
+#include <cstdlib>
+
 #include "grow.cuh"
 
 namespace {
@@ -38,6 +40,7 @@ namespace {
 constexpr int TPB = 256;
 constexpr int GW = 4;          // warps per block in slot kernels
 constexpr int SWEEP_T = 1024;  // seeds per sweeper batch == threads of the sweeper block
+constexpr int SWEEP_WORDS = 128;  // bitmap words (4096 seeds) scanned per batch for up to SWEEP_T live seeds
 constexpr int HT = 16384;      // sweeper hash table slots (keys + vals = 128 KB of shared memory)
 
 enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING = 4 };
@@ -58,6 +61,8 @@ enum {
   SC_HEAD_NS = 12,    // ... and the time they took (globaltimer)
   SC_SWEEP_NS = 13,   // time inside the sweeper
   SC_ATFAIL = 14,     // finished slots whose assumed-taken points were not all taken
+  SC_NLOG = 19,       // entries of the mark log
+  SC_T_FRONT = 15, SC_T_SLOW = 16, SC_T_FAST = 17, SC_N_SLOW = 18,  // sweeper time split (ns), slow-path count
 };
 
 __device__ __forceinline__ unsigned long long gtimer()
@@ -89,6 +94,9 @@ struct SpecArgs {
   uint32_t* flag;   // [C] candidate flags -> exclusive scan
   uint32_t* free_ids;
   uint8_t* hinted;    // [n] original index space: this tiny transaction has published hints
+  uint32_t* alive;    // [ceil(n/32)] original index space: bit = the point may still be free (filter)
+  uint2* marklog;     // (point, seed) of the orphan marks the sweeper made this round: side effects applied later
+  unsigned long long marklog_cap;
   unsigned long long* sc;
 };
 
@@ -193,6 +201,28 @@ __global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
   atomicAdd(&S.sc[SC_WASTED], sl.steps);
   slot_free(S, g);
 }
+
+// ---- side effects of the sweeper's orphan marks (see spec_sweep_kernel) ------------------------------------------
+__global__ void __launch_bounds__(TPB) spec_apply_marks_kernel(SpecArgs S)
+{
+  const GrowArgs& A = S.A;
+  unsigned long long nlog = S.sc[SC_NLOG];
+  if (nlog > S.marklog_cap) nlog = S.marklog_cap;
+  for (unsigned long long k = (unsigned long long)blockIdx.x * TPB + threadIdx.x; k < nlog;
+       k += (unsigned long long)gridDim.x * TPB) {
+    const uint2 e = S.marklog[k];
+    const uint32_t r = __ldcg(A.res + e.x);
+    if (r != RES_FREE) {
+      if (r != e.y) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
+      A.res[e.x] = RES_FREE;        // (a hint of this or a higher tiny transaction: obsolete)
+    }
+    const int32_t w = __ldg(&A.pts[e.x].w);
+    atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
+    if (__ldcg(A.slotof + w) >= 0) A.doom[w] = 1;  // the grower seeded at this point lost its seed
+  }
+}
+
+__global__ void spec_reset_log_kernel(SpecArgs S) { S.sc[SC_NLOG] = 0; }
 
 // ---- K1: scout -- the window [F, F+C) ahead of the sweeper -------------------------------------------------
 // Every seed of the window without a slot is evaluated against the committed state plus the reservations
@@ -375,12 +405,14 @@ struct SweepShared {
   int first_special;  // lowest thread whose seed needs the slow path (or lies beyond the cloud)
   int first_over;     // lowest thread beyond the hash-table budget
   int first_conf;     // lowest thread whose seed a lower seed of the batch wants
-  int n_used;         // hash slots claimed by this batch
   int stop;
   int sp_slot, sp_np, sp_bad;
   unsigned long long c_off, c_pl;
   int warp_sum[32];
-  uint16_t used[HT / 2 + 64];
+  int n_live;
+  int64_t last_seed;
+  uint32_t words[SWEEP_WORDS];
+  int pref[SWEEP_WORDS];
 };
 
 __device__ __forceinline__ uint32_t sweep_hash(uint32_t p) { return (p * 2654435761u) >> 18; }  // 14 bits
@@ -398,6 +430,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   const int lane = tid & 31;
   const int K = A.K;
   int64_t F = (int64_t)A.ctl[CTL_FRONTIER];
+  const int64_t n_words = (A.n + 31) >> 5;
   unsigned long long iters = 0, ntiny = 0;
   const unsigned long long t_begin = gtimer();
   for (int k = tid; k < HT; k += SWEEP_T) {
@@ -407,11 +440,58 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   if (tid == 0) sh.stop = 0;
   __syncthreads();
 
+  unsigned long long t_front = 0, t_slow = 0, t_fast = 0, n_slow = 0;
   while (F < A.n) {
     ++iters;
-    // ---- evaluate SWEEP_T seeds against the committed state ----
-    const int64_t i = F + tid;
-    const bool valid = i < A.n;
+    const unsigned long long ti0 = gtimer();
+    // ---- the next live seeds: scan the alive bitmap (original index order, a superset of the free points) ----
+    // Late in the sweep 5 seeds of 6 are taken; they cost one bit here instead of a gather.
+    const int64_t base = F & ~31LL;
+    if (tid < SWEEP_WORDS) {
+      const int64_t wi = (base >> 5) + tid;
+      uint32_t w = wi < n_words ? __ldcg(S.alive + wi) : 0u;
+      if (tid == 0) w &= 0xffffffffu << (int)(F & 31);  // seeds below the frontier are done
+      sh.words[tid] = w;
+      sh.pref[tid] = __popc(w);
+    }
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of SWEEP_WORDS counts by one warp
+      int carry = 0;
+      for (int k0 = 0; k0 < SWEEP_WORDS; k0 += 32) {
+        const int c = sh.pref[k0 + tid];
+        int v = c;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(FULL_MASK, v, o);
+          if (tid >= o) v += u;
+        }
+        sh.pref[k0 + tid] = carry + v - c;
+        carry += __shfl_sync(FULL_MASK, v, 31);
+      }
+      if (tid == 0) sh.n_live = carry;
+    }
+    __syncthreads();
+    const int n_live = sh.n_live;
+    const int n_eval = n_live < SWEEP_T ? n_live : SWEEP_T;
+    if (n_live == 0) {  // nothing free in this stretch
+      F = base + 32LL * SWEEP_WORDS;
+      if (F > A.n) F = A.n;
+      __syncthreads();
+      continue;
+    }
+    // thread k evaluates the k-th live seed of the stretch
+    const bool valid = tid < n_eval;
+    int64_t i = A.n;
+    if (valid) {
+      int lo = 0, hi = SWEEP_WORDS - 1;  // last word whose exclusive prefix is <= tid
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sh.pref[mid] <= tid) lo = mid;
+        else hi = mid - 1;
+      }
+      const int bit = __fns(sh.words[lo], 0, tid - sh.pref[lo] + 1);
+      i = base + 32LL * lo + bit;
+    }
+    if (tid == n_eval - 1) sh.last_seed = i;
     uint32_t s = 0, want = 0;
     int32_t slot = -1;
     bool live = false, grower = false;
@@ -419,28 +499,23 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
 #pragma unroll
     for (int j = 1; j < KM; ++j) ids[j] = -1;
     if (valid) {
-      // dependent levels of loads: (inv, gmask, slot) -> state of the seed -> [live seeds only] row -> states.
-      // One SM gathers ~1 sector per clock, so dead seeds (most of them, late in the sweep) must not gather.
+      // dependent levels of loads: (inv, gmask, slot) -> (state of the seed, row) -> neighbour states
       s = __ldg(A.inv + i);
       const uint32_t m = __ldg(S.gmask + i);
       slot = __ldcg(A.slotof + i);
-      if (i + SWEEP_T < A.n) {  // the next batch usually starts SWEEP_T seeds further: pull its lines into L2
-        const uint32_t s2 = __ldg(A.inv + i + SWEEP_T);
-        prefetch_l2(A.state + s2);
-        prefetch_l2(A.nbr + (int64_t)s2 * K);
+      const int32_t* row = A.nbr + (int64_t)s * K;
+      const int32_t st_s = __ldcg(A.state + s);  // the bitmap is only a filter: this is the truth
+#pragma unroll
+      for (int j = 1; j < KM; ++j)
+        if ((m >> j) & 1u) ids[j] = __ldg(row + j);
+      int32_t stj[KM];
+#pragma unroll
+      for (int j = 1; j < KM; ++j) {
+        stj[j] = 0;
+        if (ids[j] >= 0) stj[j] = __ldcg(A.state + ids[j]);
       }
-      live = __ldcg(A.state + s) == -1;
+      live = st_s == -1;
       if (live) {
-        const int32_t* row = A.nbr + (int64_t)s * K;
-#pragma unroll
-        for (int j = 1; j < KM; ++j)
-          if ((m >> j) & 1u) ids[j] = __ldg(row + j);
-        int32_t stj[KM];
-#pragma unroll
-        for (int j = 1; j < KM; ++j) {
-          stj[j] = 0;
-          if (ids[j] >= 0) stj[j] = __ldcg(A.state + ids[j]);
-        }
 #pragma unroll
         for (int j = 1; j < KM; ++j)
           if (ids[j] >= 0 && stj[j] == -1) want |= 1u << j;
@@ -451,22 +526,26 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       sh.first_special = SWEEP_T;
       sh.first_over = SWEEP_T;
       sh.first_conf = SWEEP_T;
-      sh.n_used = 0;
     }
     __syncthreads();
-    if (!valid || grower) atomicMin(&sh.first_special, tid);
+    if (!valid || grower) atomicMin(&sh.first_special, tid);  // (threads beyond the live list end the batch)
     // a slot whose seed is not a grower at its turn is void (the state only gets more taken: it never will be)
     if (valid && slot >= 0 && !grower) A.doom[i] = 1;
     __syncthreads();
     const int first_special = sh.first_special;
+    const unsigned long long ti1 = gtimer();
+    t_front += ti1 - ti0;
 
     if (first_special == 0) {
-      // ---- slow path: the seed at the frontier is a grower at its turn ----
+      ++n_slow;
+      // ---- slow path: the first live seed is a grower at its turn ----
       if (tid == 0) {
         sh.sp_slot = slot;
         sh.sp_bad = 0;
+        sh.last_seed = i;
       }
       __syncthreads();
+      F = sh.last_seed;  // everything before it is taken
       const int g = sh.sp_slot;
       if (g < 0) {  // no slot: the scout gives it one
         if (tid == 0) S.sc[SC_STUCK] = 1;
@@ -483,8 +562,10 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       const PagedStore st = slot_store(S, g);
       const int64_t len = sl.t.len, n_at = sl.t.n_at;
       // every point it treated as taken (reserved by a lower transaction at the time) must be taken now
+      // ... and every point it accepted must still be free (a lower tiny transaction may have marked it)
       bool bad = false;
       for (int64_t k = tid; k < n_at; k += SWEEP_T) bad |= __ldcg(A.state + st.get_at(k)) == -1;
+      for (int64_t e = 1 + tid; e < len; e += SWEEP_T) bad |= __ldcg(A.state + st.get(e)) != -1;
       if (bad) sh.sp_bad = 1;
       __syncthreads();
       if (sh.sp_bad) {
@@ -512,6 +593,8 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           if (e >= 1) {
             A.state[id] = (int32_t)F;
             A.res[id] = RES_FREE;
+            const int32_t w = __ldg(&A.pts[id].w);
+            atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
           }
         }
         if (tid == 0) {
@@ -552,6 +635,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       __threadfence();
       __syncthreads();
       F += 1;  // the seed is done (its own point stays unmarked, :191)
+      t_slow += gtimer() - ti1;
       continue;
     }
 
@@ -581,7 +665,6 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         uint32_t h = sweep_hash(id);
         for (;;) {
           const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
-          if (old == 0xffffffffu) sh.used[atomicAdd(&sh.n_used, 1)] = (uint16_t)h;
           if (old == 0xffffffffu || old == id) {
             atomicMin(hvals + h, (uint32_t)tid);
             break;
@@ -607,36 +690,57 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
     __syncthreads();
     const int seg_end = sh.first_conf < seg_hi ? sh.first_conf : seg_hi;  // >= 1: thread 0 has nobody below it
     // ---- commit the conflict-free prefix: orphan marks of the tiny transactions (:233 then :238-239) ----
-    if (in_seg && tid < seg_end) {
-      ++ntiny;
-      if (want) {
+    // Only the owner mark is on the sweeper's path; what the mark means for others (reservation void, holder
+    // doomed, alive bit, seed of a waiting grower taken) is logged and applied by a parallel kernel after the
+    // sweep -- none of it is needed for correctness (a slot is verified point by point before it commits).
+    {
+      const bool commit = in_seg && tid < seg_end;
+      const int nw = commit ? __popc(want) : 0;
+      if (commit) ++ntiny;
+      int wincl = nw;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL_MASK, wincl, o);
+        if (lane >= o) wincl += v;
+      }
+      const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
+      unsigned long long lbase = 0;
+      if (wtot > 0) {
+        if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
+        lbase = __shfl_sync(FULL_MASK, lbase, 0);
+      }
+      if (nw) {
+        unsigned long long pos = lbase + (unsigned long long)(wincl - nw);
 #pragma unroll
         for (int j = 1; j < KM; ++j) {
           if (!((want >> j) & 1u))
             continue;
           const int32_t id = ids[j];
           atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, (uint32_t)i);  // the lower seed owns a shared point
-          const uint32_t r = __ldcg(A.res + id);
-          if (r != RES_FREE) {
-            if (r != (uint32_t)i) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
-            A.res[id] = RES_FREE;                 // (a hint of this or a higher tiny transaction: obsolete)
-          }
+          if (pos < S.marklog_cap) S.marklog[pos] = make_uint2((uint32_t)id, (uint32_t)i);
+          ++pos;
         }
       }
     }
-    // wipe the table entries of this batch
-    const int n_used = sh.n_used;
-    for (int k = tid; k < n_used; k += SWEEP_T) {
-      const int h = sh.used[k];
-      hkeys[h] = 0xffffffffu;
-      hvals[h] = 0xffffffffu;
+    for (int k = tid; k < HT; k += SWEEP_T) {  // (a list of the used slots would need one contended counter)
+      hkeys[k] = 0xffffffffu;
+      hvals[k] = 0xffffffffu;
     }
-    __threadfence();
-    F += seg_end;
+    // (no fence: every reader of these marks is in this block, and the barrier orders the block's accesses)
+    if (tid == seg_end && valid) sh.last_seed = i;  // first live seed left for the next batch
     __syncthreads();
+    if (seg_end < n_eval) F = sh.last_seed;
+    else if (n_live > n_eval) F = sh.last_seed + 1;  // more live seeds in the stretch than threads
+    else F = base + 32LL * SWEEP_WORDS;
+    if (F > A.n) F = A.n;
+    __syncthreads();
+    t_fast += gtimer() - ti1;
   }
 
   if (tid == 0) {
+    S.sc[SC_T_FRONT] += t_front;
+    S.sc[SC_T_SLOW] += t_slow;
+    S.sc[SC_T_FAST] += t_fast;
+    S.sc[SC_N_SLOW] += n_slow;
     A.ctl[CTL_FRONTIER] = (unsigned long long)F;
     S.sc[SC_SWEEP_ITERS] += iters;
     S.sc[SC_SWEEP_NS] += gtimer() - t_begin;
@@ -648,6 +752,15 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
     atomicAdd(&A.ctl[CTL_TX], ntiny);
     atomicAdd(&A.ctl[CTL_STEPS], ntiny);
   }
+}
+
+__global__ void __launch_bounds__(TPB) spec_alive_init_kernel(uint32_t* alive, int64_t n, int64_t n_alloc_words)
+{
+  const int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (k >= n_alloc_words)
+    return;
+  const int64_t lo = k * 32;
+  alive[k] = lo + 32 <= n ? 0xffffffffu : (lo >= n ? 0u : (0xffffffffu >> (32 - (int)(n - lo))));
 }
 
 __global__ void spec_init_kernel(SpecArgs S)
@@ -684,9 +797,11 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.n_pool_pages = (uint32_t)pages;
   const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 8 + 256;
   RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + 64));
-  // flag[CMAX+4] | gmask[n] | slotof[n] | atby[n] | doom[n] | hinted[n]
-  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 14 + 256));
+  // flag[CMAX+4] | gmask[n] | slotof[n] | atby[n] | alive[words] | doom[n] | hinted[n]
+  const int64_t alive_words = (n + 31) / 32 + SWEEP_WORDS + 4;
+  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 14 + (size_t)alive_words * 4 + 256));
   RC_CHECK(dev_ensure(c, c->g_queue, (size_t)pages * PAGE_SIZE * 16 + 256));
+  RC_CHECK(dev_ensure(c, c->g_marklog, ((size_t)n + 4096) * sizeof(uint2)));
   S.slots = dptr<Slot>(c->g_tx);
   S.free_ids = reinterpret_cast<uint32_t*>(S.slots + S.G);
   S.ptabs = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(c->g_tx.p) + slot_bytes);
@@ -699,8 +814,11 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.gmask = gmask;
   A.slotof = reinterpret_cast<int32_t*>(gmask + n);
   A.atby = reinterpret_cast<uint32_t*>(A.slotof + n);
-  A.doom = reinterpret_cast<uint8_t*>(A.atby + n);
+  S.alive = A.atby + n;
+  A.doom = reinterpret_cast<uint8_t*>(S.alive + alive_words);
   S.hinted = A.doom + n;
+  S.marklog = dptr<uint2>(c->g_marklog);
+  S.marklog_cap = (unsigned long long)n + 4096;
   S.sc = A.ctl + 8;
   S.pool.n_free = &S.sc[SC_POOLFREE];
   A.stop_flag = &S.sc[SC_STOP];
@@ -713,6 +831,8 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     spec_init_kernel<<<(unsigned)ceil_div64(m, TPB), TPB, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     gmask_kernel<<<(unsigned)ceil_div64(n, TPB), TPB, 0, c->stream>>>(A, gmask);
+    KLAUNCH_CHECK(c);
+    spec_alive_init_kernel<<<(unsigned)ceil_div64(alive_words, TPB), TPB, 0, c->stream>>>(S.alive, n, alive_words);
     KLAUNCH_CHECK(c);
   }
   static bool attr_set = false;
@@ -753,6 +873,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     else spec_sweep_kernel<32><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     KLAUNCH_CHECK(c);
+    spec_apply_marks_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
+    KLAUNCH_CHECK(c);
+    spec_reset_log_kernel<<<1, 1, 0, c->stream>>>(S);
+    KLAUNCH_CHECK(c);
     ++rounds;
     RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
     if (ctl[CTL_ERR])
@@ -782,6 +906,9 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     if (rounds > 8 * n + 1024)
       return bseg_fail(c, BSEG_E_STATE, "plane grower: no progress");
   }
+  if (getenv("BSEG_DEBUG"))
+    fprintf(stderr, "[bseg] sweeper: front %.1f ms, slow path %.1f ms (%llu), fast path %.1f ms\n", ctl[8 + SC_T_FRONT] / 1e6,
+            ctl[8 + SC_T_SLOW] / 1e6, ctl[8 + SC_N_SLOW], ctl[8 + SC_T_FAST] / 1e6);
   c->tm.grow_rounds = rounds;
   c->tm.grow_wasted_steps = (int64_t)ctl[8 + SC_WASTED];
   c->tm.grow_sweep_iters = (int64_t)ctl[8 + SC_SWEEP_ITERS];
