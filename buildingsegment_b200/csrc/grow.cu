@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
       if (lane == 0) st.list[0] = (int32_t)seed_s;
       TxState t;
       tx_begin(t, A, seed_s);
-      const TxOutcome out = tx_run<NOTIFY ? MODE_SEQ_NOTIFY : MODE_SEQ>(A, st, t, seed_i, ~0ull,
+      const TxOutcome out = tx_run<NOTIFY ? MODE_SEQ_NOTIFY : MODE_SEQ, 0>(A, st, t, seed_i, ~0ull,
                                                                          NOTIFY && !allow_growers, lane, steps);
       if (out == TX_IS_GROWER) {
         frontier = seed_i;

@@ -206,10 +206,11 @@ struct PagedStore {
   PagePool pool;
   uint32_t* ptab;       // this slot's page table [MAX_PAGES_PER_SLOT]
   int32_t* n_pages;     // pages currently owned by the slot
+  int have_cached;      // this warp is the only writer while it runs: a register copy saves a load per step
   // make entries [0, upto) addressable; one lane allocates, the warp learns the result
   __device__ __forceinline__ bool reserve(int64_t upto, int lane)
   {
-    int have = *n_pages;
+    int have = have_cached;
     const int need = (int)((upto + PAGE_SIZE - 1) >> PAGE_SHIFT);
     if (need <= have)
       return true;
@@ -228,6 +229,7 @@ struct PagedStore {
       *n_pages = have;
     }
     ok = __shfl_sync(FULL_MASK, ok, 0);
+    have_cached = __shfl_sync(FULL_MASK, have, 0);
     __syncwarp();
     return ok != 0;
   }
@@ -285,11 +287,11 @@ __device__ __forceinline__ void tx_begin(TxState& t, const GrowArgs& A, uint32_t
 // position / normal (L2) -> tests.  The reservation atomics are NOT on the chain in MODE_SPEC: the
 // decision uses the reservation value that was gathered, the atomic's result is inspected one step later
 // and only matters when a lower transaction slipped in between (then this one gives up and is re-run).
-template <int MODE, class Store>
+template <int MODE, int KT, class Store>
 __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, unsigned long long budget,
                             bool leave_growers, int lane, unsigned long long& steps_out)
 {
-  const int K = A.K;
+  const int K = KT ? KT : A.K;  // KT: compile-time row length (15 = the reference's), 0 = run time
   const uint32_t me = (uint32_t)seed_i;
   const bool row_l1 = (A.flags & GF_ROW_L1) != 0, row_l2 = (A.flags & GF_ROW_L2) != 0;
   const bool early_pop = (A.flags & GF_EARLY_POP) != 0, state_nc = (A.flags & GF_STATE_NC) != 0;

@@ -106,6 +106,7 @@ __device__ __forceinline__ PagedStore slot_store(const SpecArgs& S, int g)
   st.pool = S.pool;
   st.ptab = S.ptabs + (size_t)g * MAX_PAGES_PER_SLOT;
   st.n_pages = &S.slots[g].n_pages;
+  st.have_cached = S.slots[g].n_pages;
   return st;
 }
 
@@ -382,7 +383,8 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   unsigned long long steps = 0;
   const bool is_head = (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT];
   const unsigned long long t0 = is_head ? gtimer() : 0ull;
-  const TxOutcome out = tx_run<MODE_SPEC>(A, st, t, seed_i, budget, false, lane, steps);
+  const TxOutcome out = A.K == 15 ? tx_run<MODE_SPEC, 15>(A, st, t, seed_i, budget, false, lane, steps)
+                                  : tx_run<MODE_SPEC, 0>(A, st, t, seed_i, budget, false, lane, steps);
   __syncwarp();
   if (lane == 0 && is_head) {
     S.sc[SC_HEAD_STEPS] += steps;
