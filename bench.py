@@ -9,8 +9,9 @@ A step = one pass of the whole hot path over one synthetic cloud:
 `value`  : cloud already in HBM when the timed region starts (bseg_set_points_device + bseg_run_device)
 `e2e`    : through bseg_segment_host with pinned HOST buffers, H2D of the cloud and D2H of the shifted
            cloud, labels and PNG bytes inside the timed region
-N > 1    : one process per GPU (torchrun); every rank runs its own x-slab of the city tile
-           (weak scaling, no data-path collective yet -- see DESIGN.md "multi-GPU")
+N > 1    : one process per GPU (torchrun); every rank owns one 500 m x-slab of the city tile (weak scaling):
+           shared tile origin, NCCL halo exchange with the neighbour ranks, halo sufficiency check, per-slab
+           segmentation, cross-slab label merge (buildingsegment_b200/slabs.py, DESIGN.md "multi-GPU")
 --impl reference : the CPU path (oracle/_ref = the reference's own grower/raster lines, oracle port for
            the Open3D kNN/normals the reference links but does not vendor) on the host cores, bounded sample.
 """
@@ -207,6 +208,9 @@ def run_ours(args):
 
     n = args.points
     xyz = make_workload(args.workload, n, rank, world)
+    x_lo, x_hi = rank * 500_000, (rank + 1) * 500_000
+    if world > 1:  # this rank's slab of the city tile: x in [x_lo, x_hi) mm
+        xyz = np.ascontiguousarray(xyz[(xyz[:, 0] >= x_lo) & (xyz[:, 0] < x_hi)])
     n = len(xyz)
     ctx = lib.Context(local)
     p = lib.default_params()
@@ -214,6 +218,11 @@ def run_ours(args):
 
     d_xyz = torch.from_numpy(xyz).to(dev)
     W, H = None, None
+    slab_info = {}
+    if world > 1:
+        from buildingsegment_b200 import slabs
+
+        backend = slabs.CudaBackend(ctx, p)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -222,8 +231,15 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     def step_device():
-        ctx.set_points_device(d_xyz.data_ptr(), n)
-        ctx.run_device(p, lib.RUN_ALL)
+        if world == 1:
+            ctx.set_points_device(d_xyz.data_ptr(), n)
+            ctx.run_device(p, lib.RUN_ALL)
+            return None
+        # tile origin -> halo exchange (NCCL P2P) -> kNN/normals + halo check -> grow -> cross-slab label merge
+        r = slabs.segment_slab(backend, d_xyz, x_lo, x_hi, halo=args.halo)
+        ctx.run_device(p, lib.RUN_RASTER)
+        slab_info.update({k: r[k] for k in ("n_planes_total", "n_components", "halo", "n_halo")})
+        return r["labels"]
 
     # ---- device-resident leg ----
     for _ in range(args.warmup):
@@ -262,8 +278,16 @@ def run_ours(args):
     h_b = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
     np_xyz, np_shift, np_label, np_a, np_b = (h_xyz.numpy(), h_shift.numpy(), h_label.numpy(), h_a.numpy(), h_b.numpy())
 
+    d_stage = torch.empty((n, 3), dtype=torch.int32, device=dev) if world > 1 else None
+
     def step_host():
-        return ctx.segment_host(p, np_xyz, np_shift, np_label, np_a, np_b)
+        if world == 1:
+            return ctx.segment_host(p, np_xyz, np_shift, np_label, np_a, np_b)
+        d_stage.copy_(h_xyz, non_blocking=True)  # H2D of the slab from pinned memory
+        r = slabs.segment_slab(backend, d_stage, x_lo, x_hi, halo=args.halo)
+        h_label.copy_(r["labels"].to(torch.int32))  # D2H of the canonical labels
+        torch.cuda.synchronize(dev)
+        return r["n_planes_total"], 0, 0
 
     for _ in range(max(1, args.warmup // 2)):
         step_host()
@@ -279,7 +303,7 @@ def run_ours(args):
     ms_e2e = float(t_max.item())
     e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
     h2d = n * 12
-    d2h = n * 12 + n * 4 + 2 * 3 * W * H
+    d2h = n * 12 + n * 4 + 2 * 3 * W * H if world == 1 else n * 4
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -315,9 +339,11 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": f"{args.workload} synthetic suburban block, {n} points per GPU, reference defaults "
                                    f"(K=15, r=100 mm, max_nn=50, 300 mm, 0.88, 400)" if world == 1 else
-                                   f"C5-style city tile, one 500 m block-slab of {n} points per GPU, reference defaults",
+                                   f"C5-style city tile, one 500 m x-slab of ~{n} points per GPU (tile origin, NCCL halo "
+                                   f"exchange, halo check, per-slab segmentation, cross-slab label merge), reference defaults",
                        "points_per_gpu": n, "l2": "inputs larger than L2 (cloud + neighbour rows >> 126 MB)",
-                       "grow_engine": "sweeper + speculative growers (grow_mode 0)", "planes": int(npl)},
+                       "grow_engine": "sweeper + speculative growers (grow_mode 0)", "planes": int(npl),
+                       **({"slabs": slab_info} if world > 1 else {})},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -348,6 +374,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--ref-sample", type=int, default=60_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--halo", type=int, default=500, help="slab halo width, mm (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -212,6 +212,38 @@ BSEG_API int bseg_set_owned(bseg_ctx* c, int64_t n_owned)
   return 0;
 }
 
+BSEG_API int bseg_set_origin(bseg_ctx* c, const int32_t* origin)
+{
+  RC_CHECK(check_ctx(c));
+  c->have_origin = origin != nullptr;
+  for (int k = 0; k < 3; ++k) c->origin[k] = origin ? origin[k] : 0;
+  return 0;
+}
+
+BSEG_API int bseg_device_results(bseg_ctx* c, const int32_t** d_label, const int32_t** d_plane_idx,
+                                 const int32_t** d_xyz_shifted)
+{
+  RC_CHECK(check_ctx(c));
+  if (!c->have_points)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_device_results: no cloud");
+  if ((d_label || d_plane_idx) && !c->have_grow)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_device_results: the grower has not run");
+  if (d_label) *d_label = dptr<int32_t>(c->g_label);
+  if (d_plane_idx) *d_plane_idx = dptr<int32_t>(c->g_pidx);
+  if (d_xyz_shifted) *d_xyz_shifted = dptr<int32_t>(c->xyz_raw);
+  return 0;
+}
+
+int stage_halo_check(bseg_ctx* c, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved);  // knn.cu
+
+BSEG_API int bseg_halo_check(bseg_ctx* c, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved)
+{
+  RC_CHECK(check_ctx(c));
+  if (!c->have_knn || !n_unresolved)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_halo_check: run bseg_knn_normals first");
+  return stage_halo_check(c, x_lo, x_hi, halo, n_unresolved);
+}
+
 static int check_params(bseg_ctx* c, const bseg_params* p)
 {
   if (!p)
@@ -409,6 +441,8 @@ BSEG_API int bseg_reset_counters(bseg_ctx* c)
 BSEG_API void* bseg_stream(bseg_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 BSEG_API int64_t bseg_point_count(const bseg_ctx* c) { return c ? c->n : -1; }
+
+BSEG_API int32_t bseg_plane_count(const bseg_ctx* c) { return (c && c->have_grow) ? c->n_planes : -1; }
 
 BSEG_API int bseg_debug_sort_pairs(bseg_ctx* c, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits)
 {

@@ -201,12 +201,21 @@ int stage_bbox_shift(bseg_ctx* c)
   int g = grid_for(c, c->n * 3, TPB * 8);
   bbox_kernel<<<g, TPB, 0, c->stream>>>(dptr<int32_t>(c->xyz_raw), c->n, dptr<int32_t>(c->minmax));
   KLAUNCH_CHECK(c);
+  int32_t mm[8];
+  if (c->have_origin) {
+    // multi-GPU slabs share the tile's origin: shift by it instead of this slab's own minimum
+    RC_CHECK(read_back(c, mm, c->minmax.p, sizeof(mm)));
+    for (int k = 0; k < 3; ++k)
+      if (c->origin[k] > mm[k])
+        return bseg_fail(c, BSEG_E_ARG, "bseg_set_origin: origin[%d] = %d lies above the cloud's minimum %d", k,
+                         c->origin[k], mm[k]);
+    CU_CHECK(c, cudaMemcpyAsync(c->minmax.p, c->origin, 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  }
   shift_kernel<<<g, TPB, 0, c->stream>>>(dptr<int32_t>(c->xyz_raw), c->n, dptr<int32_t>(c->minmax));
   KLAUNCH_CHECK(c);
   STAGE_END(c, EV_BBOX);
-  int32_t mm[8];
   RC_CHECK(read_back(c, mm, c->minmax.p, sizeof(mm)));
-  for (int k = 0; k < 3; ++k) { c->mn[k] = mm[k]; c->mx[k] = mm[3 + k]; }
+  for (int k = 0; k < 3; ++k) { c->mn[k] = mm[k]; c->mx[k] = mm[3 + k]; }  // mn = the origin that was subtracted
   return 0;
 }
 

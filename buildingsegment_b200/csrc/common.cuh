@@ -55,6 +55,8 @@ struct bseg_ctx {
   int64_t n_owned = 0;  // points this rank owns (== n on one GPU)
   int32_t mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
   bool have_points = false, have_knn = false, have_grow = false;
+  bool have_origin = false;  // bseg_set_origin: shift by origin[] instead of the cloud's own minimum
+  int32_t origin[3] = {0, 0, 0};
 
   // ---- binning state (valid after the knn stage) ----
   int32_t cell = 0;     // kNN cell edge

@@ -821,6 +821,49 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   return 0;
 }
 
+// ---- halo sufficiency of a slab (include/bseg.h: bseg_halo_check) ------------------------------------------------
+namespace {
+__global__ void halo_check_kernel(const int4* __restrict__ pts, const int32_t* __restrict__ nbr, int K, int64_t n,
+                                  int64_t n_owned, int32_t x_lo, int32_t x_hi, int32_t halo,
+                                  unsigned long long* __restrict__ count)
+{
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n)
+    return;
+  const int4 q = __ldg(pts + s);
+  if (q.w >= n_owned)
+    return;  // a halo copy: only a neighbour
+  if ((int64_t)q.x - x_lo >= halo && (int64_t)x_hi - q.x > halo)
+    return;  // deep inside the slab: its neighbourhood cannot reach past the halo
+  int32_t last = -1;
+  for (int j = K - 1; j >= 0 && last < 0; --j) last = __ldg(nbr + s * K + j);
+  bool bad = last < 0;  // fewer than K points in reach at all
+  if (!bad) {
+    const int4 r = __ldg(pts + last);
+    const int64_t dx = (int64_t)r.x - q.x, dy = (int64_t)r.y - q.y, dz = (int64_t)r.z - q.z;
+    bad = dx * dx + dy * dy + dz * dz > (int64_t)halo * halo;
+  }
+  if (bad) atomicAdd(count, 1ull);
+}
+}  // namespace
+
+int stage_halo_check(bseg_ctx* c, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved)
+{
+  *n_unresolved = 0;
+  if (c->n == 0)
+    return 0;
+  RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 190;
+  CU_CHECK(c, cudaMemsetAsync(cnt, 0, sizeof(*cnt), c->stream));
+  halo_check_kernel<<<(unsigned)ceil_div64(c->n, 256), 256, 0, c->stream>>>(dptr<int4>(c->pts), dptr<int32_t>(c->nbr), c->K,
+                                                                          c->n, c->n_owned, x_lo, x_hi, halo, cnt);
+  KLAUNCH_CHECK(c);
+  unsigned long long h = 0;
+  RC_CHECK(read_back(c, &h, cnt, sizeof(h)));
+  *n_unresolved = (int64_t)h;
+  return 0;
+}
+
 int stage_export_knn(bseg_ctx* c, const bseg_params* p, int32_t* h_neigh, double* h_normals, double* h_curv)
 {
   const int64_t n = c->n;

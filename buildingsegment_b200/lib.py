@@ -20,7 +20,7 @@ EXPORTS = [
     "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
     "bseg_grow_planes", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster",
     "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
-    "bseg_point_count", "bseg_set_owned", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
+    "bseg_point_count", "bseg_plane_count", "bseg_set_owned", "bseg_set_origin", "bseg_device_results", "bseg_halo_check", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
 ]
 
 
@@ -93,7 +93,12 @@ def lib():
         L.bseg_stream.restype = vp
         L.bseg_point_count.argtypes = [vp]
         L.bseg_point_count.restype = i64
+        L.bseg_plane_count.argtypes = [vp]
+        L.bseg_plane_count.restype = C.c_int32
         L.bseg_set_owned.argtypes = [vp, i64]
+        L.bseg_set_origin.argtypes = [vp, vp]
+        L.bseg_device_results.argtypes = [vp, vp, vp, vp]
+        L.bseg_halo_check.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
         L.bseg_debug_sort_pairs.argtypes = [vp, vp, vp, i64, C.c_int]
         L.bseg_debug_exclusive_scan.argtypes = [vp, vp, i64]
         _LIB = L
@@ -163,6 +168,28 @@ class Context:
 
     def set_owned(self, n_owned):
         self._ck(lib().bseg_set_owned(self._h, int(n_owned)))
+
+    def n_planes(self):
+        return int(lib().bseg_plane_count(self._h))
+
+    def set_origin(self, origin):
+        """Shift the next clouds by `origin` (3 ints, the tile's minimum) instead of their own minimum; None resets."""
+        if origin is None:
+            self._ck(lib().bseg_set_origin(self._h, None))
+        else:
+            o = np.ascontiguousarray(origin, np.int32)
+            self._ck(lib().bseg_set_origin(self._h, o.ctypes.data))
+
+    def device_results(self):
+        """Device addresses (ints) of label[n], planeIdx[n] (original order) and the shifted cloud [n][3]."""
+        a, b, c_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(lib().bseg_device_results(self._h, C.addressof(a), C.addressof(b), C.addressof(c_)))
+        return a.value, b.value, c_.value
+
+    def halo_check(self, x_lo, x_hi, halo):
+        n = C.c_int64(0)
+        self._ck(lib().bseg_halo_check(self._h, int(x_lo), int(x_hi), int(halo), C.addressof(n)))
+        return int(n.value)
 
     # -- a4 + a5 ----------------------------------------------------------------------------------
     def knn_normals(self, p: Params, want_neigh=True, want_normals=True, want_curvature=False):

@@ -156,11 +156,24 @@ BSEG_API int bseg_get_timings(bseg_ctx* ctx, bseg_timings* out);
 BSEG_API int bseg_reset_counters(bseg_ctx* ctx);
 BSEG_API void* bseg_stream(bseg_ctx* ctx); /* cudaStream_t the context launches on */
 BSEG_API int64_t bseg_point_count(const bseg_ctx* ctx);
+BSEG_API int32_t bseg_plane_count(const bseg_ctx* ctx); /* planes of the last grow stage (vector<plane>::size(), my_function.cpp:216), -1 = none */
 
 /* ---- multi-GPU slabs (one context per rank; the exchange itself is the caller's NCCL) --------- */
 /* Declares that the first n_owned points of the cloud passed to bseg_set_points are this rank's
  * own slab and the rest are halo copies: halo points serve as neighbours only. */
 BSEG_API int bseg_set_owned(bseg_ctx* ctx, int64_t n_owned);
+/* Shift the next clouds by `origin` (the tile's minimum, the same on every rank) instead of each cloud's
+ * own minimum (TMC3.cpp:70-72 subtracts the minimum of the WHOLE cloud); NULL restores the default.
+ * out_min of bseg_set_points then reports the origin. */
+BSEG_API int bseg_set_origin(bseg_ctx* ctx, const int32_t origin[3]);
+/* Device pointers (original point order) to label / planeIdx / the shifted cloud of the last run, for the
+ * cross-slab label merge without a host round trip; valid until the next bseg_set_points. */
+BSEG_API int bseg_device_results(bseg_ctx* ctx, const int32_t** d_label, const int32_t** d_plane_idx,
+                                 const int32_t** d_xyz_shifted);
+/* Halo sufficiency: counts owned points within `halo` of the slab faces x_lo / x_hi (shifted units) whose
+ * K-th neighbour is farther than `halo` -- a closer point beyond the halo could exist; 0 = kNN rows and
+ * normals of all owned points equal those of the undivided cloud (given halo >= params.radius). */
+BSEG_API int bseg_halo_check(bseg_ctx* ctx, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved);
 
 /* ---- self-test hooks used by tests/ (exercise the hand-written primitives in isolation) ------- */
 BSEG_API int bseg_debug_sort_pairs(bseg_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);

@@ -1,0 +1,141 @@
+"""Multi-GPU slab logic (buildingsegment_b200/slabs.py) on the CPU: world_size 2 over gloo.
+
+The compute backend here is a stand-in built on the CPU oracle (test infrastructure); what is under test is the
+host logic of the N > 1 path: tile origin, halo exchange, halo sufficiency, the cross-slab label merge.
+  * kNN rows and normals of every OWNED point equal those of the undivided cloud (bit for bit);
+  * a plane that crosses the slab face ends up with ONE canonical (minimum) global id on both ranks;
+  * plane counts add up and the merge only ever lowers ids.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cases
+import oracle_lib as O
+
+
+class OracleBackend:
+    """Same contract as slabs.CudaBackend, computed by the oracle (CPU tests only)."""
+
+    def __init__(self, K=15, radius=100.0, max_nn=50):
+        self.K, self.radius, self.max_nn = K, radius, max_nn
+        self.last = None
+
+    def segment(self, xyz_local, n_owned, origin, x_lo, x_hi, halo):
+        xs = np.ascontiguousarray(xyz_local.numpy().astype(np.int64) - np.asarray(origin, np.int64)).astype(np.int32)
+        idx, d2 = O.knn(xs, self.max_nn, cell=100)
+        nrm, _, _ = O.normals(xs, idx, d2, self.radius, self.max_nn)
+        neigh = np.ascontiguousarray(idx[:, : self.K])
+        # halo sufficiency, as bseg_halo_check: owned points near a face whose K-th neighbour is beyond the halo
+        x = xs[:n_owned, 0].astype(np.int64)
+        near = (x - (x_lo - int(origin[0])) < halo) | ((x_hi - int(origin[0])) - x <= halo)
+        dk = d2[:n_owned, self.K - 1]
+        bad = int(np.count_nonzero(near & ((dk < 0) | (dk > halo * halo))))
+        if bad:
+            return None, 0, bad
+        g = O.grow(xs, nrm, neigh)
+        self.last = dict(xs=xs, neigh=neigh, nrm=nrm, grow=g)
+        return torch.from_numpy(g.label.astype(np.int32)), int(g.n_planes), 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, kw, halo, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from buildingsegment_b200 import slabs
+
+        xyz = getattr(cases, case)(**kw)
+        gid = np.arange(len(xyz))
+        cut = int(np.median(xyz[:, 0]))
+        lo = [int(xyz[:, 0].min()), cut][rank]
+        hi = [cut, int(xyz[:, 0].max()) + 1][rank]
+        m = (xyz[:, 0] >= lo) & (xyz[:, 0] < hi)
+        owned = torch.from_numpy(np.ascontiguousarray(xyz[m]))
+        be = OracleBackend()
+        r = slabs.segment_slab(be, owned, lo, hi, halo=halo)
+        # local index -> global index: owned first, then the halo copies (re-run the exchange to learn them)
+        hl, hr = slabs.exchange_halo(owned, lo, hi, r["halo"])
+        gid_own = gid[m]
+        other = [None, None]
+        dist.all_gather_object(other, gid_own)
+        src = np.concatenate([hl.numpy()[:, 3], hr.numpy()[:, 3]]).astype(np.int64)
+        gid_halo = other[1 - rank][src] if len(src) else np.empty(0, np.int64)
+        l2g = np.concatenate([gid_own, gid_halo])
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), gid_own=gid_own, l2g=l2g, neigh=be.last["neigh"][: len(gid_own)],
+                 nrm=be.last["nrm"][: len(gid_own)], labels=r["labels"].numpy(), total=r["n_planes_total"],
+                 ncomp=r["n_components"], n_local=r["n_planes_local"], halo=r["halo"], n_halo=r["n_halo"],
+                 local_label=be.last["grow"].label[: len(gid_own)])
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(case, kw, halo, tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, case, kw, halo, str(tmp_path)), nprocs=2, join=True)
+    return [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(2)]
+
+
+@pytest.mark.parametrize("case,kw", [("building", dict(n=30000, order="shuffled"))])
+def test_two_slabs_match_undivided_knn_and_merge(case, kw, tmp_path):
+    res = _run(case, kw, 400, tmp_path)
+    xyz = getattr(cases, case)(**kw)
+    P = O.pipeline(xyz)  # the undivided cloud (shifted by its own minimum == the tile origin)
+    n_lab = 0
+    for r in res:
+        g = r["gid_own"]
+        # neighbour rows: local indices -> global ids must equal the undivided rows, ties included
+        rows = r["l2g"][r["neigh"]]
+        assert np.array_equal(rows, P["neigh"][g]), "kNN rows of owned points differ from the undivided cloud"
+        assert np.array_equal(r["nrm"].view(np.int64), P["normals"][g].view(np.int64)), "normals differ"
+        assert r["n_halo"] > 0
+        n_lab += int(np.count_nonzero(r["labels"]))
+    total = int(res[0]["total"])
+    assert total == int(res[0]["n_local"]) + int(res[1]["n_local"]) == int(res[1]["total"])
+    assert int(res[0]["ncomp"]) == int(res[1]["ncomp"]) <= total
+    for r in res:  # canonical ids: never above the rank-offset local id, 0 stays 0
+        off = 0 if r is res[0] else int(res[0]["n_local"])
+        loc = r["local_label"].astype(np.int64)
+        assert np.array_equal(r["labels"] == 0, loc == 0)
+        assert np.all(r["labels"][loc > 0] <= loc[loc > 0] + off)
+    assert n_lab > 0
+
+
+def test_plane_across_the_face_gets_one_id(tmp_path):
+    """One flat plane cut in two: every labelled point of the big plane carries the same canonical id on both ranks."""
+    res = _run("grid_plane", dict(nx=120, ny=60, order="shuffled"), 400, tmp_path)
+    ids = [np.unique(r["labels"][r["labels"] > 0]) for r in res]
+    big = [np.bincount(r["labels"][r["labels"] > 0]).argmax() for r in res]
+    assert big[0] == big[1] == 1, (big, ids)
+    assert int(res[0]["ncomp"]) < int(res[0]["total"])
+
+
+def test_world_one_is_the_plain_path():
+    from buildingsegment_b200 import slabs
+
+    xyz = cases.building(n=20000, order="shuffled")
+    be = OracleBackend()
+    r = slabs.segment_slab(be, torch.from_numpy(xyz), int(xyz[:, 0].min()), int(xyz[:, 0].max()) + 1)
+    P = O.pipeline(xyz)
+    assert r["n_halo"] == 0 and r["n_planes_total"] == P["grow"].n_planes
+    assert np.array_equal(r["labels"].numpy(), P["grow"].label.astype(np.int64))
+
+
+def test_union_find_canonical_minimum():
+    from buildingsegment_b200.slabs import _union_find_min
+
+    c = _union_find_min(6, np.array([[5, 2], [2, 6], [3, 4]]))
+    assert c.tolist() == [0, 1, 2, 3, 3, 2, 2]
