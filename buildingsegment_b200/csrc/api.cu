@@ -234,8 +234,6 @@ BSEG_API int bseg_device_results(bseg_ctx* c, const int32_t** d_label, const int
   return 0;
 }
 
-int stage_halo_check(bseg_ctx* c, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved);  // knn.cu
-
 BSEG_API int bseg_halo_check(bseg_ctx* c, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved)
 {
   RC_CHECK(check_ctx(c));

@@ -172,6 +172,7 @@ int stage_bbox_shift(bseg_ctx* c);                           // bin.cu
 int stage_bin(bseg_ctx* c, const bseg_params* p);            // bin.cu
 int stage_knn(bseg_ctx* c, const bseg_params* p);            // knn.cu
 int stage_export_knn(bseg_ctx* c, const bseg_params* p, int32_t* h_neigh, double* h_normals, double* h_curv);
+int stage_halo_check(bseg_ctx* c, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved);  // knn.cu
 int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* h_neigh, const double* h_normals);
 int stage_grow(bseg_ctx* c, const bseg_params* p);           // grow.cu
 void grow_host_free(bseg_ctx* c);
