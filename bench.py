@@ -9,7 +9,7 @@ A step = one pass of the whole hot path over one synthetic cloud:
 `value`  : cloud already in HBM when the timed region starts (bseg_set_points_device + bseg_run_device)
 `e2e`    : through bseg_segment_host with pinned HOST buffers, H2D of the cloud and D2H of the shifted
            cloud, labels and PNG bytes inside the timed region
-N > 1    : one process per GPU (torchrun); every rank owns one 500 m x-slab of the city tile (weak scaling):
+N > 1    : one process per GPU (torchrun); every rank owns one 200 m C2-like x-slab of the city tile (weak scaling):
            shared tile origin, NCCL halo exchange with the neighbour ranks, halo sufficiency check, per-slab
            segmentation, cross-slab label merge (buildingsegment_b200/slabs.py, DESIGN.md "multi-GPU")
 --impl reference : the CPU path (oracle/_ref = the reference's own grower/raster lines, oracle port for
@@ -101,15 +101,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+SLAB_M = 200.0  # slab width of the multi-GPU tile, metres
+
+
 def make_workload(name, n, rank=0, world=1):
     """Synthetic cloud of config `name` at `n` points per rank (int32 mm, unshifted)."""
     from buildingsegment_b200 import synth
 
     if world > 1:
-        # C5-style: every rank owns one 500 m block-slab of the city tile, offset along x
+        # C5-style city tile = C2-like blocks side by side: rank r owns the 200 m block at x = r * 200 m, so the
+        # per-GPU work is the N = 1 workload (same generator, another seed) plus the exchange with the neighbours
         rng = np.random.default_rng(1005 + rank)
-        nb = max(4, int(40 * (500.0 / 200.0) ** 2))
-        pts = synth._block(rng, n, rank * 500.0, 0.0, 500.0, nb, 0.15, "shuffled")
+        pts = synth._block(rng, n, rank * SLAB_M, 0.0, SLAB_M, 40, 0.15, "shuffled")
         return np.ascontiguousarray(synth.to_mm(pts))
     return synth.make(name, n)
 
@@ -208,7 +211,7 @@ def run_ours(args):
 
     n = args.points
     xyz = make_workload(args.workload, n, rank, world)
-    x_lo, x_hi = rank * 500_000, (rank + 1) * 500_000
+    x_lo, x_hi = int(rank * SLAB_M * 1000), int((rank + 1) * SLAB_M * 1000)
     if world > 1:  # this rank's slab of the city tile: x in [x_lo, x_hi) mm
         xyz = np.ascontiguousarray(xyz[(xyz[:, 0] >= x_lo) & (xyz[:, 0] < x_hi)])
     n = len(xyz)
@@ -339,7 +342,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": f"{args.workload} synthetic suburban block, {n} points per GPU, reference defaults "
                                    f"(K=15, r=100 mm, max_nn=50, 300 mm, 0.88, 400)" if world == 1 else
-                                   f"C5-style city tile, one 500 m x-slab of ~{n} points per GPU (tile origin, NCCL halo "
+                                   f"C5-style city tile, one {int(SLAB_M)} m C2-like x-slab of ~{n} points per GPU (tile origin, NCCL halo "
                                    f"exchange, halo check, per-slab segmentation, cross-slab label merge), reference defaults",
                        "points_per_gpu": n, "l2": "inputs larger than L2 (cloud + neighbour rows >> 126 MB)",
                        "grow_engine": "sweeper + speculative growers (grow_mode 0)", "planes": int(npl),
@@ -374,7 +377,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--ref-sample", type=int, default=60_000)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--halo", type=int, default=500, help="slab halo width, mm (N > 1)")
+    ap.add_argument("--halo", type=int, default=2000, help="initial slab halo width, mm (N > 1); doubled until sufficient")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
