@@ -34,7 +34,7 @@ struct GrowArgs {
   const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
   uint32_t* atby;    // [n] lowest in-flight transaction that assumed the point taken (early notification)
 };
-enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32 };
+enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32, GF_NOPAIR = 64 };
 
 // ---- "assumed taken" list of a speculative transaction --------------------------------------------------
 // A point that is free in the committed state and passes the geometric tests, but is reserved by a LOWER
@@ -495,6 +495,246 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     id = nid; stt = nstt; rs = nrs; mine = nmine; p = np; n0 = m0; n1 = m1; n2 = m2;
     has_dup = ndup;
     if (MODE == MODE_SPEC && (steps & 7) == 0) {
+      if (((volatile uint8_t*)A.doom)[seed_i]) {
+        out = TX_DOOMED;
+        break;
+      }
+      if (*(volatile unsigned long long*)A.stop_flag) break;  // the head finished: let the sweeper commit
+    }
+  }
+  steps_out += steps;
+  return out;
+}
+
+// ---- two nodes per warp step (speculative engine, K <= 16) ------------------------------------------------
+// Three Broad() calls out of four accept nothing (the neighbours are already in the plane): the model is
+// unchanged by such a call (same sums, same length), and the node visited next is simply the next entry of
+// the current DFS frame.  So half-warp 0 tests the node A that is due, half-warp 1 the node B that follows
+// if A accepts nothing, both against the same model.  When A accepts nothing B's outcome IS the next call
+// of the reference, otherwise B's tests are discarded (B stays in its frame).  Exactly the calls of the
+// sequential run, in the same order; only their latency is shared.
+__device__ __forceinline__ void tx_reserve_lane(const GrowArgs& A, int32_t id, uint32_t rs, uint32_t me, uint32_t fr,
+                                                int32_t pw, bool& ok, bool& relied, bool& fired, uint32_t& old)
+{
+  // lane wants `id`: decide from the gathered reservation `rs` (see tx_run)
+  if (rs < fr) {  // stale reservation of a transaction the sweeper has passed: free; replace it (rare)
+    uint32_t cur = rs;
+    for (;;) {
+      if (cur < fr) {
+        const uint32_t seen = atomicCAS(A.res + id, cur, me);
+        if (seen == cur) {
+          old = RES_FREE;
+          break;
+        }
+        cur = seen;
+      } else {
+        old = atomicMin(A.res + id, me);
+        if (old >= fr)
+          break;
+        cur = old;
+      }
+    }
+    if (old < me) {
+      ok = false;
+      relied = true;
+    } else {
+      if (old != RES_FREE) A.doom[old] = 1;
+      if (pw > (int32_t)me) A.doom[pw] = 1;
+    }
+    old = RES_FREE;
+  } else if (rs < me) {
+    ok = false;
+    relied = true;
+  } else {
+    old = atomicMin(A.res + id, me);  // result looked at after the next gather is on its way
+    fired = true;
+  }
+}
+
+template <int KT, class Store>
+__device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, unsigned long long budget,
+                                 int lane, unsigned long long& steps_out)
+{
+  const int K = KT ? KT : A.K;  // <= 16: one half-warp holds a row
+  const uint32_t me = (uint32_t)seed_i;
+  const uint32_t fr = (uint32_t)A.frontier;
+  const bool fastdiv = (A.flags & GF_FASTDIV) != 0;
+  const int half = lane >> 4, sl = lane & 15;
+  unsigned long long steps = 0;
+  TxOutcome out = TX_RUNNING;
+
+  // the node of this lane's half and neighbour column `sl` of it
+  bool hasB = !t.depth0 && t.have_top && t.top_cur < t.top_end;
+  uint32_t nodeB = hasB ? (uint32_t)st.get(t.top_cur) : 0u;
+  int32_t id = -1, stt = 0;
+  uint32_t rs = RES_FREE;
+  bool mine = false, has_dup = false;
+  int4 p = make_int4(0, 0, 0, 0);
+  double n0 = 0, n1 = 0, n2 = 0;
+  {
+    const bool act = half == 0 || hasB;
+    const uint32_t node = half ? nodeB : t.node;
+    if (act) has_dup = __ldg(A.rowdup + node) != 0;
+    if (act && sl >= 1 && sl < K) id = __ldg(A.nbr + (int64_t)node * K + sl);
+    if (id >= 0) {
+      stt = __ldcg(A.state + id);
+      rs = __ldcg(A.res + id);
+      p = __ldg(A.pts + id);
+      const double* nr = A.nrm + 3 * (int64_t)id;
+      n0 = __ldg(nr); n1 = __ldg(nr + 1); n2 = __ldg(nr + 2);
+    }
+  }
+  while (steps < budget) {
+    if (!st.reserve((t.len > t.n_at ? t.len : t.n_at) + 3 * K, lane)) {  // before anything is marked
+      out = TX_OVERFLOW;
+      break;
+    }
+    bool want = id >= 0 && stt == -1 && rs != me && !mine && geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
+    if (__any_sync(FULL_MASK, has_dup && want)) {  // a row that names a point twice: first occurrence only
+      const unsigned long long key = want ? (((unsigned long long)half << 32) | (uint32_t)id)
+                                          : ((1ull << 40) | (unsigned long long)lane);
+      const uint32_t same = __match_any_sync(FULL_MASK, key);
+      want = want && ((same & lanemask_lt()) == 0);
+    }
+    // ---- node A ----
+    bool ok = false, relied = false, fired = false;
+    uint32_t old = RES_FREE;
+    if (half == 0 && want) {
+      ok = true;
+      tx_reserve_lane(A, id, rs, me, fr, p.w, ok, relied, fired, old);
+    }
+    const uint32_t accA = __ballot_sync(FULL_MASK, ok);
+    const int cntA = __popc(accA);
+    if (t.depth0 && cntA < K - 1) {
+      if (ok) st.put(t.len + __popc(accA & lanemask_lt()), id);
+      __syncwarp();
+      t.len += cntA;
+      ++steps;
+      out = TX_FAILED;  // :238-239 (under assumptions: the sweeper decides)
+      break;
+    }
+    // ---- node B counts only when A accepted nothing ----
+    const bool useB = hasB && cntA == 0;
+    if (useB && half == 1 && want) {
+      ok = true;
+      tx_reserve_lane(A, id, rs, me, fr, p.w, ok, relied, fired, old);
+    }
+    const uint32_t acc = useB ? __ballot_sync(FULL_MASK, ok) : accA;  // accepted lanes of the LAST call made
+    const int cnt = __popc(acc);
+    steps += useB ? 2 : 1;
+    {  // assumed-taken records of the calls that were made
+      const bool rec = relied && (half == 0 || useB);
+      const uint32_t rel = __ballot_sync(FULL_MASK, rec);
+      if (rel) {
+        if (rec) {
+          st.put_at(t.n_at + __popc(rel & lanemask_lt()), id);
+          atomicMin(A.atby + id, me);
+        }
+        t.n_at += __popc(rel);
+      }
+    }
+    if (ok) st.put(t.len + __popc(acc & lanemask_lt()), id);
+    __syncwarp();
+    t.depth0 = 0;
+    // ---- DFS bookkeeping (:252-255) ----
+    if (useB) ++t.top_cur;  // B was the next entry of the frame: consumed
+    const int64_t s0 = t.len;
+    t.len += cnt;
+    uint32_t next = 0, nextB = 0;
+    bool have_next = false, have_nextB = false;
+    if (cnt > 0) {
+      if (t.have_top && t.top_cur < t.top_end) {
+        if (lane == 0) st.push(t.sp, make_int2((int)t.top_cur, (int)t.top_end));
+        ++t.sp;
+      }
+      t.top_cur = s0 + 1;  // the first accepted point is visited right away
+      t.top_end = t.len;
+      t.have_top = 1;
+      const int b0 = __ffs(acc) - 1;
+      next = (uint32_t)__shfl_sync(FULL_MASK, id, b0);
+      have_next = true;
+      if (cnt >= 2) {  // the second accepted point follows if the first accepts nothing
+        const int b1 = __ffs(acc & (acc - 1)) - 1;
+        nextB = (uint32_t)__shfl_sync(FULL_MASK, id, b1);
+        have_nextB = true;
+      }
+    } else {
+      while (t.have_top && t.top_cur == t.top_end) {
+        if (t.sp > 0) {
+          --t.sp;
+          __syncwarp();
+          const int2 f = st.pop(t.sp);
+          t.top_cur = f.x;
+          t.top_end = f.y;
+        } else {
+          t.have_top = 0;
+        }
+      }
+      if (t.have_top) {
+        next = (uint32_t)st.get(t.top_cur);
+        ++t.top_cur;
+        have_next = true;
+        if (t.top_cur < t.top_end) {
+          nextB = (uint32_t)st.get(t.top_cur);
+          have_nextB = true;
+        }
+      }
+    }
+    // ---- next gathers first, then the model ----
+    int32_t nid = -1;
+    bool ndup = false;
+    {
+      const bool act = half == 0 ? have_next : have_nextB;
+      const uint32_t node = half ? nextB : next;
+      if (act) ndup = __ldg(A.rowdup + node) != 0;
+      if (act && sl >= 1 && sl < K) nid = __ldg(A.nbr + (int64_t)node * K + sl);
+    }
+    if (cnt > 0) model_accumulate(t.m, acc, p, n0, n1, n2);
+    int32_t nstt = 0;
+    uint32_t nrs = RES_FREE;
+    bool nmine = false;
+    int4 np = make_int4(0, 0, 0, 0);
+    double m0 = 0, m1 = 0, m2 = 0;
+    if (nid >= 0) {
+      nstt = __ldcg(A.state + nid);
+      nrs = __ldcg(A.res + nid);
+      np = __ldg(A.pts + nid);
+      const double* nr = A.nrm + 3 * (int64_t)nid;
+      m0 = __ldg(nr); m1 = __ldg(nr + 1); m2 = __ldg(nr + 2);
+    }
+    {  // points accepted a moment ago are ours whatever the gathered reservation says
+      uint32_t a = acc;
+      while (a) {
+        const int b = __ffs(a) - 1;
+        a &= a - 1;
+        nmine |= nid == __shfl_sync(FULL_MASK, id, b);
+      }
+    }
+    if (cnt > 0) {  // a call that accepts nothing leaves sums and length, hence the model, as they are
+      if (fastdiv) model_update_fast(t.m, t.len);
+      else model_update(t.m, t.len);
+    }
+    {
+      bool race = false;
+      if (fired) {
+        if (old < me && old >= fr) race = true;                  // a lower transaction reserved it in between
+        else if (old != RES_FREE && old >= fr) A.doom[old] = 1;  // stolen from a higher transaction: it is void
+        if (p.w > (int32_t)me) A.doom[p.w] = 1;                  // the transaction seeded at this point lost its seed
+      }
+      if (__any_sync(FULL_MASK, race)) {
+        out = TX_DOOMED;
+        break;
+      }
+    }
+    if (!have_next) {
+      out = TX_FINISHED;
+      break;
+    }
+    t.node = next;
+    hasB = have_nextB;
+    id = nid; stt = nstt; rs = nrs; mine = nmine; p = np; n0 = m0; n1 = m1; n2 = m2;
+    has_dup = ndup;
+    if ((steps & 7) < 2) {
       if (((volatile uint8_t*)A.doom)[seed_i]) {
         out = TX_DOOMED;
         break;

@@ -383,8 +383,11 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   unsigned long long steps = 0;
   const bool is_head = (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT];
   const unsigned long long t0 = is_head ? gtimer() : 0ull;
-  const TxOutcome out = A.K == 15 ? tx_run<MODE_SPEC, 15>(A, st, t, seed_i, budget, false, lane, steps)
-                                  : tx_run<MODE_SPEC, 0>(A, st, t, seed_i, budget, false, lane, steps);
+  // K <= 16: two DFS nodes per warp step (grow.cuh tx_run_pair); BSEG_GROW_FLAGS bit 6 forces the single-node engine
+  const bool pair = A.K <= 16 && !(A.flags & GF_NOPAIR);
+  const TxOutcome out = pair ? (A.K == 15 ? tx_run_pair<15>(A, st, t, seed_i, budget, lane, steps)
+                                          : tx_run_pair<0>(A, st, t, seed_i, budget, lane, steps))
+                             : tx_run<MODE_SPEC, 0>(A, st, t, seed_i, budget, false, lane, steps);
   __syncwarp();
   if (lane == 0 && is_head) {
     S.sc[SC_HEAD_STEPS] += steps;
