@@ -320,12 +320,26 @@ def run_ours(args):
                 stages[k] = {"ms": round(ms, 3), "bytes_per_point": b, "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
             else:
                 stages[k] = {"ms": round(ms, 3)}
-        # the kNN kernel is the single largest launch; the grower is many small launches (latency-bound)
-        roof_stage = "knn" if "knn" in stages and "gbs" in stages["knn"] else dom
-        rs = stages[roof_stage]
-        roofline = {"bound": "hbm", "kernel": "knn_cells_kernel (exact kNN + fused PCA normal)" if roof_stage == "knn" else roof_stage,
-                    "achieved": rs.get("gbs"), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": rs.get("frac"), "traffic": None, "dominant_stage": dom, "stages": stages}
+        # dominant kernel: spec_grow_kernel (the grower's slices).  Algorithmic bytes of one Broad() call: the
+        # node's row (4K) + per neighbour position 12, normal 24, state/label/reservation ~10; calls
+        # per launch = (committed + released) calls / launches; duration = CUDA events around every slice.
+        slice_ms = float(last_t["grow_slice_ms"])
+        calls = int(last_t["grow_steps"]) - int(last_t["grow_tiny_tx"]) + int(last_t["grow_wasted_steps"])
+        slices = max(1, int(last_t["grow_rounds"]) - 1)
+        ach = BYTES_PER_POINT["grow"] * calls / (slice_ms * 1e-3) / 1e9 if slice_ms > 0 else None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f).get("spec_grow_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": "spec_grow_kernel (plane grower slices; dependent-gather latency bound, "
+                                              "see DESIGN.md 6)",
+                    "achieved": round(ach, 2) if ach else None, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": round(ach / peak, 5) if ach else None, "traffic": traffic,
+                    "launches": slices, "avg_launch_ms": round(slice_ms / slices, 3),
+                    "bytes_per_call": BYTES_PER_POINT["grow"], "calls_per_launch": round(calls / slices, 1),
+                    "dominant_stage": dom, "stages": stages}
         cpu = None
         if world == 1 and not args.no_cpu:
             import oracle_lib as O

@@ -399,9 +399,9 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
     sl.steps += steps;
     // a depth-0 failure under assumptions is a tiny transaction: the sweeper's job
     sl.status = out == TX_RUNNING ? ST_RUNNING : (out == TX_FINISHED ? ST_FINISHED : ST_DEAD);
-    if (out == TX_FINISHED && (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT]) {
-      *(volatile unsigned long long*)&S.sc[SC_STOP] = 1ull;
-    }
+    // the head sets the pace: when it finishes OR has used its budget the slice is over for everybody
+    // (a slot that keeps running after the head has stopped only delays the sweeper)
+    if (is_head) *(volatile unsigned long long*)&S.sc[SC_STOP] = 1ull;
   }
 }
 
@@ -849,6 +849,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   }
 
   int64_t F = 0, rounds = 0, stalls = 0, fallbacks = 0;
+  const bool dbg = getenv("BSEG_DEBUG") != nullptr;
+  cudaEvent_t pe[5];
+  float pt[4] = {0, 0, 0, 0};
+  for (auto& e : pe) cudaEventCreate(&e);
   unsigned long long ctl[32] = {0};
   uint32_t* d_ncand = reinterpret_cast<uint32_t*>(&S.sc[SC_NCAND]);
   const unsigned sb = (unsigned)((S.G + GW - 1) / GW);
@@ -858,6 +862,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     const int64_t C = n - F < CMAX ? n - F : CMAX;
     const unsigned gb = (unsigned)ceil_div64(C, TPB);
     S.A.frontier = F;
+    cudaEventRecord(pe[0], c->stream);
     if (rounds > 0) {
       spec_mark_release_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
@@ -865,6 +870,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       KLAUNCH_CHECK(c);
       spec_release_slots_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
+      cudaEventRecord(pe[1], c->stream);
       spec_scout_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
       KLAUNCH_CHECK(c);
       RC_CHECK(bseg_exclusive_scan_u32(c, S.flag, C, d_ncand));
@@ -872,9 +878,11 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       KLAUNCH_CHECK(c);
       spec_pop_free_kernel<<<1, 1, 0, c->stream>>>(S, F);
       KLAUNCH_CHECK(c);
+      cudaEventRecord(pe[2], c->stream);
       spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget);
       KLAUNCH_CHECK(c);
     }
+    cudaEventRecord(pe[3], c->stream);
     if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     else spec_sweep_kernel<32><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     KLAUNCH_CHECK(c);
@@ -882,8 +890,15 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     KLAUNCH_CHECK(c);
     spec_reset_log_kernel<<<1, 1, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
+    cudaEventRecord(pe[4], c->stream);
     ++rounds;
     RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
+    if (rounds > 1)
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pe[k], pe[k + 1]);
+        pt[k] += ms;
+      }
     if (ctl[CTL_ERR])
       break;
     const int64_t Fn = (int64_t)ctl[CTL_FRONTIER];
@@ -911,7 +926,14 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     if (rounds > 8 * n + 1024)
       return bseg_fail(c, BSEG_E_STATE, "plane grower: no progress");
   }
-  if (getenv("BSEG_DEBUG"))
+  if (dbg) {
+    fprintf(stderr, "[bseg] rounds %lld: release %.1f ms, scout+assign %.1f ms, slices %.1f ms, sweep+apply %.1f ms\n", (long long)rounds,
+            pt[0], pt[1], pt[2], pt[3]);
+  }
+  for (auto& e : pe) cudaEventDestroy(e);
+  c->tm.grow_slice_ms = pt[2];
+  c->tm.grow_sweep_ms = pt[3];
+  if (dbg)
     fprintf(stderr, "[bseg] sweeper: front %.1f ms, slow path %.1f ms (%llu), fast path %.1f ms\n", ctl[8 + SC_T_FRONT] / 1e6,
             ctl[8 + SC_T_SLOW] / 1e6, ctl[8 + SC_N_SLOW], ctl[8 + SC_T_FAST] / 1e6);
   c->tm.grow_rounds = rounds;

@@ -36,7 +36,7 @@ class Params(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_float) for k in
                 ("h2d", "bbox_keys", "sort", "cells", "knn", "knn_fallback", "normals", "grow", "finalize",
-                 "raster", "d2h", "total")] + \
+                 "raster", "d2h", "total", "grow_slice_ms", "grow_sweep_ms")] + \
                [(k, C.c_int64) for k in ("n_unresolved", "grow_steps", "grow_rounds", "kernel_launches",
                                          "n_big_cells", "grow_wasted_steps", "grow_sweep_iters",
                                          "grow_tiny_tx", "grow_seq_fallbacks", "grow_head_steps", "grow_head_ns",

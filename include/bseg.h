@@ -64,6 +64,7 @@ typedef struct bseg_params {
 /* Per-stage device time of the last call, milliseconds (CUDA events on the context's stream). */
 typedef struct bseg_timings {
   float h2d, bbox_keys, sort, cells, knn, knn_fallback, normals, grow, finalize, raster, d2h, total;
+  float grow_slice_ms, grow_sweep_ms; /* parallel engine: device time of the grower slices / of sweeper + mark log */
   int64_t n_unresolved;   /* queries that needed the ring-expansion fallback */
   int64_t grow_steps;     /* Broad() calls executed (committed work)          */
   int64_t grow_rounds;    /* rounds of the speculative engine                 */
