@@ -289,7 +289,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.frontier = 0;
   {
     const char* gf = getenv("BSEG_GROW_FLAGS");  // tuning switches of the step engine (grow.cuh GF_*)
-    A.flags = gf ? atoi(gf) : (GF_ROWDUP | GF_FASTDIV);
+    A.flags = gf ? atoi(gf) : (GF_ROWDUP | GF_FASTDIV | GF_ROW_L1);
   }
   RC_CHECK(dev_ensure(c, c->g_rowdup, (size_t)n + 64));
   A.rowdup = dptr<uint8_t>(c->g_rowdup);

@@ -558,7 +558,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
   const int K = KT ? KT : A.K;  // <= 16: one half-warp holds a row
   const uint32_t me = (uint32_t)seed_i;
   const uint32_t fr = (uint32_t)A.frontier;
-  const bool fastdiv = (A.flags & GF_FASTDIV) != 0;
+  const bool fastdiv = (A.flags & GF_FASTDIV) != 0, row_l1 = (A.flags & GF_ROW_L1) != 0;
   const int half = lane >> 4, sl = lane & 15;
   unsigned long long steps = 0;
   TxOutcome out = TX_RUNNING;
@@ -701,6 +701,10 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
       np = __ldg(A.pts + nid);
       const double* nr = A.nrm + 3 * (int64_t)nid;
       m0 = __ldg(nr); m1 = __ldg(nr + 1); m2 = __ldg(nr + 2);
+      if (row_l1) {  // the row of a neighbour that gets accepted is needed one step later
+        prefetch_l1(A.nbr + (int64_t)nid * K);
+        prefetch_l1(A.nbr + (int64_t)nid * K + (K - 1));
+      }
     }
     {  // points accepted a moment ago are ours whatever the gathered reservation says
       uint32_t a = acc;
