@@ -41,6 +41,7 @@ constexpr int TPB = 256;
 constexpr int GW = 4;          // warps per block in slot kernels
 constexpr int SWEEP_T = 1024;  // seeds per sweeper batch == threads of the sweeper block
 constexpr int SWEEP_WORDS = 128;  // bitmap words (4096 seeds) scanned per batch for up to SWEEP_T live seeds
+constexpr int PT_CACHE = 256;      // sweeper: cached page-table entries of the slot being committed
 constexpr int HT = 16384;      // sweeper hash table slots (keys + vals = 128 KB of shared memory)
 
 enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING = 4 };
@@ -415,7 +416,8 @@ struct SweepShared {
   unsigned long long c_off, c_pl;
   int warp_sum[32];
   int n_live;
-  int64_t last_seed;
+  int64_t last_seed, last_open, sp_seed;
+  uint32_t ptc[PT_CACHE];  // page table of the slot being committed
   uint32_t words[SWEEP_WORDS];
   int pref[SWEEP_WORDS];
 };
@@ -444,9 +446,10 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   }
   if (tid == 0) sh.stop = 0;
   __syncthreads();
-
   unsigned long long t_front = 0, t_slow = 0, t_fast = 0, n_slow = 0;
-  while (F < A.n) {
+  bool stop = false;
+
+  while (F < A.n && !stop) {
     ++iters;
     const unsigned long long ti0 = gtimer();
     // ---- the next live seeds: scan the alive bitmap (original index order, a superset of the free points) ----
@@ -477,9 +480,9 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
     __syncthreads();
     const int n_live = sh.n_live;
     const int n_eval = n_live < SWEEP_T ? n_live : SWEEP_T;
+    const int64_t stretch_end = (base + 32LL * SWEEP_WORDS < A.n) ? base + 32LL * SWEEP_WORDS : A.n;
     if (n_live == 0) {  // nothing free in this stretch
-      F = base + 32LL * SWEEP_WORDS;
-      if (F > A.n) F = A.n;
+      F = stretch_end;
       __syncthreads();
       continue;
     }
@@ -496,7 +499,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       const int bit = __fns(sh.words[lo], 0, tid - sh.pref[lo] + 1);
       i = base + 32LL * lo + bit;
     }
-    if (tid == n_eval - 1) sh.last_seed = i;
+    if (tid == n_eval - 1) sh.last_seed = i;  // the seed after it starts the next batch when all of these are done
     uint32_t s = 0, want = 0;
     int32_t slot = -1;
     bool live = false, grower = false;
@@ -527,218 +530,259 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         grower = __popc(want) == K - 1;  // :238 -- every neighbour accepted
       }
     }
-    if (tid == 0) {
-      sh.first_special = SWEEP_T;
-      sh.first_over = SWEEP_T;
-      sh.first_conf = SWEEP_T;
-    }
-    __syncthreads();
-    if (!valid || grower) atomicMin(&sh.first_special, tid);  // (threads beyond the live list end the batch)
-    // a slot whose seed is not a grower at its turn is void (the state only gets more taken: it never will be)
-    if (valid && slot >= 0 && !grower) A.doom[i] = 1;
-    __syncthreads();
-    const int first_special = sh.first_special;
-    const unsigned long long ti1 = gtimer();
-    t_front += ti1 - ti0;
+    t_front += gtimer() - ti0;
 
-    if (first_special == 0) {
-      ++n_slow;
-      // ---- slow path: the first live seed is a grower at its turn ----
+    // ---- sub-steps on this batch: threads [0, done) are finished; after every commit the others only
+    //      re-gather the states of what they already know (one load level instead of four) ----
+    int done = 0;
+    while (done < n_eval && !stop) {
+      const unsigned long long ti1 = gtimer();
       if (tid == 0) {
-        sh.sp_slot = slot;
-        sh.sp_bad = 0;
-        sh.last_seed = i;
+        sh.first_special = SWEEP_T;
+        sh.first_over = SWEEP_T;
+        sh.first_conf = SWEEP_T;
       }
       __syncthreads();
-      F = sh.last_seed;  // everything before it is taken
-      const int g = sh.sp_slot;
-      if (g < 0) {  // no slot: the scout gives it one
-        if (tid == 0) S.sc[SC_STUCK] = 1;
-        break;
-      }
-      Slot& sl = S.slots[g];
-      const int status = sl.status;
-      const bool doomed = ((volatile uint8_t*)A.doom)[F] != 0;
-      if (status != ST_FINISHED || doomed) {
-        // still growing (the head), or void: released next round, then the scout re-assigns it
-        if (tid == 0 && status != ST_RUNNING) S.sc[SC_STUCK] = 1;
-        break;
-      }
-      const PagedStore st = slot_store(S, g);
-      const int64_t len = sl.t.len, n_at = sl.t.n_at;
-      // every point it treated as taken (reserved by a lower transaction at the time) must be taken now
-      // ... and every point it accepted must still be free (a lower tiny transaction may have marked it)
-      bool bad = false;
-      for (int64_t k = tid; k < n_at; k += SWEEP_T) bad |= __ldcg(A.state + st.get_at(k)) == -1;
-      for (int64_t e = 1 + tid; e < len; e += SWEEP_T) bad |= __ldcg(A.state + st.get(e)) != -1;
-      if (bad) sh.sp_bad = 1;
+      const bool act = valid && tid >= done;
+      if (act && grower) atomicMin(&sh.first_special, tid);
+      // a slot whose seed is not a grower at its turn is void (the state only gets more taken: it never will be)
+      if (act && slot >= 0 && !grower) A.doom[i] = 1;
       __syncthreads();
-      if (sh.sp_bad) {
-        if (tid == 0) {
-          A.doom[F] = 1;
-          S.sc[SC_STUCK] = 1;
-          atomicAdd(&S.sc[SC_ATFAIL], 1ull);
+      int first_special = sh.first_special;
+      if (first_special > n_eval) first_special = n_eval;
+
+      if (first_special == done) {
+        // ---- slow path: the first unfinished seed is a grower at its turn ----
+        ++n_slow;
+        if (tid == done) {
+          sh.sp_slot = slot;
+          sh.sp_bad = 0;
+          sh.sp_seed = i;
         }
-        break;
-      }
-      if (len > A.th_count) {  // :199-202
+        __syncthreads();
+        const int64_t Fs = sh.sp_seed;  // everything before it is done
+        F = Fs;
+        const int g = sh.sp_slot;
+        if (g < 0) {  // no slot: the scout gives it one
+          if (tid == 0) S.sc[SC_STUCK] = 1;
+          stop = true;
+          break;
+        }
+        Slot& sl = S.slots[g];
+        const int status = sl.status;
+        const bool doomed = ((volatile uint8_t*)A.doom)[Fs] != 0;
+        if (status != ST_FINISHED || doomed) {
+          // still growing (the head), or void: released next round, then the scout re-assigns it
+          if (tid == 0 && status != ST_RUNNING) S.sc[SC_STUCK] = 1;
+          stop = true;
+          break;
+        }
+        const PagedStore st = slot_store(S, g);
+        const int64_t len = sl.t.len, n_at = sl.t.n_at;
+        // the slot's page table goes to shared memory: one dependent load level less in every loop below
+        if (tid < PT_CACHE && tid < sl.n_pages) sh.ptc[tid] = st.ptab[tid];
         if (tid == 0) {
           sh.c_off = A.ctl[CTL_POOL];
           sh.c_pl = A.ctl[CTL_PLANES];
         }
         __syncthreads();
-        const unsigned long long off = sh.c_off, pl = sh.c_pl;
-        if ((int64_t)(off + len) > A.pool_cap - A.n - 2 || (int64_t)pl >= A.planes_cap) {
-          if (tid == 0) A.ctl[CTL_ERR] = 2;
+        auto at = [&](int64_t e) -> size_t {
+          const int64_t pg = e >> PAGE_SHIFT;
+          const uint32_t page = pg < PT_CACHE ? sh.ptc[pg] : st.ptab[pg];
+          return ((size_t)page << PAGE_SHIFT) + (size_t)(e & (PAGE_SIZE - 1));
+        };
+        // every point it treated as taken (reserved by a lower transaction at the time) must be taken now,
+        // and every point it accepted must still be free (a lower tiny transaction may have marked it)
+        bool bad = false;
+        for (int64_t k = tid; k < n_at; k += SWEEP_T) bad |= __ldcg(A.state + S.pool.at_pages[at(k)]) == -1;
+        for (int64_t e = 1 + tid; e < len; e += SWEEP_T) bad |= __ldcg(A.state + S.pool.list_pages[at(e)]) != -1;
+        if (bad) sh.sp_bad = 1;
+        __syncthreads();
+        if (sh.sp_bad) {
+          if (tid == 0) {
+            A.doom[Fs] = 1;
+            S.sc[SC_STUCK] = 1;
+            atomicAdd(&S.sc[SC_ATFAIL], 1ull);
+          }
+          stop = true;
           break;
         }
-        for (int64_t e = tid; e < len; e += SWEEP_T) {
-          const int32_t id = st.get(e);
-          A.pool[off + e] = id;
-          if (e >= 1) {
-            A.state[id] = (int32_t)F;
-            A.res[id] = RES_FREE;
-            const int32_t w = __ldg(&A.pts[id].w);
-            atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
-          }
-        }
-        if (tid == 0) {
-          PlaneRec r;
-          r.seed = (int32_t)F; r.pad = 0;
-          r.off = (int64_t)off; r.len = len;
-          r.nrm[0] = sl.t.m.mn0; r.nrm[1] = sl.t.m.mn1; r.nrm[2] = sl.t.m.mn2;
-          r.ctr[0] = sl.t.m.mc0; r.ctr[1] = sl.t.m.mc1; r.ctr[2] = sl.t.m.mc2; r.pad2 = 0;
-          A.planes[pl] = r;
-          A.ctl[CTL_POOL] = off + (unsigned long long)len;
-          A.ctl[CTL_PLANES] = pl + 1;
-        }
-      } else {  // roll back (:203-209): nothing persists
-        for (int64_t e = 1 + tid; e < len; e += SWEEP_T) {
-          const int32_t pt = st.get(e);
-          if (atomicCAS(A.res + pt, (uint32_t)F, RES_FREE) == (uint32_t)F) unreserve_notify(A.atby, A.slotof, A.doom, pt);
-        }
-      }
-      if (tid == 0) {
-        A.ctl[CTL_STEPS] += sl.steps;
-        A.ctl[CTL_TX] += 1;
-      }
-      __threadfence();
-      __syncthreads();
-      // give the slot back; its pages are returned by the whole block
-      if (tid == 0) {
-        const int np = sl.n_pages;
-        sh.sp_np = np;
-        sh.c_off = np > 0 ? atomicAdd(S.pool.n_free, (unsigned long long)np) : 0ull;
-      }
-      __syncthreads();
-      for (int k = tid; k < sh.sp_np; k += SWEEP_T) S.pool.free_pages[sh.c_off + k] = st.ptab[k];
-      __syncthreads();
-      if (tid == 0) {
-        sl.n_pages = 0;
-        slot_free(S, g);
-      }
-      __threadfence();
-      __syncthreads();
-      F += 1;  // the seed is done (its own point stays unmarked, :191)
-      t_slow += gtimer() - ti1;
-      continue;
-    }
-
-    // ---- fast path: seeds [F, F + first_special) are dead or tiny ----
-    const bool cand = tid < first_special && live;
-    // cap the batch so that the hash table stays at most half full
-    int wsum = cand ? __popc(want) : 0;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL_MASK, wsum, o);
-      if (lane >= o) wsum += v;
-    }
-    if (lane == 31) sh.warp_sum[tid >> 5] = wsum;
-    __syncthreads();
-    int incl = wsum;  // inclusive prefix of wants in index order
-    for (int w = 0; w < (tid >> 5); ++w) incl += sh.warp_sum[w];
-    if (cand && incl > HT / 2) atomicMin(&sh.first_over, tid);
-    __syncthreads();
-    const int seg_hi = sh.first_over < first_special ? sh.first_over : first_special;  // >= 1
-    const bool in_seg = cand && tid < seg_hi;
-    // which seeds are about to be marked by a LOWER seed of this batch?
-    if (in_seg && want) {
-#pragma unroll
-      for (int j = 1; j < KM; ++j) {
-        if (!((want >> j) & 1u))
-          continue;
-        const uint32_t id = (uint32_t)ids[j];
-        uint32_t h = sweep_hash(id);
-        for (;;) {
-          const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
-          if (old == 0xffffffffu || old == id) {
-            atomicMin(hvals + h, (uint32_t)tid);
+        if (len > A.th_count) {  // :199-202
+          const unsigned long long off = sh.c_off, pl = sh.c_pl;
+          if ((int64_t)(off + len) > A.pool_cap - A.n - 2 || (int64_t)pl >= A.planes_cap) {
+            if (tid == 0) A.ctl[CTL_ERR] = 2;
+            stop = true;
             break;
           }
-          h = (h + 1) & (HT - 1);
+          for (int64_t e = tid; e < len; e += SWEEP_T) {
+            const int32_t id = S.pool.list_pages[at(e)];
+            A.pool[off + e] = id;
+            if (e >= 1) {
+              A.state[id] = (int32_t)Fs;
+              A.res[id] = RES_FREE;
+              const int32_t w = __ldg(&A.pts[id].w);
+              atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
+            }
+          }
+          if (tid == 0) {
+            PlaneRec r;
+            r.seed = (int32_t)Fs; r.pad = 0;
+            r.off = (int64_t)off; r.len = len;
+            r.nrm[0] = sl.t.m.mn0; r.nrm[1] = sl.t.m.mn1; r.nrm[2] = sl.t.m.mn2;
+            r.ctr[0] = sl.t.m.mc0; r.ctr[1] = sl.t.m.mc1; r.ctr[2] = sl.t.m.mc2; r.pad2 = 0;
+            A.planes[pl] = r;
+            A.ctl[CTL_POOL] = off + (unsigned long long)len;
+            A.ctl[CTL_PLANES] = pl + 1;
+          }
+        } else {  // roll back (:203-209): nothing persists
+          for (int64_t e = 1 + tid; e < len; e += SWEEP_T) {
+            const int32_t pt = S.pool.list_pages[at(e)];
+            if (atomicCAS(A.res + pt, (uint32_t)Fs, RES_FREE) == (uint32_t)Fs) unreserve_notify(A.atby, A.slotof, A.doom, pt);
+          }
         }
-      }
-    }
-    __syncthreads();
-    if (in_seg) {
-      uint32_t h = sweep_hash(s);
-      for (;;) {
-        const uint32_t k = hkeys[h];
-        if (k == 0xffffffffu)
-          break;
-        if (k == s) {
-          if (hvals[h] < (uint32_t)tid) atomicMin(&sh.first_conf, tid);
-          break;
+        // give the slot back; its pages are returned by the whole block
+        if (tid == 0) {
+          A.ctl[CTL_STEPS] += sl.steps;
+          A.ctl[CTL_TX] += 1;
+          const int np = sl.n_pages;
+          sh.sp_np = np;
+          sh.c_off = np > 0 ? atomicAdd(S.pool.n_free, (unsigned long long)np) : 0ull;
         }
-        h = (h + 1) & (HT - 1);
-      }
-    }
-    __syncthreads();
-    const int seg_end = sh.first_conf < seg_hi ? sh.first_conf : seg_hi;  // >= 1: thread 0 has nobody below it
-    // ---- commit the conflict-free prefix: orphan marks of the tiny transactions (:233 then :238-239) ----
-    // Only the owner mark is on the sweeper's path; what the mark means for others (reservation void, holder
-    // doomed, alive bit, seed of a waiting grower taken) is logged and applied by a parallel kernel after the
-    // sweep -- none of it is needed for correctness (a slot is verified point by point before it commits).
-    {
-      const bool commit = in_seg && tid < seg_end;
-      const int nw = commit ? __popc(want) : 0;
-      if (commit) ++ntiny;
-      int wincl = nw;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL_MASK, wincl, o);
-        if (lane >= o) wincl += v;
-      }
-      const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
-      unsigned long long lbase = 0;
-      if (wtot > 0) {
-        if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
-        lbase = __shfl_sync(FULL_MASK, lbase, 0);
-      }
-      if (nw) {
-        unsigned long long pos = lbase + (unsigned long long)(wincl - nw);
+        __syncthreads();
+        for (int k = tid; k < sh.sp_np; k += SWEEP_T) S.pool.free_pages[sh.c_off + k] = k < PT_CACHE ? sh.ptc[k] : st.ptab[k];
+        __syncthreads();
+        if (tid == 0) {
+          sl.n_pages = 0;
+          slot_free(S, g);
+        }
+        __syncthreads();
+        F = Fs + 1;  // the seed is done (its own point stays unmarked, :191)
+        done += 1;
+        t_slow += gtimer() - ti1;
+      } else {
+        // ---- fast path: seeds of threads [done, first_special) are dead or tiny ----
+        const bool cand = act && tid < first_special && live;
+        // cap the batch so that the hash table stays at most half full
+        int wsum = cand ? __popc(want) : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL_MASK, wsum, o);
+          if (lane >= o) wsum += v;
+        }
+        if (lane == 31) sh.warp_sum[tid >> 5] = wsum;
+        __syncthreads();
+        int incl = wsum;  // inclusive prefix of wants in index order
+        for (int w = 0; w < (tid >> 5); ++w) incl += sh.warp_sum[w];
+        if (cand && incl > HT / 2) atomicMin(&sh.first_over, tid);
+        __syncthreads();
+        int seg_hi = sh.first_over < first_special ? sh.first_over : first_special;
+        if (seg_hi <= done) seg_hi = done + 1;  // a single seed always fits (K-1 <= 31 wants)
+        const bool in_seg = cand && tid < seg_hi;
+        // which seeds are about to be marked by a LOWER seed of this batch?
+        if (in_seg && want) {
 #pragma unroll
-        for (int j = 1; j < KM; ++j) {
-          if (!((want >> j) & 1u))
-            continue;
-          const int32_t id = ids[j];
-          atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, (uint32_t)i);  // the lower seed owns a shared point
-          if (pos < S.marklog_cap) S.marklog[pos] = make_uint2((uint32_t)id, (uint32_t)i);
-          ++pos;
+          for (int j = 1; j < KM; ++j) {
+            if (!((want >> j) & 1u))
+              continue;
+            const uint32_t id = (uint32_t)ids[j];
+            uint32_t h = sweep_hash(id);
+            for (;;) {
+              const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
+              if (old == 0xffffffffu || old == id) {
+                atomicMin(hvals + h, (uint32_t)tid);
+                break;
+              }
+              h = (h + 1) & (HT - 1);
+            }
+          }
+        }
+        __syncthreads();
+        if (in_seg) {
+          uint32_t h = sweep_hash(s);
+          for (;;) {
+            const uint32_t k = hkeys[h];
+            if (k == 0xffffffffu)
+              break;
+            if (k == s) {
+              if (hvals[h] < (uint32_t)tid) atomicMin(&sh.first_conf, tid);
+              break;
+            }
+            h = (h + 1) & (HT - 1);
+          }
+        }
+        __syncthreads();
+        const int seg_end = sh.first_conf < seg_hi ? sh.first_conf : seg_hi;  // > done: the first one has nobody below it
+        // ---- commit the conflict-free prefix: orphan marks of the tiny transactions (:233 then :238-239) ----
+        // Only the owner mark is on the sweeper's path; what the mark means for others (reservation void, holder
+        // doomed, alive bit, seed of a waiting grower taken) is logged and applied by a parallel kernel after the
+        // sweep -- none of it is needed for correctness (a slot is verified point by point before it commits).
+        {
+          const bool commit = in_seg && tid < seg_end;
+          const int nw = commit ? __popc(want) : 0;
+          if (commit) ++ntiny;
+          int wincl = nw;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, wincl, o);
+            if (lane >= o) wincl += v;
+          }
+          const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
+          unsigned long long lbase = 0;
+          if (wtot > 0) {
+            if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
+            lbase = __shfl_sync(FULL_MASK, lbase, 0);
+          }
+          if (nw) {
+            unsigned long long pos = lbase + (unsigned long long)(wincl - nw);
+#pragma unroll
+            for (int j = 1; j < KM; ++j) {
+              if (!((want >> j) & 1u))
+                continue;
+              const int32_t id = ids[j];
+              atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, (uint32_t)i);  // the lower seed owns a shared point
+              if (pos < S.marklog_cap) S.marklog[pos] = make_uint2((uint32_t)id, (uint32_t)i);
+              ++pos;
+            }
+          }
+        }
+        for (int k = tid; k < HT; k += SWEEP_T) {  // (a list of the used slots would need one contended counter)
+          hkeys[k] = 0xffffffffu;
+          hvals[k] = 0xffffffffu;
+        }
+        // (no fence: every reader of these marks is in this block, and the barrier orders the block's accesses)
+        if (tid == seg_end && valid) sh.last_open = i;  // first seed of the batch that is not finished
+        __syncthreads();
+        done = seg_end;
+        if (done < n_eval) F = sh.last_open;
+        t_fast += gtimer() - ti1;
+      }
+      if (done < n_eval && !stop) {
+        // ---- refresh: the states of what this thread already knows (one load level) ----
+        if (valid && tid >= done) {
+          const int32_t st_s = __ldcg(A.state + s);
+          int32_t stj[KM];
+#pragma unroll
+          for (int j = 1; j < KM; ++j) {
+            stj[j] = 0;
+            if (ids[j] >= 0) stj[j] = __ldcg(A.state + ids[j]);
+          }
+          slot = __ldcg(A.slotof + i);
+          live = st_s == -1;
+          want = 0;
+          grower = false;
+          if (live) {
+#pragma unroll
+            for (int j = 1; j < KM; ++j)
+              if (ids[j] >= 0 && stj[j] == -1) want |= 1u << j;
+            grower = __popc(want) == K - 1;
+          }
         }
       }
     }
-    for (int k = tid; k < HT; k += SWEEP_T) {  // (a list of the used slots would need one contended counter)
-      hkeys[k] = 0xffffffffu;
-      hvals[k] = 0xffffffffu;
+    if (!stop) {  // the whole batch is done
+      if (n_live > n_eval) F = sh.last_seed + 1;  // more live seeds in the stretch than threads
+      else F = stretch_end;
+      if (F > A.n) F = A.n;
     }
-    // (no fence: every reader of these marks is in this block, and the barrier orders the block's accesses)
-    if (tid == seg_end && valid) sh.last_seed = i;  // first live seed left for the next batch
     __syncthreads();
-    if (seg_end < n_eval) F = sh.last_seed;
-    else if (n_live > n_eval) F = sh.last_seed + 1;  // more live seeds in the stretch than threads
-    else F = base + 32LL * SWEEP_WORDS;
-    if (F > A.n) F = A.n;
-    __syncthreads();
-    t_fast += gtimer() - ti1;
   }
 
   if (tid == 0) {
