@@ -44,7 +44,7 @@ constexpr int SWEEP_WORDS = 128;  // bitmap words (4096 seeds) scanned per batch
 constexpr int PT_CACHE = 256;      // sweeper: cached page-table entries of the slot being committed
 constexpr int HT = 16384;      // sweeper hash table slots (keys + vals = 128 KB of shared memory)
 
-enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING = 4 };
+enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING = 4, ST_DONE = 5 };  // DONE: committed by the sweeper, slot and pages still to be returned
 // spec control block (A.ctl + 8)
 enum {
   SC_NFREE = 0,       // free slots
@@ -63,6 +63,7 @@ enum {
   SC_SWEEP_NS = 13,   // time inside the sweeper
   SC_ATFAIL = 14,     // finished slots whose assumed-taken points were not all taken
   SC_NLOG = 19,       // entries of the mark log
+  SC_POOL0 = 20,      // pool fill at the start of the sweep (planes committed since: [SC_POOL0, CTL_POOL))
   SC_T_FRONT = 15, SC_T_SLOW = 16, SC_T_FAST = 17, SC_N_SLOW = 18,  // sweeper time split (ns), slow-path count
 };
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(TPB) spec_mark_release_kernel(SpecArgs S)
   if (g >= S.G)
     return;
   Slot& sl = S.slots[g];
-  if (sl.status == ST_FREE)
+  if (sl.status == ST_FREE || sl.status == ST_DONE)
     return;
   if (sl.status == ST_DEAD || S.A.doom[sl.seed_i]) sl.status = ST_RELEASING;
 }
@@ -198,9 +199,9 @@ __global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
   if (g >= S.G)
     return;
   Slot& sl = S.slots[g];
-  if (sl.status != ST_RELEASING)
+  if (sl.status != ST_RELEASING && sl.status != ST_DONE)
     return;
-  atomicAdd(&S.sc[SC_WASTED], sl.steps);
+  if (sl.status == ST_RELEASING) atomicAdd(&S.sc[SC_WASTED], sl.steps);
   slot_free(S, g);
 }
 
@@ -224,7 +225,23 @@ __global__ void __launch_bounds__(TPB) spec_apply_marks_kernel(SpecArgs S)
   }
 }
 
-__global__ void spec_reset_log_kernel(SpecArgs S) { S.sc[SC_NLOG] = 0; }
+// alive bits of the points of the planes this sweep committed: pool entries [SC_POOL0, CTL_POOL)
+__global__ void __launch_bounds__(TPB) spec_apply_planes_kernel(SpecArgs S)
+{
+  const GrowArgs& A = S.A;
+  const unsigned long long lo = S.sc[SC_POOL0], hi = A.ctl[CTL_POOL];
+  for (unsigned long long k = lo + (unsigned long long)blockIdx.x * TPB + threadIdx.x; k < hi;
+       k += (unsigned long long)gridDim.x * TPB) {
+    const int32_t w = __ldg(&A.pts[A.pool[k]].w);
+    atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
+  }
+}
+
+__global__ void spec_reset_log_kernel(SpecArgs S)
+{
+  S.sc[SC_NLOG] = 0;
+  S.sc[SC_POOL0] = S.A.ctl[CTL_POOL];
+}
 
 // ---- K1: scout -- the window [F, F+C) ahead of the sweeper -------------------------------------------------
 // Every seed of the window without a slot is evaluated against the committed state plus the reservations
@@ -594,8 +611,23 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         // every point it treated as taken (reserved by a lower transaction at the time) must be taken now,
         // and every point it accepted must still be free (a lower tiny transaction may have marked it)
         bool bad = false;
-        for (int64_t k = tid; k < n_at; k += SWEEP_T) bad |= __ldcg(A.state + S.pool.at_pages[at(k)]) == -1;
-        for (int64_t e = 1 + tid; e < len; e += SWEEP_T) bad |= __ldcg(A.state + S.pool.list_pages[at(e)]) != -1;
+        // (four entries per thread and trip: the loads of a trip are independent, one block has to do it all)
+        for (int64_t k0 = tid; k0 < n_at; k0 += 4 * SWEEP_T) {
+          int32_t pt[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pt[u] = k0 + u * SWEEP_T < n_at ? S.pool.at_pages[at(k0 + u * SWEEP_T)] : -1;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (pt[u] >= 0) bad |= __ldcg(A.state + pt[u]) == -1;
+        }
+        for (int64_t e0 = 1 + tid; e0 < len; e0 += 4 * SWEEP_T) {
+          int32_t pt[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pt[u] = e0 + u * SWEEP_T < len ? S.pool.list_pages[at(e0 + u * SWEEP_T)] : -1;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (pt[u] >= 0) bad |= __ldcg(A.state + pt[u]) != -1;
+        }
         if (bad) sh.sp_bad = 1;
         __syncthreads();
         if (sh.sp_bad) {
@@ -614,14 +646,20 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
             stop = true;
             break;
           }
-          for (int64_t e = tid; e < len; e += SWEEP_T) {
-            const int32_t id = S.pool.list_pages[at(e)];
-            A.pool[off + e] = id;
-            if (e >= 1) {
-              A.state[id] = (int32_t)Fs;
-              A.res[id] = RES_FREE;
-              const int32_t w = __ldg(&A.pts[id].w);
-              atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
+          for (int64_t e0 = tid; e0 < len; e0 += 4 * SWEEP_T) {
+            int32_t id[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) id[u] = e0 + u * SWEEP_T < len ? S.pool.list_pages[at(e0 + u * SWEEP_T)] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (id[u] < 0)
+                continue;
+              const int64_t e = e0 + u * SWEEP_T;
+              A.pool[off + e] = id[u];  // (the alive bits of these points are cleared from the pool by the apply kernel)
+              if (e >= 1) {
+                A.state[id[u]] = (int32_t)Fs;
+                A.res[id[u]] = RES_FREE;
+              }
             }
           }
           if (tid == 0) {
@@ -640,20 +678,11 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
             if (atomicCAS(A.res + pt, (uint32_t)Fs, RES_FREE) == (uint32_t)Fs) unreserve_notify(A.atby, A.slotof, A.doom, pt);
           }
         }
-        // give the slot back; its pages are returned by the whole block
+        // the slot and its pages go back in the next round's release pass (parallel), not on this block's path
         if (tid == 0) {
           A.ctl[CTL_STEPS] += sl.steps;
           A.ctl[CTL_TX] += 1;
-          const int np = sl.n_pages;
-          sh.sp_np = np;
-          sh.c_off = np > 0 ? atomicAdd(S.pool.n_free, (unsigned long long)np) : 0ull;
-        }
-        __syncthreads();
-        for (int k = tid; k < sh.sp_np; k += SWEEP_T) S.pool.free_pages[sh.c_off + k] = k < PT_CACHE ? sh.ptc[k] : st.ptab[k];
-        __syncthreads();
-        if (tid == 0) {
-          sl.n_pages = 0;
-          slot_free(S, g);
+          sl.status = ST_DONE;
         }
         __syncthreads();
         F = Fs + 1;  // the seed is done (its own point stays unmarked, :191)
@@ -931,6 +960,8 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     else spec_sweep_kernel<32><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     spec_apply_marks_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
+    KLAUNCH_CHECK(c);
+    spec_apply_planes_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     spec_reset_log_kernel<<<1, 1, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
