@@ -553,14 +553,14 @@ __device__ __forceinline__ void tx_reserve_lane(const GrowArgs& A, int32_t id, u
 
 template <int KT, class Store>
 __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, unsigned long long budget,
-                                 int lane, unsigned long long& steps_out)
+                                 int lane, unsigned long long& steps_out, unsigned long long* iters_out = nullptr)
 {
   const int K = KT ? KT : A.K;  // <= 16: one half-warp holds a row
   const uint32_t me = (uint32_t)seed_i;
   const uint32_t fr = (uint32_t)A.frontier;
   const bool fastdiv = (A.flags & GF_FASTDIV) != 0, row_l1 = (A.flags & GF_ROW_L1) != 0;
   const int half = lane >> 4, sl = lane & 15;
-  unsigned long long steps = 0;
+  unsigned long long steps = 0, iters = 0;
   TxOutcome out = TX_RUNNING;
 
   // the node of this lane's half and neighbour column `sl` of it
@@ -589,6 +589,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
       out = TX_OVERFLOW;
       break;
     }
+    ++iters;
     bool want = id >= 0 && stt == -1 && rs != me && !mine && geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
     if (__any_sync(FULL_MASK, has_dup && want)) {  // a row that names a point twice: first occurrence only
       const unsigned long long key = want ? (((unsigned long long)half << 32) | (uint32_t)id)
@@ -747,5 +748,6 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     }
   }
   steps_out += steps;
+  if (iters_out) *iters_out += iters;
   return out;
 }

@@ -63,6 +63,7 @@ enum {
   SC_SWEEP_NS = 13,   // time inside the sweeper
   SC_ATFAIL = 14,     // finished slots whose assumed-taken points were not all taken
   SC_NLOG = 19,       // entries of the mark log
+  SC_HEAD_ITERS = 21, // warp iterations of the head slot (two-node engine: <= steps)
   SC_POOL0 = 20,      // pool fill at the start of the sweep (planes committed since: [SC_POOL0, CTL_POOL))
   SC_T_FRONT = 15, SC_T_SLOW = 16, SC_T_FAST = 17, SC_N_SLOW = 18,  // sweeper time split (ns), slow-path count
 };
@@ -398,17 +399,18 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
     t = sl.t;
   }
   __syncwarp();
-  unsigned long long steps = 0;
+  unsigned long long steps = 0, iters = 0;
   const bool is_head = (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT];
   const unsigned long long t0 = is_head ? gtimer() : 0ull;
   // K <= 16: two DFS nodes per warp step (grow.cuh tx_run_pair); BSEG_GROW_FLAGS bit 6 forces the single-node engine
   const bool pair = A.K <= 16 && !(A.flags & GF_NOPAIR);
-  const TxOutcome out = pair ? (A.K == 15 ? tx_run_pair<15>(A, st, t, seed_i, budget, lane, steps)
-                                          : tx_run_pair<0>(A, st, t, seed_i, budget, lane, steps))
+  const TxOutcome out = pair ? (A.K == 15 ? tx_run_pair<15>(A, st, t, seed_i, budget, lane, steps, &iters)
+                                          : tx_run_pair<0>(A, st, t, seed_i, budget, lane, steps, &iters))
                              : tx_run<MODE_SPEC, 0>(A, st, t, seed_i, budget, false, lane, steps);
   __syncwarp();
   if (lane == 0 && is_head) {
     S.sc[SC_HEAD_STEPS] += steps;
+    S.sc[SC_HEAD_ITERS] += iters;
     S.sc[SC_HEAD_NS] += gtimer() - t0;
   }
   if (lane == 0) {
@@ -1002,6 +1004,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       return bseg_fail(c, BSEG_E_STATE, "plane grower: no progress");
   }
   if (dbg) {
+    fprintf(stderr, "[bseg] head: %llu calls in %llu warp steps\n", ctl[8 + SC_HEAD_STEPS], ctl[8 + SC_HEAD_ITERS]);
     fprintf(stderr, "[bseg] rounds %lld: release %.1f ms, scout+assign %.1f ms, slices %.1f ms, sweep+apply %.1f ms\n", (long long)rounds,
             pt[0], pt[1], pt[2], pt[3]);
   }
