@@ -34,7 +34,7 @@ struct GrowArgs {
   const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
   uint32_t* atby;    // [n] lowest in-flight transaction that assumed the point taken (early notification)
 };
-enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32, GF_NOPAIR = 64 };
+enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32, GF_NOPAIR = 64, GF_NOSKIP = 128, GF_SKIP_EAGER = 256, GF_NEVER = 1 << 30 /* never set */ };
 
 // ---- "assumed taken" list of a speculative transaction --------------------------------------------------
 // A point that is free in the committed state and passes the geometric tests, but is reserved by a LOWER
@@ -551,14 +551,214 @@ __device__ __forceinline__ void tx_reserve_lane(const GrowArgs& A, int32_t id, u
   }
 }
 
+// ---- skipping runs of calls that accept nothing (speculative engine) ----------------------------------------
+// Three Broad() calls out of four accept nothing, and they come in RUNS (the DFS unwinding over a finished
+// region: 88 % of them sit in runs of 32 and more, the last run of a large plane is half of its calls).  Such a
+// call changes nothing: no mark, no list entry, the model keeps its sums.  The nodes the DFS visits while
+// nothing is accepted are known in advance: the rest of the current frame, then the frames below it on the
+// stack (my_function.cpp:252-255).  So one warp step looks at the next 32 of them at once, one node per lane,
+// all against the current model; the calls before the first node that WANTS a point (free in the committed
+// state, not ours, passes the geometric tests -- whatever its reservation says) are exactly the calls the
+// reference makes next, they are counted and the frames advanced past them.  The wanting node is left to the
+// regular step.  Conservative by construction: stale reservation data can only end a run early.
+struct SkipScratch {
+  int32_t id[32 * 16];    // (node, neighbour) pairs that need the geometric tests: neighbour id ...
+  uint8_t owner[32 * 16]; // ... and the lane holding the node
+  uint32_t hit;           // lanes whose node wants a point
+};
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p)
+{
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// lanes whose node (one per lane, `act` lanes only) wants a point
+template <int KT>
+__device__ __forceinline__ uint32_t skip_eval(const GrowArgs& A, const Model& m, uint32_t me, bool act, uint32_t node,
+                                              int lane, SkipScratch* ss, unsigned long long* pairs)
+{
+  const int K = KT ? KT : A.K;
+  // ---- phase 1: the node's row, then state and reservation of ALL its neighbours in one round trip ----
+  // (every load is issued before the first test: a padded column reads the node's own entry)
+  const uint32_t nd = act ? node : 0u;
+  const int32_t* row = A.nbr + (int64_t)nd * K;
+  int32_t ids[16];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) ids[k] = (k < K) ? __ldg(row + k) : -1;
+  uint32_t stt[16], rs[16];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) {
+    const uint32_t sid = ids[k] >= 0 ? (uint32_t)ids[k] : nd;
+    stt[k] = ld_cg_u32(A.state + sid);
+    rs[k] = ld_cg_u32(A.res + sid);
+  }
+  // Every test below is made to depend on ALL the loads above (a mask that is zero at run time but unknown to
+  // the compiler): ptxas would otherwise sink each load next to its test to save registers and serialise the
+  // 28 round trips.
+  uint32_t mix = 0;
+#pragma unroll
+  for (int k = 1; k < 16; ++k) mix ^= stt[k] ^ rs[k];
+  const uint32_t z = mix & (uint32_t)(A.flags & GF_NEVER);
+#pragma unroll
+  for (int k = 1; k < 16; ++k) {
+    stt[k] ^= z;
+    rs[k] ^= z;
+  }
+  uint32_t cand = 0;
+#pragma unroll
+  for (int k = 1; k < 16; ++k)
+    if (ids[k] >= 0 && stt[k] == 0xffffffffu && rs[k] != me) cand |= 1u << k;
+  if (!act) cand = 0;
+  // ---- phase 2: geometric tests of the free neighbours, spread over the lanes ----
+  const int nc = __popc(cand);
+  int cincl = nc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL_MASK, cincl, o);
+    if (lane >= o) cincl += v;
+  }
+  const int C = __shfl_sync(FULL_MASK, cincl, 31);
+  uint32_t hit = 0;
+  if (C) {
+    if (lane == 0) ss->hit = 0;
+    int w = cincl - nc;
+#pragma unroll
+    for (int k = 1; k < 16; ++k)
+      if ((cand >> k) & 1u) {
+        ss->id[w] = ids[k];
+        ss->owner[w] = (uint8_t)lane;
+        ++w;
+      }
+    __syncwarp();
+    for (int r0 = 0; r0 < C; r0 += 64) {  // two pairs per lane and trip
+      const int ra = r0 + lane, rb = r0 + 32 + lane;
+      const bool va = ra < C, vb = rb < C;
+      const int32_t ia = ss->id[va ? ra : 0], ib = ss->id[vb ? rb : 0];
+      const int4 pa = __ldg(A.pts + ia), pb = __ldg(A.pts + ib);
+      const double* na = A.nrm + 3 * (int64_t)ia;
+      const double* nb = A.nrm + 3 * (int64_t)ib;
+      const double a0 = __ldg(na), a1 = __ldg(na + 1), a2 = __ldg(na + 2);
+      const double b0 = __ldg(nb), b1 = __ldg(nb + 1), b2 = __ldg(nb + 2);
+      if (va && geo_test(m, pa, a0, a1, a2, A.th_thick, A.th_dot)) atomicOr(&ss->hit, 1u << ss->owner[ra]);
+      if (vb && geo_test(m, pb, b0, b1, b2, A.th_thick, A.th_dot)) atomicOr(&ss->hit, 1u << ss->owner[rb]);
+    }
+    __syncwarp();
+    hit = ss->hit;
+    __syncwarp();
+  }
+  if (pairs) *pairs += (unsigned long long)C;
+  return hit;
+}
+
+template <int KT, class Store>
+__device__ __forceinline__ unsigned long long tx_skip_noops(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, int lane,
+                                                         SkipScratch* ss, unsigned long long budget,
+                                                         unsigned long long& iters, bool& halt,
+                                                         unsigned long long* dbg = nullptr)
+{
+  const uint32_t me = (uint32_t)seed_i;
+  unsigned long long skipped = 0;
+  while (iters + 6 <= budget) {
+    const long long c0 = dbg ? clock64() : 0;
+    // segment of upcoming entries held by this lane: lane 0 the current frame, lane l the l-th frame below it
+    int cur = 0, end = 0;
+    if (lane == 0) {
+      if (t.have_top) {
+        cur = (int)t.top_cur;
+        end = (int)t.top_end;
+      }
+    } else if (t.sp >= lane) {
+      const int2 f = st.pop(t.sp - lane);
+      cur = f.x;
+      end = f.y;
+    }
+    const uint8_t doomed = ((volatile uint8_t*)A.doom)[seed_i];
+    const unsigned long long stop = *(volatile unsigned long long*)A.stop_flag;
+    const int len = end - cur;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = incl - len;
+    const int T = __shfl_sync(FULL_MASK, incl, 31);
+    if (T == 0)
+      break;
+    // upcoming entries `lane` and `lane + 32`: the segment holding each, then the node ids (one round trip)
+    int seg0 = 0, seg1 = 0;
+#pragma unroll 8
+    for (int s = 0; s < 32; ++s) {
+      const int v = __shfl_sync(FULL_MASK, incl, s);
+      seg0 += (v <= lane) ? 1 : 0;
+      seg1 += (v <= lane + 32) ? 1 : 0;
+    }
+    const bool act0 = lane < T, act1 = lane + 32 < T;
+    const int s0 = act0 ? seg0 : 0, s1 = act1 ? seg1 : 0;
+    const int e0 = __shfl_sync(FULL_MASK, cur, s0) + (lane - __shfl_sync(FULL_MASK, excl, s0));
+    const int e1 = __shfl_sync(FULL_MASK, cur, s1) + (lane + 32 - __shfl_sync(FULL_MASK, excl, s1));
+    uint32_t node0 = 0, node1 = 0;
+    if (act0) node0 = (uint32_t)st.get(e0);
+    if (act1) {  // the second half's rows travel while the first half is evaluated
+      node1 = (uint32_t)st.get(e1);
+      const int K = KT ? KT : A.K;
+      prefetch_l1(A.nbr + (int64_t)node1 * K);
+      prefetch_l1(A.nbr + (int64_t)node1 * K + (K - 1));
+    }
+    const long long c1 = dbg ? clock64() + (long long)((node0 | node1) & 0u) : 0;
+    int f;  // entries [0, f) are calls that accept nothing
+    uint32_t hit = skip_eval<KT>(A, t.m, me, act0, node0, lane, ss, dbg ? dbg + 4 : nullptr);
+    iters += 3;
+    if (hit) {
+      f = __ffs(hit) - 1;
+    } else if (T <= 32) {
+      f = T;
+    } else {
+      hit = skip_eval<KT>(A, t.m, me, act1, node1, lane, ss, dbg ? dbg + 4 : nullptr);
+      iters += 2;
+      if (dbg && lane == 0) dbg[0] += 1;
+      f = 32 + (hit ? __ffs(hit) - 1 : (T < 64 ? T - 32 : 32));
+    }
+    if (dbg && lane == 0) {
+      const long long c3 = clock64() + (long long)(hit & 0u);
+      dbg[0] += 1; dbg[1] += (unsigned long long)(c1 - c0); dbg[2] += (unsigned long long)(c3 - c1);
+    }
+    if (f > 0) {
+      skipped += (unsigned long long)f;
+      if (f < T) {  // entry f stays: the segment holding it becomes the current frame
+        const int sf = __popc(__ballot_sync(FULL_MASK, incl <= f));
+        t.top_cur = (int64_t)(__shfl_sync(FULL_MASK, cur, sf) + (f - __shfl_sync(FULL_MASK, excl, sf)));
+        t.top_end = (int64_t)__shfl_sync(FULL_MASK, end, sf);
+        t.sp -= sf;
+      } else {      // every loaded segment is used up
+        t.sp -= t.sp < 31 ? t.sp : 31;
+        t.top_cur = t.top_end;
+      }
+      t.have_top = 1;
+    }
+    if (doomed || stop) {
+      halt = true;
+      break;
+    }
+    if (hit || f == 0)
+      break;
+  }
+  return skipped;
+}
+
 template <int KT, class Store>
 __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64_t seed_i, unsigned long long budget,
-                                 int lane, unsigned long long& steps_out, unsigned long long* iters_out = nullptr)
+                                 int lane, unsigned long long& steps_out, unsigned long long* iters_out = nullptr,
+                                 SkipScratch* ss = nullptr, unsigned long long* dbg = nullptr)
 {
   const int K = KT ? KT : A.K;  // <= 16: one half-warp holds a row
   const uint32_t me = (uint32_t)seed_i;
   const uint32_t fr = (uint32_t)A.frontier;
   const bool fastdiv = (A.flags & GF_FASTDIV) != 0, row_l1 = (A.flags & GF_ROW_L1) != 0;
+  const bool skip = ss != nullptr && (A.flags & GF_NOSKIP) == 0;
+  bool halt = false;
   const int half = lane >> 4, sl = lane & 15;
   unsigned long long steps = 0, iters = 0;
   TxOutcome out = TX_RUNNING;
@@ -584,12 +784,13 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
       n0 = __ldg(nr); n1 = __ldg(nr + 1); n2 = __ldg(nr + 2);
     }
   }
-  while (steps < budget) {
+  while (iters < budget) {  // budget in warp iterations (a skip batch weighs 3): a slice is a TIME slice
     if (!st.reserve((t.len > t.n_at ? t.len : t.n_at) + 3 * K, lane)) {  // before anything is marked
       out = TX_OVERFLOW;
       break;
     }
     ++iters;
+    if (dbg && lane == 0) dbg[3] += 1;
     bool want = id >= 0 && stt == -1 && rs != me && !mine && geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
     if (__any_sync(FULL_MASK, has_dup && want)) {  // a row that names a point twice: first occurrence only
       const unsigned long long key = want ? (((unsigned long long)half << 32) | (uint32_t)id)
@@ -660,6 +861,8 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
         have_nextB = true;
       }
     } else {
+      // two calls in a row accepted nothing: look at the next 32 nodes at once (tx_skip_noops)
+      if (skip && (useB || (A.flags & GF_SKIP_EAGER)) && iters + 6 <= budget) steps += tx_skip_noops<KT>(A, st, t, seed_i, lane, ss, budget, iters, halt, dbg);
       while (t.have_top && t.top_cur == t.top_end) {
         if (t.sp > 0) {
           --t.sp;
@@ -739,7 +942,8 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     hasB = have_nextB;
     id = nid; stt = nstt; rs = nrs; mine = nmine; p = np; n0 = m0; n1 = m1; n2 = m2;
     has_dup = ndup;
-    if ((steps & 7) < 2) {
+    if ((steps & 7) < 2 || halt) {
+      halt = false;
       if (((volatile uint8_t*)A.doom)[seed_i]) {
         out = TX_DOOMED;
         break;

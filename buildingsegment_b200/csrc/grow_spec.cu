@@ -65,6 +65,7 @@ enum {
   SC_NLOG = 19,       // entries of the mark log
   SC_HEAD_ITERS = 21, // warp iterations of the head slot (two-node engine: <= steps)
   SC_POOL0 = 20,      // pool fill at the start of the sweep (planes committed since: [SC_POOL0, CTL_POOL))
+  SC_SKIP_DBG = 24,   // [24, 29): head skip batches, cycles in enumerate / row+state / geometry, pairs tested
   SC_T_FRONT = 15, SC_T_SLOW = 16, SC_T_FAST = 17, SC_N_SLOW = 18,  // sweeper time split (ns), slow-path count
 };
 
@@ -404,8 +405,11 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   const unsigned long long t0 = is_head ? gtimer() : 0ull;
   // K <= 16: two DFS nodes per warp step (grow.cuh tx_run_pair); BSEG_GROW_FLAGS bit 6 forces the single-node engine
   const bool pair = A.K <= 16 && !(A.flags & GF_NOPAIR);
-  const TxOutcome out = pair ? (A.K == 15 ? tx_run_pair<15>(A, st, t, seed_i, budget, lane, steps, &iters)
-                                          : tx_run_pair<0>(A, st, t, seed_i, budget, lane, steps, &iters))
+  __shared__ SkipScratch skip_scratch[GW];
+  SkipScratch* ss = &skip_scratch[threadIdx.x >> 5];
+  unsigned long long* dbg = is_head ? &S.sc[SC_SKIP_DBG] : nullptr;
+  const TxOutcome out = pair ? (A.K == 15 ? tx_run_pair<15>(A, st, t, seed_i, budget, lane, steps, &iters, ss, dbg)
+                                          : tx_run_pair<0>(A, st, t, seed_i, budget, lane, steps, &iters, ss, dbg))
                              : tx_run<MODE_SPEC, 0>(A, st, t, seed_i, budget, false, lane, steps);
   __syncwarp();
   if (lane == 0 && is_head) {
@@ -928,10 +932,11 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   cudaEvent_t pe[5];
   float pt[4] = {0, 0, 0, 0};
   for (auto& e : pe) cudaEventCreate(&e);
-  unsigned long long ctl[32] = {0};
+  unsigned long long ctl[64] = {0};
   uint32_t* d_ncand = reinterpret_cast<uint32_t*>(&S.sc[SC_NCAND]);
   const unsigned sb = (unsigned)((S.G + GW - 1) / GW);
-  const unsigned long long budget = 4096;
+  // slice length in warp iterations of the head (two-node engine: ~1.6 calls each, a skip batch weighs 3)
+  const unsigned long long budget = getenv("BSEG_SLICE") ? strtoull(getenv("BSEG_SLICE"), nullptr, 10) : 2560;
   // the first pass of the sweeper runs before anything is in flight: it stops at the first grower
   while (F < n) {
     const int64_t C = n - F < CMAX ? n - F : CMAX;
@@ -1005,6 +1010,11 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   }
   if (dbg) {
     fprintf(stderr, "[bseg] head: %llu calls in %llu warp steps\n", ctl[8 + SC_HEAD_STEPS], ctl[8 + SC_HEAD_ITERS]);
+    const unsigned long long* sd = ctl + 8 + SC_SKIP_DBG;
+    if (sd[0])
+      fprintf(stderr, "[bseg] head skip batches %llu: cycles/batch enumerate %llu, evaluate %llu; pairs/batch %.1f; regular steps %llu, "
+              "batch time %.1f ms of head %.1f ms\n", sd[0], sd[1] / sd[0], sd[2] / sd[0], (double)sd[4] / (double)sd[0], sd[3],
+              (double)(sd[1] + sd[2]) / 1.965e6, ctl[8 + SC_HEAD_NS] / 1e6);
     fprintf(stderr, "[bseg] rounds %lld: release %.1f ms, scout+assign %.1f ms, slices %.1f ms, sweep+apply %.1f ms\n", (long long)rounds,
             pt[0], pt[1], pt[2], pt[3]);
   }
