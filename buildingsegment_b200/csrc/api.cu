@@ -128,7 +128,7 @@ BSEG_API void bseg_destroy(bseg_ctx* c)
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->xyz_raw, &c->minmax, &c->keys[0], &c->keys[1], &c->vals[0], &c->vals[1], &c->sort_cnt,
                    &c->scan_tmp, &c->pts, &c->inv, &c->flags, &c->cell_key, &c->cell_start, &c->hash_keys,
-                   &c->hash_vals, &c->nbr, &c->nrm, &c->curv, &c->worklist, &c->counters, &c->out_tmp,
+                   &c->hash_vals, &c->cell_key2, &c->cell_start2, &c->hash_keys2, &c->hash_vals2, &c->nbr, &c->nrm, &c->curv, &c->worklist, &c->counters, &c->out_tmp,
                    &c->g_state, &c->g_res, &c->g_spec, &c->g_pool, &c->g_planes, &c->g_tx, &c->g_queue, &c->g_rowdup, &c->g_marklog,
                    &c->g_stack, &c->g_label, &c->g_pidx, &c->r_hist, &c->r_image, &c->r_png, &c->r_pix};
   for (DevBuf* b : all)

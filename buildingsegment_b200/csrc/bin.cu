@@ -115,6 +115,16 @@ __global__ void __launch_bounds__(TPB) gather_kernel(const int32_t* __restrict__
   head[s] = (k != kp) ? 1u : 0u;
 }
 
+// heads of the cells at another level of the same sorted keys
+__global__ void __launch_bounds__(TPB) head_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                   uint32_t* __restrict__ head)
+{
+  int64_t s = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (s >= n)
+    return;
+  head[s] = (s == 0 || (keys[s] >> shift) != (keys[s - 1] >> shift)) ? 1u : 0u;
+}
+
 // keys >>= lvl3 in a second pass (the gather reads its left neighbour's unshifted key)
 __global__ void __launch_bounds__(TPB) shift_keys_kernel(uint64_t* __restrict__ keys, int64_t n, int lvl3)
 {
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(TPB) shift_keys_kernel(uint64_t* __restrict__ 
 // ---- cell table from scanned heads: R 4+4+8, W 12 B/cell ---------------------------------------------
 __global__ void __launch_bounds__(TPB) cells_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ excl,
                                                     int64_t n, uint64_t* __restrict__ cell_key,
-                                                    uint32_t* __restrict__ cell_start, uint32_t n_cells)
+                                                    uint32_t* __restrict__ cell_start, uint32_t n_cells, int shift = 0)
 {
   int64_t s = (int64_t)blockIdx.x * TPB + threadIdx.x;
   if (s >= n)
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(TPB) cells_kernel(const uint64_t* __restrict__
   bool is_head = (s + 1 < n) ? (excl[s + 1] != e) : (e + 1 == n_cells);
   // head[s] == 1  <=>  excl[s+1] == excl[s] + 1; the last element is a head iff e == n_cells - 1
   if (is_head) {
-    cell_key[e] = keys[s];
+    cell_key[e] = keys[s] >> shift;
     cell_start[e] = (uint32_t)s;
   }
   if (s == n - 1)
@@ -299,6 +309,32 @@ int stage_bin(bseg_ctx* c, const bseg_params* p)
   gather_kernel<<<nb, TPB, 0, c->stream>>>(dptr<int32_t>(c->xyz_raw), keys, vals, n, lvl3, dptr<int4>(c->pts),
                                            dptr<uint32_t>(c->inv), head);
   KLAUNCH_CHECK(c);
+  // the finer table (edge cell / 2) for the dense groups of the kNN: same sorted cloud, one level down
+  c->have_mid = false;
+  if (lvl >= 1) {
+    const int shift2 = 3 * (lvl - 1);
+    c->n_cells2 = cells_at[lvl - 1];
+    uint32_t* head2 = dptr<uint32_t>(c->vals[1 - sel]);  // the sort's other value buffer is free now
+    head_kernel<<<nb, TPB, 0, c->stream>>>(keys, n, shift2, head2);
+    KLAUNCH_CHECK(c);
+    RC_CHECK(bseg_exclusive_scan_u32(c, head2, n, nullptr));
+    RC_CHECK(dev_ensure(c, c->cell_key2, (size_t)c->n_cells2 * 8));
+    RC_CHECK(dev_ensure(c, c->cell_start2, (size_t)(c->n_cells2 + 1) * 4));
+    cells_kernel<<<nb, TPB, 0, c->stream>>>(keys, head2, n, dptr<uint64_t>(c->cell_key2), dptr<uint32_t>(c->cell_start2),
+                                            (uint32_t)c->n_cells2, shift2);
+    KLAUNCH_CHECK(c);
+    uint64_t hsize2 = 1024;
+    while (hsize2 < (uint64_t)c->n_cells2 * 2) hsize2 <<= 1;
+    c->hash_mask2 = hsize2 - 1;
+    RC_CHECK(dev_ensure(c, c->hash_keys2, hsize2 * 8));
+    RC_CHECK(dev_ensure(c, c->hash_vals2, hsize2 * 4));
+    CU_CHECK(c, cudaMemsetAsync(c->hash_keys2.p, 0xff, hsize2 * 8, c->stream));
+    hash_build_kernel<<<(unsigned)ceil_div64(c->n_cells2, TPB), TPB, 0, c->stream>>>(
+        dptr<uint64_t>(c->cell_key2), (uint32_t)c->n_cells2, reinterpret_cast<unsigned long long*>(c->hash_keys2.p),
+        dptr<uint32_t>(c->hash_vals2), c->hash_mask2);
+    KLAUNCH_CHECK(c);
+    c->have_mid = true;
+  }
   if (lvl3) {
     shift_keys_kernel<<<nb, TPB, 0, c->stream>>>(keys, n, lvl3);
     KLAUNCH_CHECK(c);

@@ -65,6 +65,10 @@ struct bseg_ctx {
   uint64_t hash_mask = 0;
   int sort_sel = 0;     // which of keys[]/vals[] holds the sorted result
   int K = 0;
+  // second, finer cell table (edge cell / 2) over the same sorted cloud: dense groups of the kNN descend to it
+  bool have_mid = false;
+  int64_t n_cells2 = 0;
+  uint64_t hash_mask2 = 0;
 
   // ---- grow results ----
   int32_t n_planes = 0;
@@ -89,6 +93,7 @@ struct bseg_ctx {
   DevBuf cell_start;  // u32 [n_cells+1]
   DevBuf hash_keys;   // u64 [hash]
   DevBuf hash_vals;   // u32 [hash]
+  DevBuf cell_key2, cell_start2, hash_keys2, hash_vals2;  // the finer table (have_mid)
   DevBuf nbr;         // int32 [n][K] sorted-position space, -1 padded
   DevBuf nrm;         // double [n][3] sorted-position space
   DevBuf curv;        // double [n]

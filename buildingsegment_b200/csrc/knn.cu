@@ -19,6 +19,8 @@
 // A row is exact when its K-th distance is below cell+1 (nothing outside the 27 cells can be
 // closer); other queries go to the ring-expansion fallback (level-L ancestor cells are contiguous
 // key ranges of the Morton-sorted cloud).  The hybrid set is always exact because cell >= radius.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "bseg_arith.h"
 
@@ -50,7 +52,13 @@ struct KnnArgs {
   uint32_t* unres;            // queries needing ring expansion
   uint32_t* n_unres;
   int64_t n;
+  const uint32_t* inv;        // original index -> sorted position
+  // cells the group kernel left to the per-cell kernels: cell | HYB_ONLY (rows done, hybrid set still to do)
+  uint32_t* cell_list;
+  uint32_t* n_cell_list;
+  uint32_t* next_chunk;       // work counter of the group kernel
 };
+constexpr uint32_t HYB_ONLY = 0x80000000u;
 
 // selection predicate: d2 < t, plus (eq && d2 == t && idx <= u)
 struct Sel {
@@ -319,10 +327,10 @@ __device__ __forceinline__ void hybrid_from_view(const KnnArgs& A, const V& v, c
 // One query against the staged 27-cell block: K-row + hybrid moments.
 template <class V>
 __device__ __forceinline__ void serve_query(const KnnArgs& A, V& v, WarpScratch* ws, const int4& q, uint32_t qpos,
-                                            uint32_t M, const int3& org, int lane, int& cnt_out, int (&ms)[9])
+                                            uint32_t M, const int3& org, int lane, int& cnt_out, int (&ms)[9], bool rows)
 {
   v.load(q);
-  if (!row_from_view(A, v, ws, qpos, M, lane))
+  if (rows && !row_from_view(A, v, ws, qpos, M, lane))
     push_unresolved(A, qpos, lane);
   hybrid_from_view(A, v, org, cnt_out, ms);
 }
@@ -354,7 +362,7 @@ __device__ __forceinline__ void finish_normal(const KnnArgs& A, uint32_t qpos, i
 
 template <class V>
 __device__ __forceinline__ void serve_cell(const KnnArgs& A, V& v, WarpScratch* ws, uint32_t qstart, uint32_t qlen,
-                                           uint32_t M, const int3& org, int lane)
+                                           uint32_t M, const int3& org, int lane, bool rows)
 {
   for (uint32_t b0 = 0; b0 < qlen; b0 += 32) {
     const uint32_t nb = min(32u, qlen - b0);
@@ -365,7 +373,7 @@ __device__ __forceinline__ void serve_cell(const KnnArgs& A, V& v, WarpScratch* 
       const int4 q = __ldg(A.pts + qpos);
       int cnt;
       int ms[9];
-      serve_query(A, v, ws, q, qpos, M, org, lane, cnt, ms);
+      serve_query(A, v, ws, q, qpos, M, org, lane, cnt, ms, rows);
       if ((uint32_t)lane == qi) {
         my_cnt = cnt;
 #pragma unroll
@@ -404,7 +412,8 @@ __device__ __forceinline__ uint32_t find_ranges(const KnnArgs& A, uint32_t cell,
   return tot;
 }
 
-__global__ void __launch_bounds__(KTHREADS) knn_cells_kernel(KnnArgs A)
+// Per-cell kernel: the whole cloud when `use_list` is 0, else the cells the group kernel left over.
+__global__ void __launch_bounds__(KTHREADS) knn_cells_kernel(KnnArgs A, int use_list)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -412,47 +421,51 @@ __global__ void __launch_bounds__(KTHREADS) knn_cells_kernel(KnnArgs A)
   uint32_t* spos = reinterpret_cast<uint32_t*>(smem + (size_t)KW * CAP * 16) + (size_t)w * CAP;
   WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + (size_t)KW * CAP * 20) + w;
 
-  const uint32_t cell = blockIdx.x * KW + w;
-  if (cell >= A.n_cells)
-    return;
-  int3 org;
-  const uint32_t M = find_ranges(A, cell, ws, lane, org);
-  const uint32_t qstart = __ldg(A.cell_start + cell);
-  const uint32_t qlen = __ldg(A.cell_start + cell + 1) - qstart;
-  if (M > CAP) {
-    const uint32_t nbatch = (qlen + 31) / 32;
-    uint32_t slot = 0;
-    if (lane == 0) slot = atomicAdd(A.n_big, nbatch);
-    slot = __shfl_sync(FULL_MASK, slot, 0);
-    for (uint32_t b = lane; b < nbatch; b += 32) {
-      A.big_cells[2 * (slot + b)] = cell;
-      A.big_cells[2 * (slot + b) + 1] = b;
+  const uint32_t nitems = use_list ? *A.n_cell_list : A.n_cells;
+  for (uint32_t it = blockIdx.x * KW + w; it < nitems; it += gridDim.x * KW) {
+    const uint32_t item = use_list ? A.cell_list[it] : it;
+    const uint32_t cell = item & ~HYB_ONLY;
+    const bool rows = (item & HYB_ONLY) == 0;
+    int3 org;
+    const uint32_t M = find_ranges(A, cell, ws, lane, org);
+    const uint32_t qstart = __ldg(A.cell_start + cell);
+    const uint32_t qlen = __ldg(A.cell_start + cell + 1) - qstart;
+    if (M > CAP) {
+      const uint32_t nbatch = (qlen + 31) / 32;
+      uint32_t slot = 0;
+      if (lane == 0) slot = atomicAdd(A.n_big, nbatch);
+      slot = __shfl_sync(FULL_MASK, slot, 0);
+      for (uint32_t b = lane; b < nbatch; b += 32) {
+        A.big_cells[2 * (slot + b)] = item;
+        A.big_cells[2 * (slot + b) + 1] = b;
+      }
+      continue;
     }
-    return;
-  }
-  // stage the candidates
-  uint32_t off = 0;
-  for (int c = 0; c < 27; ++c) {
-    const uint32_t s = ws->rs[c], l = ws->rl[c];
-    for (uint32_t t = lane; t < l; t += 32) {
-      sp[off + t] = __ldg(A.pts + s + t);
-      spos[off + t] = s + t;
+    // stage the candidates
+    uint32_t off = 0;
+    for (int c = 0; c < 27; ++c) {
+      const uint32_t s = ws->rs[c], l = ws->rl[c];
+      for (uint32_t t = lane; t < l; t += 32) {
+        sp[off + t] = __ldg(A.pts + s + t);
+        spos[off + t] = s + t;
+      }
+      off += l;
     }
-    off += l;
-  }
-  __syncwarp();
-  if (M <= 128) {
-    CachedView<4> v;
-    v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
-    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
-  } else if (M <= 256) {
-    CachedView<8> v;
-    v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
-    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
-  } else {
-    CachedView<16> v;
-    v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
-    serve_cell(A, v, ws, qstart, qlen, M, org, lane);
+    __syncwarp();
+    if (M <= 128) {
+      CachedView<4> v;
+      v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
+      serve_cell(A, v, ws, qstart, qlen, M, org, lane, rows);
+    } else if (M <= 256) {
+      CachedView<8> v;
+      v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
+      serve_cell(A, v, ws, qstart, qlen, M, org, lane, rows);
+    } else {
+      CachedView<16> v;
+      v.sp = sp; v.spos = spos; v.M = (int)M; v.lane = lane;
+      serve_cell(A, v, ws, qstart, qlen, M, org, lane, rows);
+    }
+    __syncwarp();
   }
 }
 
@@ -538,7 +551,9 @@ __global__ void __launch_bounds__(KTHREADS) knn_big_cells_kernel(KnnArgs A)
   WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + (size_t)KW * CAP * 20) + w;
   const uint32_t nitems = *A.n_big;
   for (uint32_t it = blockIdx.x * KW + w; it < nitems; it += gridDim.x * KW) {
-    const uint32_t cell = A.big_cells[2 * it], batch = A.big_cells[2 * it + 1];
+    const uint32_t item = A.big_cells[2 * it], batch = A.big_cells[2 * it + 1];
+    const uint32_t cell = item & ~HYB_ONLY;
+    const bool rows = (item & HYB_ONLY) == 0;
     int3 org;
     const uint32_t M = find_ranges(A, cell, ws, lane, org);
     const uint32_t cstart = __ldg(A.cell_start + cell);
@@ -559,14 +574,14 @@ __global__ void __launch_bounds__(KTHREADS) knn_big_cells_kernel(KnnArgs A)
       // ---- hybrid set: candidates with d2 < r2i, the max_nn nearest of them ----
       uint32_t c1 = 0;
       const uint32_t T1 = find_threshold(gv, A.r2i, sc.a, (uint32_t)A.max_nn, c1);
-      bool row_done = false;
+      bool row_done = !rows;
       if (T1) {
         const uint32_t m1 = stream_compact(gv, T1, sp, spos, lane);
         CachedView<16> v;
         v.sp = sp; v.spos = spos; v.M = (int)m1; v.lane = lane;
         v.load(q);
         hybrid_from_view(A, v, org, cnt, ms);
-        if (m1 >= (uint32_t)A.K) {  // the K nearest overall are among them (T1 <= r2i <= guar2)
+        if (rows && m1 >= (uint32_t)A.K) {  // the K nearest overall are among them (T1 <= r2i <= guar2)
           row_from_view(A, v, ws, qpos, m1, lane);
           row_done = true;
         }
@@ -602,6 +617,273 @@ __global__ void __launch_bounds__(KTHREADS) knn_big_cells_kernel(KnnArgs A)
     if ((uint32_t)lane < nb)
       finish_normal(A, qstart + lane, my_cnt, my_ms, org);
     __syncwarp();
+  }
+}
+
+// ---- the fast path: one warp per 2x2x2 group of cells, one query per lane ----------------------------------
+// The points of a level-1 Morton parent (8 cells) are one contiguous range of the sorted cloud, and the union of
+// their 27-cell neighbourhoods is the 4x4x4 block of cells around the parent.  The warp stages that block once
+// (the group's own points first: they are the queries), then every lane serves ONE query: it walks the staged
+// candidates (a shared-memory broadcast per candidate), keeps its K best (d^2, original index) keys in a sorted
+// register list and sums the integer moments of everything inside the radius on the way.  No warp-wide
+// selection, no re-reading: ~10 instructions per candidate and lane, an insertion only while the list still
+// improves.  A superset of the 27 cells changes nothing in the exactness argument (rows with K-th d^2 <
+// (cell+1)^2 are exact).  Left to the per-cell kernels: groups with more than GCAP candidates (dense scans) and
+// -- hybrid set only -- groups where some query has more than max_nn points inside the radius (the max_nn
+// nearest of them then need a selection).
+constexpr int GCAP = 1024;  // staged candidates per warp
+constexpr int GKW = 4;      // warps per block
+
+struct GroupScratch {
+  uint32_t rs[64];   // start of the range in the sorted cloud, slot order = 2 * lane + {0, 1}
+  uint32_t ro[65];   // its offset in the staging area (non-decreasing), ro[64] = M
+  int32_t rows[32 * 16];
+};
+
+// one level of the cell hierarchy as the group kernel sees it
+struct GridLevel {
+  const uint32_t* cell_start;
+  const uint64_t* hk;
+  const uint32_t* hv;
+  uint64_t hmask;
+  uint32_t gmax[3];
+  uint32_t guar2;  // (edge + 1)^2
+};
+
+template <int KT>
+__device__ __forceinline__ void list_insert(unsigned long long (&L)[KT], unsigned long long key)
+{
+#pragma unroll
+  for (int i = KT - 1; i > 0; --i) {
+    const unsigned long long below = L[i - 1];
+    L[i] = key < below ? below : (key < L[i] ? key : L[i]);
+  }
+  L[0] = key < L[0] ? key : L[0];
+}
+
+enum { GROUP_DONE = 0, GROUP_TOO_BIG = 1, GROUP_HYBRID_LEFT = 2 };
+
+// Serves the queries [qstart, qstart + Q) -- the points of the 2x2x2 block of level-`G` cells whose parent has
+// the Morton code P -- from the 4x4x4 block of cells around it.  Returns GROUP_TOO_BIG (nothing done) when the
+// block holds more than GCAP points.
+template <int KT>
+__device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uint32_t qstart, uint32_t Q, int4* sp,
+                           GroupScratch* gs, int lane)
+{
+  // the 56 other cells of the 4x4x4 block
+  const int64_t bx = 2 * (int64_t)morton_compact21(P) - 1, by = 2 * (int64_t)morton_compact21(P >> 1) - 1,
+                bz = 2 * (int64_t)morton_compact21(P >> 2) - 1;
+  uint32_t st2[2], ln2[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    const int dx = i & 3, dy = (i >> 2) & 3, dz = i >> 4;
+    st2[h] = 0;
+    ln2[h] = 0;
+    const bool own = (dx == 1 || dx == 2) && (dy == 1 || dy == 2) && (dz == 1 || dz == 2);
+    const int64_t nx = bx + dx, ny = by + dy, nz = bz + dz;
+    if (!own && nx >= 0 && ny >= 0 && nz >= 0 && nx <= G.gmax[0] && ny <= G.gmax[1] && nz <= G.gmax[2]) {
+      const uint32_t c = hash_lookup(G.hk, G.hv, G.hmask, morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+      if (c != 0xffffffffu) {
+        st2[h] = __ldg(G.cell_start + c);
+        ln2[h] = __ldg(G.cell_start + c + 1) - st2[h];
+      }
+    }
+  }
+  uint32_t incl = ln2[0] + ln2[1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const uint32_t M = Q + __shfl_sync(FULL_MASK, incl, 31);
+  if (M > (uint32_t)GCAP)
+    return GROUP_TOO_BIG;
+  __syncwarp();
+  {
+    const uint32_t base = Q + incl - (ln2[0] + ln2[1]);
+    gs->rs[2 * lane] = st2[0];
+    gs->ro[2 * lane] = base;
+    gs->rs[2 * lane + 1] = st2[1];
+    gs->ro[2 * lane + 1] = base + ln2[0];
+    if (lane == 31) gs->ro[64] = M;
+  }
+  __syncwarp();
+  // stage: the group's own points (the queries) first, then the 56 ranges flattened
+  for (uint32_t e = lane; e < Q; e += 32) sp[e] = __ldg(A.pts + qstart + e);
+  for (uint32_t e = Q + lane; e < M; e += 32) {
+    int lo = 0, hi = 64;  // first slot with ro > e
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (gs->ro[mid] > e) hi = mid;
+      else lo = mid + 1;
+    }
+    const int sidx = lo - 1;
+    sp[e] = __ldg(A.pts + gs->rs[sidx] + (e - gs->ro[sidx]));
+  }
+  __syncwarp();
+  bool hybrid_left = false;
+  for (uint32_t b0 = 0; b0 < Q; b0 += 32) {
+    const uint32_t nb = min(32u, Q - b0);
+    const bool act = (uint32_t)lane < nb;
+    const int4 q = sp[act ? b0 + lane : 0];
+    unsigned long long L[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) L[i] = ~0ull;
+    uint32_t cnt = 0;
+    uint32_t a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t j = 0; j < M; ++j) {
+      const int4 c = sp[j];
+      const int dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
+      const uint32_t d2 = (uint32_t)(dx * dx) + (uint32_t)(dy * dy) + (uint32_t)(dz * dz);
+      if (d2 < A.r2i) {
+        ++cnt;
+        a[0] += (uint32_t)dx; a[1] += (uint32_t)dy; a[2] += (uint32_t)dz;
+        a[3] += (uint32_t)(dx * dx); a[4] += (uint32_t)(dx * dy); a[5] += (uint32_t)(dx * dz);
+        a[6] += (uint32_t)(dy * dy); a[7] += (uint32_t)(dy * dz); a[8] += (uint32_t)(dz * dz);
+      }
+      const unsigned long long key = ((unsigned long long)d2 << 32) | (uint32_t)c.w;
+      if (key < L[KT - 1]) list_insert<KT>(L, key);
+    }
+    // ---- rows: sorted positions of the K best, through shared memory for a coalesced store ----
+    const uint32_t qpos = qstart + b0 + lane;
+    __syncwarp();
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < KT; ++i)
+        gs->rows[lane * KT + i] = L[i] == ~0ull ? -1 : (int32_t)__ldg(A.inv + (uint32_t)L[i]);
+      const bool resolved = L[KT - 1] != ~0ull && (uint32_t)(L[KT - 1] >> 32) < G.guar2;
+      if (!resolved) {
+        const uint32_t slot = atomicAdd(A.n_unres, 1u);
+        A.unres[slot] = qpos;
+      }
+    }
+    __syncwarp();
+    {
+      int32_t* dst = A.nbr + (int64_t)(qstart + b0) * KT;
+      for (uint32_t e = lane; e < nb * KT; e += 32) dst[e] = gs->rows[e];
+    }
+    // ---- hybrid set: everything inside the radius, or the max_nn nearest of it ----
+    bool over = act && cnt > (uint32_t)A.max_nn;
+    if (__any_sync(FULL_MASK, over)) {
+      if (A.max_nn < KT) {
+        hybrid_left = true;  // odd parameters: the per-cell kernels select
+      } else {
+        // T = the max_nn-th smallest key: the list holds the first KT, further passes fetch the next KT above
+        // the last one known (keys are unique: the index is part of them)
+        unsigned long long T = L[KT - 1];
+        int more = over ? A.max_nn - KT : 0;
+        while (__any_sync(FULL_MASK, more > 0)) {
+          const unsigned long long lower = T;
+#pragma unroll
+          for (int i = 0; i < KT; ++i) L[i] = ~0ull;
+          for (uint32_t j = 0; j < M; ++j) {
+            const int4 c = sp[j];
+            const int dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
+            const uint32_t d2 = (uint32_t)(dx * dx) + (uint32_t)(dy * dy) + (uint32_t)(dz * dz);
+            const unsigned long long key = ((unsigned long long)d2 << 32) | (uint32_t)c.w;
+            if (more > 0 && key > lower && key < L[KT - 1]) list_insert<KT>(L, key);
+          }
+          if (more > 0) {
+            const int take = more < KT ? more : KT;
+            unsigned long long t = L[0];
+#pragma unroll
+            for (int i = 1; i < KT; ++i)
+              if (i < take) t = L[i];
+            T = t;
+            more -= take;
+          }
+        }
+        if (over) {
+          cnt = (uint32_t)A.max_nn;
+#pragma unroll
+          for (int m = 0; m < 9; ++m) a[m] = 0;
+        }
+        for (uint32_t j = 0; j < M; ++j) {
+          const int4 c = sp[j];
+          const int dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
+          const uint32_t d2 = (uint32_t)(dx * dx) + (uint32_t)(dy * dy) + (uint32_t)(dz * dz);
+          const unsigned long long key = ((unsigned long long)d2 << 32) | (uint32_t)c.w;
+          if (over && key <= T) {
+            a[0] += (uint32_t)dx; a[1] += (uint32_t)dy; a[2] += (uint32_t)dz;
+            a[3] += (uint32_t)(dx * dx); a[4] += (uint32_t)(dx * dy); a[5] += (uint32_t)(dx * dz);
+            a[6] += (uint32_t)(dy * dy); a[7] += (uint32_t)(dy * dz); a[8] += (uint32_t)(dz * dz);
+          }
+        }
+        over = false;
+      }
+    }
+    if (act && !over) {
+      int ms[9];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) ms[m] = (int)a[m];
+      finish_normal(A, qpos, (int)cnt, ms, make_int3(q.x, q.y, q.z));
+    }
+    __syncwarp();
+  }
+  return hybrid_left ? GROUP_HYBRID_LEFT : GROUP_DONE;
+}
+
+__device__ __forceinline__ void push_cells(const KnnArgs& A, uint32_t c0, int ng, uint32_t flag, int lane)
+{
+  uint32_t slot = 0;
+  if (lane == 0) slot = atomicAdd(A.n_cell_list, (uint32_t)ng);
+  slot = __shfl_sync(FULL_MASK, slot, 0);
+  if (lane < ng) A.cell_list[slot + lane] = (c0 + lane) | flag;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(GKW * 32) knn_groups_kernel(KnnArgs A, GridLevel G0, GridLevel G1, int have_mid)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int4* sp = reinterpret_cast<int4*>(smem) + (size_t)w * GCAP;
+  GroupScratch* gs = reinterpret_cast<GroupScratch*>(smem + (size_t)GKW * GCAP * 16) + w;
+  const uint32_t n_chunks = (A.n_cells + 31) / 32;
+  for (;;) {
+    uint32_t chunk = 0;
+    if (lane == 0) chunk = atomicAdd(A.next_chunk, 1u);
+    chunk = __shfl_sync(FULL_MASK, chunk, 0);
+    if (chunk >= n_chunks)
+      break;
+    // group leaders among the chunk's 32 cells: first cell of its level-1 parent
+    const uint32_t myc = chunk * 32 + lane;
+    uint64_t mykey = 0;
+    bool leader = false;
+    if (myc < A.n_cells) {
+      mykey = __ldg(A.cell_key + myc);
+      leader = myc == 0 || (__ldg(A.cell_key + myc - 1) >> 3) != (mykey >> 3);
+    }
+    uint32_t leaders = __ballot_sync(FULL_MASK, leader);
+    while (leaders) {
+      const int ll = __ffs(leaders) - 1;
+      leaders &= leaders - 1;
+      const uint32_t c0 = chunk * 32 + ll;
+      const uint64_t P = __shfl_sync(FULL_MASK, mykey, ll) >> 3;
+      // cells of the group (contiguous: the keys are sorted)
+      bool in = false;
+      if (lane < 8 && c0 + lane < A.n_cells) in = (__ldg(A.cell_key + c0 + lane) >> 3) == P;
+      const int ng = __popc(__ballot_sync(FULL_MASK, in));
+      const uint32_t qstart = __ldg(A.cell_start + c0);
+      const uint32_t Q = __ldg(A.cell_start + c0 + ng) - qstart;
+      const int r = serve_group<KT>(A, G0, P, qstart, Q, sp, gs, lane);
+      if (r == GROUP_HYBRID_LEFT) {
+        push_cells(A, c0, ng, HYB_ONLY, lane);
+      } else if (r == GROUP_TOO_BIG) {
+        if (!have_mid) {
+          push_cells(A, c0, ng, 0u, lane);  // dense: the per-cell kernels take the group's cells
+        } else {
+          // dense: every cell of the group becomes a group of the finer level (its 8 half-size cells)
+          for (int i = 0; i < ng; ++i) {
+            const uint32_t cs = __ldg(A.cell_start + c0 + i);
+            const uint32_t cq = __ldg(A.cell_start + c0 + i + 1) - cs;
+            const int r1 = serve_group<KT>(A, G1, __ldg(A.cell_key + c0 + i), cs, cq, sp, gs, lane);
+            if (r1 != GROUP_DONE) push_cells(A, c0 + i, 1, r1 == GROUP_HYBRID_LEFT ? HYB_ONLY : 0u, lane);
+          }
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -760,7 +1042,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   RC_CHECK(dev_ensure(c, c->nrm, (size_t)n * 24));
   RC_CHECK(dev_ensure(c, c->curv, (size_t)n * 8));
   const size_t max_items = (size_t)c->n_cells + (size_t)n / 32 + 8;
-  RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + 2 * max_items + 16) * 4));
+  RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + 2 * max_items + (size_t)c->n_cells + 16) * 4));
   RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
 
   KnnArgs A;
@@ -792,12 +1074,48 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   A.n_unres = cnt + 1;
   A.big_cells = dptr<uint32_t>(c->worklist);
   A.unres = dptr<uint32_t>(c->worklist) + 2 * max_items;
+  A.cell_list = A.unres + n;
+  A.n_cell_list = cnt + 2;
+  A.next_chunk = cnt + 3;
+  A.inv = dptr<uint32_t>(c->inv);
   A.n = n;
 
   STAGE_BEGIN(c, EV_KNN);
-  CU_CHECK(c, cudaMemsetAsync(cnt, 0, 2 * sizeof(uint32_t), c->stream));
+  CU_CHECK(c, cudaMemsetAsync(cnt, 0, 4 * sizeof(uint32_t), c->stream));
   const size_t smem = (size_t)KW * CAP * 20 + KW * sizeof(WarpScratch);
-  knn_cells_kernel<<<(unsigned)ceil_div64(c->n_cells, KW), KTHREADS, smem, c->stream>>>(A);
+  // the group kernel serves K = 15 (the reference) and 16; BSEG_KNN_GROUPS=0 forces the per-cell kernels
+  static const bool groups_on = !(getenv("BSEG_KNN_GROUPS") && atoi(getenv("BSEG_KNN_GROUPS")) == 0);
+  const bool groups = groups_on && (p->K == 15 || p->K == 16);
+  if (groups) {
+    const size_t gsmem = (size_t)GKW * GCAP * 16 + GKW * sizeof(GroupScratch);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_CHECK(c, cudaFuncSetAttribute(knn_groups_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+      CU_CHECK(c, cudaFuncSetAttribute(knn_groups_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+      attr_set = true;
+    }
+    GridLevel G0, G1;
+    G0.cell_start = A.cell_start; G0.hk = A.hk; G0.hv = A.hv; G0.hmask = A.hmask; G0.guar2 = A.guar2;
+    for (int k = 0; k < 3; ++k) G0.gmax[k] = A.gmax[k];
+    G1 = G0;
+    const bool mid = c->have_mid && (c->cell % 2) == 0 && (double)(c->cell / 2) >= p->radius;
+    if (mid) {
+      const int32_t cell2 = c->cell / 2;
+      G1.cell_start = dptr<uint32_t>(c->cell_start2);
+      G1.hk = dptr<uint64_t>(c->hash_keys2);
+      G1.hv = dptr<uint32_t>(c->hash_vals2);
+      G1.hmask = c->hash_mask2;
+      G1.guar2 = (uint32_t)(cell2 + 1) * (uint32_t)(cell2 + 1);
+      for (int k = 0; k < 3; ++k) G1.gmax[k] = (uint32_t)(c->mx[k] - c->mn[k]) / (uint32_t)cell2;
+    }
+    const unsigned gb = (unsigned)(c->num_sms * 3);
+    if (p->K == 15) knn_groups_kernel<15><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1, mid ? 1 : 0);
+    else knn_groups_kernel<16><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1, mid ? 1 : 0);
+    KLAUNCH_CHECK(c);
+    knn_cells_kernel<<<c->num_sms * 4, KTHREADS, smem, c->stream>>>(A, 1);
+  } else {
+    knn_cells_kernel<<<c->num_sms * 8, KTHREADS, smem, c->stream>>>(A, 0);
+  }
   KLAUNCH_CHECK(c);
   knn_big_cells_kernel<<<c->num_sms * 4, KTHREADS, smem, c->stream>>>(A);
   KLAUNCH_CHECK(c);
