@@ -57,6 +57,10 @@ struct KnnArgs {
   uint32_t* cell_list;
   uint32_t* n_cell_list;
   uint32_t* next_chunk;       // work counter of the group kernel
+  // 32-query batches of groups whose block does not fit the staging area (streamed in chunks, one warp per batch)
+  uint32_t* dense_items;      // (cell | level << 31, batch)
+  uint32_t* n_dense;
+  uint32_t* next_dense;
 };
 constexpr uint32_t HYB_ONLY = 0x80000000u;
 
@@ -666,9 +670,12 @@ enum { GROUP_DONE = 0, GROUP_TOO_BIG = 1, GROUP_HYBRID_LEFT = 2 };
 // Serves the queries [qstart, qstart + Q) -- the points of the 2x2x2 block of level-`G` cells whose parent has
 // the Morton code P -- from the 4x4x4 block of cells around it.  Returns GROUP_TOO_BIG (nothing done) when the
 // block holds more than GCAP points.
+// `item` >= 0: the call comes from the main pass; a block that has to be streamed is not served but queued, one
+// work item (item, batch) per 32 queries, so that a crowded group is shared by many warps.  Otherwise only the
+// batches [b_begin, b_end) are served.
 template <int KT>
 __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uint32_t qstart, uint32_t Q, int4* sp,
-                           GroupScratch* gs, int lane)
+                           GroupScratch* gs, int lane, bool allow_chunks, int64_t item, uint32_t b_begin, uint32_t b_end)
 {
   // the 56 other cells of the 4x4x4 block
   const int64_t bx = 2 * (int64_t)morton_compact21(P) - 1, by = 2 * (int64_t)morton_compact21(P >> 1) - 1,
@@ -697,8 +704,20 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
     if (lane >= o) incl += v;
   }
   const uint32_t M = Q + __shfl_sync(FULL_MASK, incl, 31);
-  if (M > (uint32_t)GCAP)
+  const bool single = M <= (uint32_t)GCAP;  // else the block is streamed through the staging area in chunks
+  if (!single && !allow_chunks)
     return GROUP_TOO_BIG;
+  if (!single && item >= 0) {
+    const uint32_t nbatch = (Q + 31) / 32;
+    uint32_t slot = 0;
+    if (lane == 0) slot = atomicAdd(A.n_dense, nbatch);
+    slot = __shfl_sync(FULL_MASK, slot, 0);
+    for (uint32_t b = lane; b < nbatch; b += 32) {
+      A.dense_items[2 * (slot + b)] = (uint32_t)item;
+      A.dense_items[2 * (slot + b) + 1] = b;
+    }
+    return GROUP_DONE;
+  }
   __syncwarp();
   {
     const uint32_t base = Q + incl - (ln2[0] + ln2[1]);
@@ -709,31 +728,50 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
     if (lane == 31) gs->ro[64] = M;
   }
   __syncwarp();
-  // stage: the group's own points (the queries) first, then the 56 ranges flattened
-  for (uint32_t e = lane; e < Q; e += 32) sp[e] = __ldg(A.pts + qstart + e);
-  for (uint32_t e = Q + lane; e < M; e += 32) {
-    int lo = 0, hi = 64;  // first slot with ro > e
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (gs->ro[mid] > e) hi = mid;
-      else lo = mid + 1;
+  // candidate e of the block: the group's own points (the queries) first, then the 56 ranges flattened
+  auto stage = [&](uint32_t base, uint32_t m) {
+    for (uint32_t t = lane; t < m; t += 32) {
+      const uint32_t e = base + t;
+      if (e < Q) {
+        sp[t] = __ldg(A.pts + qstart + e);
+      } else {
+        int lo = 0, hi = 64;  // first slot with ro > e
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (gs->ro[mid] > e) hi = mid;
+          else lo = mid + 1;
+        }
+        const int sidx = lo - 1;
+        sp[t] = __ldg(A.pts + gs->rs[sidx] + (e - gs->ro[sidx]));
+      }
     }
-    const int sidx = lo - 1;
-    sp[e] = __ldg(A.pts + gs->rs[sidx] + (e - gs->ro[sidx]));
-  }
-  __syncwarp();
+    __syncwarp();
+  };
+  // f(candidate) for every point of the block
+  auto scan = [&](auto&& f) {
+    if (single) {
+      for (uint32_t j = 0; j < M; ++j) f(sp[j]);
+    } else {
+      for (uint32_t base = 0; base < M; base += GCAP) {
+        const uint32_t m = min((uint32_t)GCAP, M - base);
+        __syncwarp();
+        stage(base, m);
+        for (uint32_t j = 0; j < m; ++j) f(sp[j]);
+      }
+    }
+  };
+  if (single) stage(0, M);
   bool hybrid_left = false;
-  for (uint32_t b0 = 0; b0 < Q; b0 += 32) {
+  for (uint32_t b0 = 32 * b_begin; b0 < Q && b0 < 32 * (uint64_t)b_end; b0 += 32) {
     const uint32_t nb = min(32u, Q - b0);
     const bool act = (uint32_t)lane < nb;
-    const int4 q = sp[act ? b0 + lane : 0];
+    const int4 q = __ldg(A.pts + qstart + (act ? b0 + lane : 0));
     unsigned long long L[KT];
 #pragma unroll
     for (int i = 0; i < KT; ++i) L[i] = ~0ull;
     uint32_t cnt = 0;
     uint32_t a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (uint32_t j = 0; j < M; ++j) {
-      const int4 c = sp[j];
+    scan([&](const int4& c) {
       const int dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
       const uint32_t d2 = (uint32_t)(dx * dx) + (uint32_t)(dy * dy) + (uint32_t)(dz * dz);
       if (d2 < A.r2i) {
@@ -744,7 +782,7 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
       }
       const unsigned long long key = ((unsigned long long)d2 << 32) | (uint32_t)c.w;
       if (key < L[KT - 1]) list_insert<KT>(L, key);
-    }
+    });
     // ---- rows: sorted positions of the K best, through shared memory for a coalesced store ----
     const uint32_t qpos = qstart + b0 + lane;
     __syncwarp();
@@ -777,13 +815,12 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
           const unsigned long long lower = T;
 #pragma unroll
           for (int i = 0; i < KT; ++i) L[i] = ~0ull;
-          for (uint32_t j = 0; j < M; ++j) {
-            const int4 c = sp[j];
+          scan([&](const int4& c) {
             const int dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
             const uint32_t d2 = (uint32_t)(dx * dx) + (uint32_t)(dy * dy) + (uint32_t)(dz * dz);
             const unsigned long long key = ((unsigned long long)d2 << 32) | (uint32_t)c.w;
             if (more > 0 && key > lower && key < L[KT - 1]) list_insert<KT>(L, key);
-          }
+          });
           if (more > 0) {
             const int take = more < KT ? more : KT;
             unsigned long long t = L[0];
@@ -799,8 +836,7 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
 #pragma unroll
           for (int m = 0; m < 9; ++m) a[m] = 0;
         }
-        for (uint32_t j = 0; j < M; ++j) {
-          const int4 c = sp[j];
+        scan([&](const int4& c) {
           const int dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
           const uint32_t d2 = (uint32_t)(dx * dx) + (uint32_t)(dy * dy) + (uint32_t)(dz * dz);
           const unsigned long long key = ((unsigned long long)d2 << 32) | (uint32_t)c.w;
@@ -809,7 +845,7 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
             a[3] += (uint32_t)(dx * dx); a[4] += (uint32_t)(dx * dy); a[5] += (uint32_t)(dx * dz);
             a[6] += (uint32_t)(dy * dy); a[7] += (uint32_t)(dy * dz); a[8] += (uint32_t)(dz * dz);
           }
-        }
+        });
         over = false;
       }
     }
@@ -866,7 +902,7 @@ __global__ void __launch_bounds__(GKW * 32) knn_groups_kernel(KnnArgs A, GridLev
       const int ng = __popc(__ballot_sync(FULL_MASK, in));
       const uint32_t qstart = __ldg(A.cell_start + c0);
       const uint32_t Q = __ldg(A.cell_start + c0 + ng) - qstart;
-      const int r = serve_group<KT>(A, G0, P, qstart, Q, sp, gs, lane);
+      const int r = serve_group<KT>(A, G0, P, qstart, Q, sp, gs, lane, !have_mid, (int64_t)c0, 0u, 0xffffffffu);
       if (r == GROUP_HYBRID_LEFT) {
         push_cells(A, c0, ng, HYB_ONLY, lane);
       } else if (r == GROUP_TOO_BIG) {
@@ -877,13 +913,53 @@ __global__ void __launch_bounds__(GKW * 32) knn_groups_kernel(KnnArgs A, GridLev
           for (int i = 0; i < ng; ++i) {
             const uint32_t cs = __ldg(A.cell_start + c0 + i);
             const uint32_t cq = __ldg(A.cell_start + c0 + i + 1) - cs;
-            const int r1 = serve_group<KT>(A, G1, __ldg(A.cell_key + c0 + i), cs, cq, sp, gs, lane);
+            const int r1 = serve_group<KT>(A, G1, __ldg(A.cell_key + c0 + i), cs, cq, sp, gs, lane, true,
+                                           (int64_t)((c0 + i) | 0x80000000u), 0u, 0xffffffffu);
             if (r1 != GROUP_DONE) push_cells(A, c0 + i, 1, r1 == GROUP_HYBRID_LEFT ? HYB_ONLY : 0u, lane);
           }
         }
       }
       __syncwarp();
     }
+  }
+}
+
+// one warp per queued batch of a crowded group: the block is streamed through the staging area
+template <int KT>
+__global__ void __launch_bounds__(GKW * 32) knn_dense_kernel(KnnArgs A, GridLevel G0, GridLevel G1)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int4* sp = reinterpret_cast<int4*>(smem) + (size_t)w * GCAP;
+  GroupScratch* gs = reinterpret_cast<GroupScratch*>(smem + (size_t)GKW * GCAP * 16) + w;
+  const uint32_t nitems = *A.n_dense;
+  for (;;) {
+    uint32_t it = 0;
+    if (lane == 0) it = atomicAdd(A.next_dense, 1u);
+    it = __shfl_sync(FULL_MASK, it, 0);
+    if (it >= nitems)
+      break;
+    const uint32_t item = A.dense_items[2 * it], batch = A.dense_items[2 * it + 1];
+    const uint32_t c = item & 0x7fffffffu;
+    int r;
+    int ng = 1;
+    if (item & 0x80000000u) {  // a cell of the coarse table as a group of the finer one
+      const uint32_t cs = __ldg(A.cell_start + c);
+      const uint32_t cq = __ldg(A.cell_start + c + 1) - cs;
+      r = serve_group<KT>(A, G1, __ldg(A.cell_key + c), cs, cq, sp, gs, lane, true, -1, batch, batch + 1);
+    } else {
+      const uint64_t P = __ldg(A.cell_key + c) >> 3;
+      bool in = false;
+      if (lane < 8 && c + lane < A.n_cells) in = (__ldg(A.cell_key + c + lane) >> 3) == P;
+      ng = __popc(__ballot_sync(FULL_MASK, in));
+      const uint32_t qstart = __ldg(A.cell_start + c);
+      const uint32_t Q = __ldg(A.cell_start + c + ng) - qstart;
+      r = serve_group<KT>(A, G0, P, qstart, Q, sp, gs, lane, true, -1, batch, batch + 1);
+    }
+    // odd parameters (max_nn < K): the per-cell kernels select the hybrid sets of the whole group
+    (void)r;
+    if (batch == 0 && A.max_nn < KT) push_cells(A, c, ng, HYB_ONLY, lane);
+    __syncwarp();
   }
 }
 
@@ -1042,7 +1118,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   RC_CHECK(dev_ensure(c, c->nrm, (size_t)n * 24));
   RC_CHECK(dev_ensure(c, c->curv, (size_t)n * 8));
   const size_t max_items = (size_t)c->n_cells + (size_t)n / 32 + 8;
-  RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + 2 * max_items + (size_t)c->n_cells + 16) * 4));
+  RC_CHECK(dev_ensure(c, c->worklist, ((size_t)n + 4 * max_items + (size_t)c->n_cells + 16) * 4));
   RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
 
   KnnArgs A;
@@ -1077,14 +1153,17 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   A.cell_list = A.unres + n;
   A.n_cell_list = cnt + 2;
   A.next_chunk = cnt + 3;
+  A.n_dense = cnt + 4;
+  A.next_dense = cnt + 5;
+  A.dense_items = A.cell_list + c->n_cells;
   A.inv = dptr<uint32_t>(c->inv);
   A.n = n;
 
   STAGE_BEGIN(c, EV_KNN);
-  CU_CHECK(c, cudaMemsetAsync(cnt, 0, 4 * sizeof(uint32_t), c->stream));
+  CU_CHECK(c, cudaMemsetAsync(cnt, 0, 6 * sizeof(uint32_t), c->stream));
   const size_t smem = (size_t)KW * CAP * 20 + KW * sizeof(WarpScratch);
   // the group kernel serves K = 15 (the reference) and 16; BSEG_KNN_GROUPS=0 forces the per-cell kernels
-  static const bool groups_on = !(getenv("BSEG_KNN_GROUPS") && atoi(getenv("BSEG_KNN_GROUPS")) == 0);
+  const bool groups_on = !(getenv("BSEG_KNN_GROUPS") && atoi(getenv("BSEG_KNN_GROUPS")) == 0);
   const bool groups = groups_on && (p->K == 15 || p->K == 16);
   if (groups) {
     const size_t gsmem = (size_t)GKW * GCAP * 16 + GKW * sizeof(GroupScratch);
@@ -1092,6 +1171,8 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
     if (!attr_set) {
       CU_CHECK(c, cudaFuncSetAttribute(knn_groups_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
       CU_CHECK(c, cudaFuncSetAttribute(knn_groups_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+      CU_CHECK(c, cudaFuncSetAttribute(knn_dense_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+      CU_CHECK(c, cudaFuncSetAttribute(knn_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
       attr_set = true;
     }
     GridLevel G0, G1;
@@ -1111,6 +1192,9 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
     const unsigned gb = (unsigned)(c->num_sms * 3);
     if (p->K == 15) knn_groups_kernel<15><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1, mid ? 1 : 0);
     else knn_groups_kernel<16><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1, mid ? 1 : 0);
+    KLAUNCH_CHECK(c);
+    if (p->K == 15) knn_dense_kernel<15><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1);
+    else knn_dense_kernel<16><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1);
     KLAUNCH_CHECK(c);
     knn_cells_kernel<<<c->num_sms * 4, KTHREADS, smem, c->stream>>>(A, 1);
   } else {

@@ -101,12 +101,25 @@ def test_voxel_units(ctx):
     _check_case(ctx, cases.voxels(40000), K=16, radius=2.5, max_nn=50)
 
 
-def test_dense_cells_use_streaming_path(ctx):
-    """> 512 candidates in the 27-cell block: the global-memory streaming variant serves the cell."""
+def test_dense_groups_are_streamed_in_chunks(ctx):
+    """30 000 points in a 300 mm cube: far more than the staging area of a group holds => the group kernel
+    streams the block in chunks (and every radius is crowded: the max_nn nearest come from further passes)."""
+    rng = np.random.default_rng(11)
+    xyz = rng.integers(0, 300, (30000, 3)).astype(np.int32)
+    _check_case(ctx, xyz, K=15, radius=100.0, max_nn=50, cell=100)
+    _check_case(ctx, xyz, K=16, radius=100.0, max_nn=20, cell=100)
+
+
+def test_per_cell_kernels_alone(ctx, monkeypatch):
+    """BSEG_KNN_GROUPS=0: the per-cell kernels (the path of K other than 15/16) serve the whole cloud, including
+    the global-memory streaming variant for blocks of more than 512 candidates."""
+    monkeypatch.setenv("BSEG_KNN_GROUPS", "0")
     rng = np.random.default_rng(11)
     xyz = rng.integers(0, 300, (30000, 3)).astype(np.int32)
     t = _check_case(ctx, xyz, K=15, radius=100.0, max_nn=50, cell=100)
     assert t["n_big_cells"] > 0
+    _check_case(ctx, cases.block(60000))
+    _check_case(ctx, cases.quantised(30000))
 
 
 def test_extent_limit_is_loud(ctx):
