@@ -111,7 +111,8 @@ def make_workload(name, n, rank=0, world=1):
     if world > 1:
         # C5-style city tile = C2-like blocks side by side: rank r owns the 200 m block at x = r * 200 m, so the
         # per-GPU work is the N = 1 workload (same generator, another seed) plus the exchange with the neighbours
-        rng = np.random.default_rng(1005 + rank)
+        # (seed 1002 + rank: rank 0's block IS the C2 cloud of the N = 1 run, so the per-N values are comparable)
+        rng = np.random.default_rng(1002 + rank)
         pts = synth._block(rng, n, rank * SLAB_M, 0.0, SLAB_M, 40, 0.15, "shuffled")
         return np.ascontiguousarray(synth.to_mm(pts))
     return synth.make(name, n)
