@@ -339,6 +339,16 @@ BSEG_API int bseg_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int
   return stage_raster_size(c, p, W, H);
 }
 
+BSEG_API int bseg_label_raster(bseg_ctx* c, const bseg_params* p, const uint16_t* plane_rgb_Px3, int32_t* label_WxH,
+                               uint8_t* rgb_WxHx3)
+{
+  RC_CHECK(check_ctx(c));
+  RC_CHECK(check_params(c, p));
+  if (!c->have_grow)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_label_raster before bseg_grow_planes");
+  return stage_label_raster(c, p, plane_rgb_Px3, label_WxH, rgb_WxHx3);
+}
+
 BSEG_API int bseg_raster(bseg_ctx* c, const bseg_params* p, double* image_WxHx3, uint8_t* png_a, uint8_t* png_b,
                          uint8_t* png_c, double* ground_th)
 {

@@ -269,3 +269,73 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
   }
   return 0;
 }
+
+// ---- label raster (north_star stage 5; the reference has no counterpart: its images are height / count) ------
+// Pixel (x / bin, y / bin) of the W x H grid of the height map shows the plane label of its HIGHEST point
+// (ties: the lower original index); 0 where the pixel is empty or that point belongs to no plane.  One
+// atomicMax per point on a packed (z, ~index) key, then one pass over the pixels.
+namespace {
+__global__ void __launch_bounds__(TPB) label_top_kernel(const int32_t* __restrict__ xyz, int64_t n, int32_t bin, int32_t W,
+                                                        unsigned long long* __restrict__ top)
+{
+  int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  const unsigned long long key = ((unsigned long long)(uint32_t)z << 32) | (uint32_t)~(uint32_t)i;
+  atomicMax(top + (int64_t)(y / bin) * W + (x / bin), key + 1ull);  // 0 = empty pixel
+}
+
+__global__ void __launch_bounds__(TPB) label_pixels_kernel(const unsigned long long* __restrict__ top, int64_t npx,
+                                                           const int32_t* __restrict__ label,
+                                                           const uint16_t* __restrict__ plane_rgb,
+                                                           int32_t* __restrict__ out_label, uint8_t* __restrict__ out_rgb)
+{
+  int64_t px = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (px >= npx)
+    return;
+  const unsigned long long t = top[px];
+  int32_t l = 0;
+  if (t) l = label[~(uint32_t)((t - 1ull) & 0xffffffffull)];
+  out_label[px] = l;
+  if (out_rgb) {
+    uint8_t r = 0, g = 0, b = 0;
+    if (l > 0 && plane_rgb) {
+      r = (uint8_t)plane_rgb[3 * (int64_t)(l - 1)];
+      g = (uint8_t)plane_rgb[3 * (int64_t)(l - 1) + 1];
+      b = (uint8_t)plane_rgb[3 * (int64_t)(l - 1) + 2];
+    }
+    out_rgb[3 * px] = r;
+    out_rgb[3 * px + 1] = g;
+    out_rgb[3 * px + 2] = b;
+  }
+}
+}  // namespace
+
+int stage_label_raster(bseg_ctx* c, const bseg_params* p, const uint16_t* h_plane_rgb, int32_t* h_label, uint8_t* h_rgb)
+{
+  int32_t W = 0, H = 0;
+  RC_CHECK(stage_raster_size(c, p, &W, &H));
+  const int64_t n = c->n, npx = (int64_t)W * H;
+  if (n == 0 || npx == 0)
+    return 0;
+  const size_t rgb_bytes = (size_t)c->n_planes * 6;
+  // top keys | labels | rgb | plane colours
+  RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)npx * (8 + 4 + 3) + rgb_bytes + 64));
+  unsigned long long* top = dptr<unsigned long long>(c->out_tmp);
+  int32_t* d_label = reinterpret_cast<int32_t*>(top + npx);
+  uint16_t* d_prgb = reinterpret_cast<uint16_t*>(d_label + npx);
+  uint8_t* d_rgb = reinterpret_cast<uint8_t*>(d_prgb) + ((rgb_bytes + 15) & ~(size_t)15);
+  CU_CHECK(c, cudaMemsetAsync(top, 0, (size_t)npx * 8, c->stream));
+  if (h_plane_rgb && rgb_bytes)
+    CU_CHECK(c, cudaMemcpyAsync(d_prgb, h_plane_rgb, rgb_bytes, cudaMemcpyHostToDevice, c->stream));
+  label_top_kernel<<<(unsigned)ceil_div64(n, TPB), TPB, 0, c->stream>>>(dptr<int32_t>(c->xyz_raw), n, p->bin, W, top);
+  KLAUNCH_CHECK(c);
+  label_pixels_kernel<<<(unsigned)ceil_div64(npx, TPB), TPB, 0, c->stream>>>(
+      top, npx, dptr<int32_t>(c->g_label), (h_plane_rgb && rgb_bytes) ? d_prgb : nullptr, d_label, h_rgb ? d_rgb : nullptr);
+  KLAUNCH_CHECK(c);
+  if (h_label) CU_CHECK(c, cudaMemcpyAsync(h_label, d_label, (size_t)npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (h_rgb) CU_CHECK(c, cudaMemcpyAsync(h_rgb, d_rgb, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}

@@ -140,6 +140,15 @@ BSEG_API int bseg_raster_size(bseg_ctx* ctx, const bseg_params* p, int32_t* W, i
 BSEG_API int bseg_raster(bseg_ctx* ctx, const bseg_params* p, double* image_WxHx3, uint8_t* png_a,
                          uint8_t* png_b, uint8_t* png_c, double* ground_th);
 
+/* ---- label raster (north_star stage 5; extension: the reference rasters height and count only, TMC3.cpp:127-172,
+ * and paints labels per point, my_function.cpp:260-275) ---------------------------------------
+ * Same W x H grid as bseg_raster.  label_WxH[y*W+x] = plane label (1..P, 0 = none) of the highest point of
+ * the pixel (ties: lower index); rgb_WxHx3 = that plane's colour from plane_rgb_Px3 (the set_plane_color
+ * sequence handed to bseg_paint), black where the label is 0 -- the byte image for stbi_write_png.
+ * Any of the three buffers may be NULL. */
+BSEG_API int bseg_label_raster(bseg_ctx* ctx, const bseg_params* p, const uint16_t* plane_rgb_Px3, int32_t* label_WxH,
+                               uint8_t* rgb_WxHx3);
+
 /* ---- whole path, device resident (no host transfers): what bench.py times as `value` --------- */
 #define BSEG_RUN_KNN 1
 #define BSEG_RUN_GROW 2

@@ -221,3 +221,21 @@ def pipeline(xyz_unshifted, **kw):
     neigh = np.ascontiguousarray(idx[:, : p["K"]])
     g = grow(xyz, nrm, neigh, p["K"], p["th_thickness"], p["th_point_count"], p["th_dot"])
     return dict(xyz=xyz, mn=mn, mx=mx, wh=wh, knn=idx, d2=d2, normals=nrm, curvature=curv, n_hyb=nh, neigh=neigh, grow=g)
+
+
+def label_raster(xyz_shifted, label, W, H, plane_rgb=None, bin=100):
+    """Label raster restated in numpy (include/bseg.h bseg_label_raster; no reference counterpart): per pixel the
+    label of the highest point, ties to the lower index; the colour image from the set_plane_color sequence."""
+    xs = np.asarray(xyz_shifted, np.int64)
+    px = (xs[:, 1] // bin) * W + (xs[:, 0] // bin)
+    order = np.lexsort((np.arange(len(xs)), -xs[:, 2], px))  # pixel, then z descending, then index ascending
+    first = np.ones(len(xs), bool)
+    first[1:] = px[order][1:] != px[order][:-1]
+    win = order[first]
+    lab = np.zeros(W * H, np.int32)
+    lab[px[win]] = np.asarray(label, np.int32)[win]
+    rgb = np.zeros((W * H, 3), np.uint8)
+    if plane_rgb is not None and len(plane_rgb):
+        m = lab > 0
+        rgb[m] = np.asarray(plane_rgb, np.uint16)[lab[m] - 1].astype(np.uint8)
+    return lab.reshape(H, W), rgb.reshape(H, W, 3)

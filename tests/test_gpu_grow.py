@@ -172,6 +172,26 @@ def test_segment_host_end_to_end(ctx):
     assert np.array_equal(a, oa) and np.array_equal(b, ob)
 
 
+@pytest.mark.parametrize("case,kw", [("building", dict(n=60000)), ("block", dict(n=120000)), ("voxels", dict(n=40000))])
+def test_label_raster(ctx, case, kw):
+    """bseg_label_raster: per pixel the label of the highest point (ties: lower index) and its plane colour."""
+    from buildingsegment_b200 import lib
+
+    xyz = getattr(cases, case)(**kw)
+    p = lib.default_params()
+    mn, mx, xs = ctx.set_points(xyz)
+    ctx.knn_normals(p, want_neigh=False, want_normals=False)
+    pidx, label, npl = ctx.grow_planes(p)
+    rgb = O.libc_plane_colors(npl)
+    W, H = ctx.raster_size(p)
+    lab, img = ctx.label_raster(p, rgb)
+    olab, oimg = O.label_raster(xs, label, W, H, rgb)
+    assert np.array_equal(lab, olab) and np.array_equal(img, oimg)
+    assert lab.max(initial=0) <= npl
+    if npl:
+        assert (lab > 0).any()
+
+
 def test_stage_order_errors_are_loud(ctx):
     from buildingsegment_b200 import lib
 
@@ -179,5 +199,7 @@ def test_stage_order_errors_are_loud(ctx):
     ctx.set_points(cases.tiny(50))
     with pytest.raises(lib.BsegError):
         ctx.grow_planes(p)
+    with pytest.raises(lib.BsegError):
+        ctx.label_raster(p)
     with pytest.raises(lib.BsegError):
         lib.Context(99)
