@@ -872,9 +872,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
 {
   (void)p;
   const int64_t n = A.n;
-  const int64_t CMAX = 1 << 16;
+  // window of seeds the scout looks at / grower slots (tunables: BSEG_WINDOW, BSEG_SLOTS)
+  const int64_t CMAX = getenv("BSEG_WINDOW") ? atoll(getenv("BSEG_WINDOW")) : (1 << 18);
   SpecArgs S;
-  S.G = 1024;
+  S.G = getenv("BSEG_SLOTS") ? atoi(getenv("BSEG_SLOTS")) : 1024;
   // page pool: room for every point once plus one page per slot, capped at 64 Mi entries
   int64_t pages = (3 * n) / PAGE_SIZE + 2 * S.G;
   if (pages > 32768) pages = 32768;
