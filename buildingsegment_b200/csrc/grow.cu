@@ -290,6 +290,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   {
     const char* gf = getenv("BSEG_GROW_FLAGS");  // tuning switches of the step engine (grow.cuh GF_*)
     A.flags = gf ? atoi(gf) : (GF_ROWDUP | GF_FASTDIV | GF_ROW_L1);
+    if (getenv("BSEG_DEBUG")) A.flags |= GF_TIMING;  // per-phase cycle counters of the head slot (they cost ~10 %)
   }
   RC_CHECK(dev_ensure(c, c->g_rowdup, (size_t)n + 64));
   A.rowdup = dptr<uint8_t>(c->g_rowdup);

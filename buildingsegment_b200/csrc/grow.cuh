@@ -34,7 +34,7 @@ struct GrowArgs {
   const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
   uint32_t* atby;    // [n] lowest in-flight transaction that assumed the point taken (early notification)
 };
-enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32, GF_NOPAIR = 64, GF_NOSKIP = 128, GF_SKIP_EAGER = 256, GF_NEVER = 1 << 30 /* never set */ };
+enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32, GF_NOPAIR = 64, GF_NOSKIP = 128, GF_SKIP_EAGER = 256, GF_EXACT_MODEL = 512, GF_TIMING = 1024, GF_NEVER = 1 << 30 /* never set */ };
 
 // ---- "assumed taken" list of a speculative transaction --------------------------------------------------
 // A point that is free in the committed state and passes the geometric tests, but is reserved by a LOWER
@@ -144,18 +144,82 @@ __device__ __forceinline__ void model_update_fast(Model& m, int64_t len)
   }
 }
 
+// ---- the model between two decisions (speculative two-node engine) ------------------------------------------
+// The reference renormalises the model after every accepting call: a correctly rounded sqrt and three correctly
+// rounded divisions, ~1500 cycles of dependent fp64 work on the grower's critical path -- only to compare two
+// numbers with thresholds that almost no point comes near.  The engine therefore carries cur_normal as
+// sn * rsqrt(sn.sn), which is within 2^-50 (relative) of the exact quotients, and decides with it whenever both
+// test values are clear of their thresholds by far more than that can move them (|dot - th_dot| > 1e-9; the
+// distance term sums three products of magnitude < 2^24, so its error is < 1e-7: margin 1e-4).  A test value
+// inside a margin makes the warp compute the exact model from the (always exact) running sums and decide again;
+// the exact model is also what a finished transaction reports.  cur_center (an integer quotient) is always exact.
+__device__ __forceinline__ bool geo_test_margin(const Model& m, const int4& p, double n0, double n1, double n2,
+                                                double th_thick, double th_dot, bool& near)
+{
+  int32_t p0 = (int32_t)((uint32_t)p.x - (uint32_t)m.mc0);
+  int32_t p1 = (int32_t)((uint32_t)p.y - (uint32_t)m.mc1);
+  int32_t p2 = (int32_t)((uint32_t)p.z - (uint32_t)m.mc2);
+  double dist = bseg_fabs((double)p0 * m.mn0 + (double)p1 * m.mn1 + (double)p2 * m.mn2);
+  double dot = m.mn0 * n0 + m.mn1 * n1 + m.mn2 * n2;
+  near = bseg_fabs(dist - th_thick) <= 1e-4 || bseg_fabs(dot - th_dot) <= 1e-9;
+  return dist <= th_thick && dot >= th_dot;
+}
+
+// cur_center /= size with a float-seeded reciprocal (one Newton step: relative error < 2^-43, the quotient is
+// off by at most one and the remainder tells which way) -- same result as center_div
+__device__ __forceinline__ void center_update(Model& m, uint32_t l)
+{
+  if ((int32_t)(m.sc0 | m.sc1 | m.sc2) >= 0) {  // all three sums below 2^31 (always, before Q6 strikes)
+    const double dl = (double)l;
+    const double r0 = (double)__frcp_rn((float)l);
+    const double rl = __fma_rn(r0, __fma_rn(-dl, r0, 1.0), r0);
+    uint32_t q, rem;
+    q = (uint32_t)__dmul_rn((double)m.sc0, rl); rem = m.sc0 - q * l;
+    m.mc0 = (int32_t)((int32_t)rem < 0 ? q - 1 : (rem >= l ? q + 1 : q));
+    q = (uint32_t)__dmul_rn((double)m.sc1, rl); rem = m.sc1 - q * l;
+    m.mc1 = (int32_t)((int32_t)rem < 0 ? q - 1 : (rem >= l ? q + 1 : q));
+    q = (uint32_t)__dmul_rn((double)m.sc2, rl); rem = m.sc2 - q * l;
+    m.mc2 = (int32_t)((int32_t)rem < 0 ? q - 1 : (rem >= l ? q + 1 : q));
+  } else {
+    m.mc0 = center_div(m.sc0, l);
+    m.mc1 = center_div(m.sc1, l);
+    m.mc2 = center_div(m.sc2, l);
+  }
+}
+
+// returns false when the sums are outside the range the error bound was derived for (the caller goes exact)
+__device__ __forceinline__ bool model_update_approx(Model& m, int64_t len)
+{
+  const double ss = (m.sn0 * m.sn0) + (m.sn1 * m.sn1) + (m.sn2 * m.sn2);
+  if (!div_safe_operand(ss) || !div_safe_operand(m.sn0) || !div_safe_operand(m.sn1) || !div_safe_operand(m.sn2))
+    return false;
+  const double r = rsqrt(ss);
+  m.mn0 = m.sn0 * r; m.mn1 = m.sn1 * r; m.mn2 = m.sn2 * r;
+  center_update(m, (uint32_t)len);
+  return true;
+}
+
 // add the accepted lanes' normals / positions to the running sums in neighbour order
 __device__ __forceinline__ void model_accumulate(Model& m, uint32_t acc, const int4& p, double n0, double n1, double n2)
 {
-  while (acc) {
-    int b = __ffs(acc) - 1;
+  while (acc) {  // two accepted lanes per trip: their shuffles are in flight together, the sums stay in order
+    const int b = __ffs(acc) - 1;
     acc &= acc - 1;
-    m.sn0 += __shfl_sync(FULL_MASK, n0, b);
-    m.sn1 += __shfl_sync(FULL_MASK, n1, b);
-    m.sn2 += __shfl_sync(FULL_MASK, n2, b);
-    m.sc0 += (uint32_t)__shfl_sync(FULL_MASK, p.x, b);
-    m.sc1 += (uint32_t)__shfl_sync(FULL_MASK, p.y, b);
-    m.sc2 += (uint32_t)__shfl_sync(FULL_MASK, p.z, b);
+    const bool two = acc != 0;
+    const int c = two ? __ffs(acc) - 1 : b;
+    acc &= acc - 1;
+    const double x0 = __shfl_sync(FULL_MASK, n0, b), x1 = __shfl_sync(FULL_MASK, n1, b), x2 = __shfl_sync(FULL_MASK, n2, b);
+    const uint32_t u0 = (uint32_t)__shfl_sync(FULL_MASK, p.x, b), u1 = (uint32_t)__shfl_sync(FULL_MASK, p.y, b),
+                   u2 = (uint32_t)__shfl_sync(FULL_MASK, p.z, b);
+    const double y0 = __shfl_sync(FULL_MASK, n0, c), y1 = __shfl_sync(FULL_MASK, n1, c), y2 = __shfl_sync(FULL_MASK, n2, c);
+    const uint32_t v0 = (uint32_t)__shfl_sync(FULL_MASK, p.x, c), v1 = (uint32_t)__shfl_sync(FULL_MASK, p.y, c),
+                   v2 = (uint32_t)__shfl_sync(FULL_MASK, p.z, c);
+    m.sn0 += x0; m.sn1 += x1; m.sn2 += x2;
+    m.sc0 += u0; m.sc1 += u1; m.sc2 += u2;
+    if (two) {
+      m.sn0 += y0; m.sn1 += y1; m.sn2 += y2;
+      m.sc0 += v0; m.sc1 += v1; m.sc2 += v2;
+    }
   }
 }
 
@@ -252,6 +316,7 @@ struct TxState {
   int64_t n_at;  // entries of the assumed-taken list (speculative engine)
   uint32_t node;
   int have_top, depth0;
+  int model_exact;  // m.mn* are the reference's correctly rounded quotients (else within ~2^-50 of them, see model_update_approx)
 };
 
 enum TxOutcome {
@@ -276,6 +341,7 @@ __device__ __forceinline__ void tx_begin(TxState& t, const GrowArgs& A, uint32_t
   t.node = seed_s;
   t.have_top = 0;
   t.depth0 = 1;
+  t.model_exact = 1;
 }
 
 // Runs Broad() calls of transaction `seed_i` until it ends or `budget` calls were made.
@@ -641,8 +707,11 @@ __device__ __forceinline__ uint32_t skip_eval(const GrowArgs& A, const Model& m,
       const double* nb = A.nrm + 3 * (int64_t)ib;
       const double a0 = __ldg(na), a1 = __ldg(na + 1), a2 = __ldg(na + 2);
       const double b0 = __ldg(nb), b1 = __ldg(nb + 1), b2 = __ldg(nb + 2);
-      if (va && geo_test(m, pa, a0, a1, a2, A.th_thick, A.th_dot)) atomicOr(&ss->hit, 1u << ss->owner[ra]);
-      if (vb && geo_test(m, pb, b0, b1, b2, A.th_thick, A.th_dot)) atomicOr(&ss->hit, 1u << ss->owner[rb]);
+      bool near_a = false, near_b = false;  // inside a margin counts as a hit: the regular step decides exactly
+      const bool ga = geo_test_margin(m, pa, a0, a1, a2, A.th_thick, A.th_dot, near_a);
+      const bool gb = geo_test_margin(m, pb, b0, b1, b2, A.th_thick, A.th_dot, near_b);
+      if (va && (ga || near_a)) atomicOr(&ss->hit, 1u << ss->owner[ra]);
+      if (vb && (gb || near_b)) atomicOr(&ss->hit, 1u << ss->owner[rb]);
     }
     __syncwarp();
     hit = ss->hit;
@@ -758,7 +827,9 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
   const uint32_t fr = (uint32_t)A.frontier;
   const bool fastdiv = (A.flags & GF_FASTDIV) != 0, row_l1 = (A.flags & GF_ROW_L1) != 0;
   const bool skip = ss != nullptr && (A.flags & GF_NOSKIP) == 0;
+  const bool approx = (A.flags & GF_EXACT_MODEL) == 0;
   bool halt = false;
+  long long klast = dbg ? clock64() : 0;
   const int half = lane >> 4, sl = lane & 15;
   unsigned long long steps = 0, iters = 0;
   TxOutcome out = TX_RUNNING;
@@ -791,7 +862,17 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     }
     ++iters;
     if (dbg && lane == 0) dbg[3] += 1;
-    bool want = id >= 0 && stt == -1 && rs != me && !mine && geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
+    const long long k0 = dbg ? clock64() : 0;
+    const bool open = id >= 0 && stt == -1 && rs != me && !mine;
+    bool near = false;
+    bool want = geo_test_margin(t.m, p, n0, n1, n2, A.th_thick, A.th_dot, near) && open;
+    if (!t.model_exact && __any_sync(FULL_MASK, open && near)) {  // too close to call: the reference's own model
+      if (fastdiv) model_update_fast(t.m, t.len);
+      else model_update(t.m, t.len);
+      t.model_exact = 1;
+      want = open && geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
+    }
+    const long long k1 = dbg ? clock64() + (long long)(__ballot_sync(FULL_MASK, want) & 0u) : 0;
     if (__any_sync(FULL_MASK, has_dup && want)) {  // a row that names a point twice: first occurrence only
       const unsigned long long key = want ? (((unsigned long long)half << 32) | (uint32_t)id)
                                           : ((1ull << 40) | (unsigned long long)lane);
@@ -838,6 +919,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     if (ok) st.put(t.len + __popc(acc & lanemask_lt()), id);
     __syncwarp();
     t.depth0 = 0;
+    const long long k2 = dbg ? clock64() + (long long)(acc & 0u) : 0;
     // ---- DFS bookkeeping (:252-255) ----
     if (useB) ++t.top_cur;  // B was the next entry of the frame: consumed
     const int64_t s0 = t.len;
@@ -884,6 +966,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
         }
       }
     }
+    const long long k3 = dbg ? clock64() + (long long)(next & 0u) : 0;
     // ---- next gathers first, then the model ----
     int32_t nid = -1;
     bool ndup = false;
@@ -893,7 +976,9 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
       if (act) ndup = __ldg(A.rowdup + node) != 0;
       if (act && sl >= 1 && sl < K) nid = __ldg(A.nbr + (int64_t)node * K + sl);
     }
+    const long long k4 = dbg ? clock64() + (long long)(nid & 0) : 0;
     if (cnt > 0) model_accumulate(t.m, acc, p, n0, n1, n2);
+    const long long k5 = dbg ? clock64() + (long long)(bseg_d2u(t.m.sn0) & 0ull) : 0;
     int32_t nstt = 0;
     uint32_t nrs = RES_FREE;
     bool nmine = false;
@@ -908,6 +993,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
       if (row_l1) {  // the row of a neighbour that gets accepted is needed one step later
         prefetch_l1(A.nbr + (int64_t)nid * K);
         prefetch_l1(A.nbr + (int64_t)nid * K + (K - 1));
+        prefetch_l1(A.rowdup + nid);
       }
     }
     {  // points accepted a moment ago are ours whatever the gathered reservation says
@@ -919,9 +1005,14 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
       }
     }
     if (cnt > 0) {  // a call that accepts nothing leaves sums and length, hence the model, as they are
-      if (fastdiv) model_update_fast(t.m, t.len);
-      else model_update(t.m, t.len);
+      t.model_exact = 0;
+      if (!approx || !model_update_approx(t.m, t.len)) {
+        if (fastdiv) model_update_fast(t.m, t.len);
+        else model_update(t.m, t.len);
+        t.model_exact = 1;
+      }
     }
+    const long long k6 = dbg ? clock64() + (long long)(bseg_d2u(t.m.mn0) & 0ull) : 0;
     {
       bool race = false;
       if (fired) {
@@ -934,6 +1025,13 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
         break;
       }
     }
+    if (dbg && lane == 0) {
+      const long long k7 = clock64();
+      dbg[8] += (unsigned long long)(k1 - k0); dbg[9] += (unsigned long long)(k2 - k1); dbg[10] += (unsigned long long)(k3 - k2);
+      dbg[11] += (unsigned long long)(k4 - k3); dbg[12] += (unsigned long long)(k5 - k4); dbg[13] += (unsigned long long)(k6 - k5);
+      dbg[14] += (unsigned long long)(k7 - k6); dbg[15] += (unsigned long long)(k0 - klast); dbg[16] += cnt > 0 ? 1 : 0;
+      klast = k7;
+    }
     if (!have_next) {
       out = TX_FINISHED;
       break;
@@ -942,7 +1040,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     hasB = have_nextB;
     id = nid; stt = nstt; rs = nrs; mine = nmine; p = np; n0 = m0; n1 = m1; n2 = m2;
     has_dup = ndup;
-    if ((steps & 7) < 2 || halt) {
+    if ((iters & 7) == 0 || halt) {
       halt = false;
       if (((volatile uint8_t*)A.doom)[seed_i]) {
         out = TX_DOOMED;
@@ -950,6 +1048,11 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
       }
       if (*(volatile unsigned long long*)A.stop_flag) break;  // the head finished: let the sweeper commit
     }
+  }
+  if (out == TX_FINISHED && !t.model_exact) {  // what the plane reports is the reference's model
+    if (fastdiv) model_update_fast(t.m, t.len);
+    else model_update(t.m, t.len);
+    t.model_exact = 1;
   }
   steps_out += steps;
   if (iters_out) *iters_out += iters;

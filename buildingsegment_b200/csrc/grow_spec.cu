@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   const bool pair = A.K <= 16 && !(A.flags & GF_NOPAIR);
   __shared__ SkipScratch skip_scratch[GW];
   SkipScratch* ss = &skip_scratch[threadIdx.x >> 5];
-  unsigned long long* dbg = is_head ? &S.sc[SC_SKIP_DBG] : nullptr;
+  unsigned long long* dbg = (is_head && (A.flags & GF_TIMING)) ? &S.sc[SC_SKIP_DBG] : nullptr;
   const TxOutcome out = pair ? (A.K == 15 ? tx_run_pair<15>(A, st, t, seed_i, budget, lane, steps, &iters, ss, dbg)
                                           : tx_run_pair<0>(A, st, t, seed_i, budget, lane, steps, &iters, ss, dbg))
                              : tx_run<MODE_SPEC, 0>(A, st, t, seed_i, budget, false, lane, steps);
@@ -1012,6 +1012,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   if (dbg) {
     fprintf(stderr, "[bseg] head: %llu calls in %llu warp steps\n", ctl[8 + SC_HEAD_STEPS], ctl[8 + SC_HEAD_ITERS]);
     const unsigned long long* sd = ctl + 8 + SC_SKIP_DBG;
+    if (sd[3])
+      fprintf(stderr, "[bseg] head regular steps %llu (%llu accepting): cycles/step want %llu, reserve+ballots %llu, dfs %llu, row %llu, accumulate %llu, "
+              "gather issue+update %llu, race+tail %llu, between %llu\n", sd[3], sd[16], sd[8] / sd[3], sd[9] / sd[3], sd[10] / sd[3], sd[11] / sd[3],
+              sd[12] / sd[3], sd[13] / sd[3], sd[14] / sd[3], sd[15] / sd[3]);
     if (sd[0])
       fprintf(stderr, "[bseg] head skip batches %llu: cycles/batch enumerate %llu, evaluate %llu; pairs/batch %.1f; regular steps %llu, "
               "batch time %.1f ms of head %.1f ms\n", sd[0], sd[1] / sd[0], sd[2] / sd[0], (double)sd[4] / (double)sd[0], sd[3],
