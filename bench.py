@@ -389,7 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--points", type=int, default=10_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=3_000_000)
     ap.add_argument("--ref-sample", type=int, default=60_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--halo", type=int, default=2000, help="initial slab halo width, mm (N > 1); doubled until sufficient")
