@@ -652,7 +652,9 @@ struct GridLevel {
   uint64_t hmask;
   uint32_t gmax[3];
   uint32_t guar2;  // (edge + 1)^2
+  uint32_t unres_flag;  // FROM_MID for the finer table: the fallback then starts with the 27 cells of the coarse one
 };
+constexpr uint32_t FROM_MID = 0x80000000u;
 
 template <int KT>
 __device__ __forceinline__ void list_insert(unsigned long long (&L)[KT], unsigned long long key)
@@ -666,6 +668,13 @@ __device__ __forceinline__ void list_insert(unsigned long long (&L)[KT], unsigne
 }
 
 enum { GROUP_DONE = 0, GROUP_TOO_BIG = 1, GROUP_HYBRID_LEFT = 2 };
+
+// staging order of the 4x4x4 block: the group's own 8 cells, then the 24 cells sharing a face with the core, the 24
+// along its edges, the 8 corners -- near candidates first, so the lanes' K-th best tightens early and the far
+// cells cause few insertions
+__device__ const unsigned char block_order[64] = {
+    21, 22, 25, 26, 37, 38, 41, 42, 5,  6,  9,  10, 17, 18, 20, 23, 24, 27, 29, 30, 33, 34, 36, 39, 40, 43, 45, 46, 53, 54, 57, 58,
+    1,  2,  4,  7,  8,  11, 13, 14, 16, 19, 28, 31, 32, 35, 44, 47, 49, 50, 52, 55, 56, 59, 61, 62, 0,  3,  12, 15, 48, 51, 60, 63};
 
 // Serves the queries [qstart, qstart + Q) -- the points of the 2x2x2 block of level-`G` cells whose parent has
 // the Morton code P -- from the 4x4x4 block of cells around it.  Returns GROUP_TOO_BIG (nothing done) when the
@@ -683,7 +692,7 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
   uint32_t st2[2], ln2[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int i = lane + 32 * h;
+    const int i = block_order[2 * lane + h];  // staging slot 2 * lane + h
     const int dx = i & 3, dy = (i >> 2) & 3, dz = i >> 4;
     st2[h] = 0;
     ln2[h] = 0;
@@ -793,7 +802,7 @@ __device__ int serve_group(const KnnArgs& A, const GridLevel& G, uint64_t P, uin
       const bool resolved = L[KT - 1] != ~0ull && (uint32_t)(L[KT - 1] >> 32) < G.guar2;
       if (!resolved) {
         const uint32_t slot = atomicAdd(A.n_unres, 1u);
-        A.unres[slot] = qpos;
+        A.unres[slot] = qpos | G.unres_flag;
       }
     }
     __syncwarp();
@@ -986,13 +995,14 @@ __global__ void __launch_bounds__(KTHREADS) knn_fallback_kernel(KnnArgs A, int m
   const uint32_t nun = *A.n_unres;
   const uint32_t kmask = A.K >= 32 ? 0xffffffffu : ((1u << A.K) - 1u);
   for (uint32_t i = blockIdx.x * KW + w; i < nun; i += gridDim.x * KW) {
-    const uint32_t qpos = A.unres[i];
+    const uint32_t entry = A.unres[i];
+    const uint32_t qpos = entry & ~FROM_MID;
     const int4 q = __ldg(A.pts + qpos);
     const uint32_t qcx = (uint32_t)q.x / (uint32_t)A.cell, qcy = (uint32_t)q.y / (uint32_t)A.cell,
                    qcz = (uint32_t)q.z / (uint32_t)A.cell;
     uint64_t bd2 = ~0ull;
     uint32_t bidx = 0xffffffffu, bpos = 0xffffffffu;
-    for (int L = 1; L <= max_level; ++L) {
+    for (int L = (entry & FROM_MID) ? 0 : 1; L <= max_level; ++L) {
       bd2 = ~0ull; bidx = 0xffffffffu; bpos = 0xffffffffu;
       const uint32_t X = qcx >> L, Y = qcy >> L, Z = qcz >> L;
       const uint32_t gx = A.gmax[0] >> L, gy = A.gmax[1] >> L, gz = A.gmax[2] >> L;
@@ -1177,6 +1187,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
     }
     GridLevel G0, G1;
     G0.cell_start = A.cell_start; G0.hk = A.hk; G0.hv = A.hv; G0.hmask = A.hmask; G0.guar2 = A.guar2;
+    G0.unres_flag = 0;
     for (int k = 0; k < 3; ++k) G0.gmax[k] = A.gmax[k];
     G1 = G0;
     const bool mid = c->have_mid && (c->cell % 2) == 0 && (double)(c->cell / 2) >= p->radius;
@@ -1187,6 +1198,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
       G1.hv = dptr<uint32_t>(c->hash_vals2);
       G1.hmask = c->hash_mask2;
       G1.guar2 = (uint32_t)(cell2 + 1) * (uint32_t)(cell2 + 1);
+      G1.unres_flag = FROM_MID;
       for (int k = 0; k < 3; ++k) G1.gmax[k] = (uint32_t)(c->mx[k] - c->mn[k]) / (uint32_t)cell2;
     }
     const unsigned gb = (unsigned)(c->num_sms * 3);
