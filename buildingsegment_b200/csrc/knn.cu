@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(KTHREADS) knn_big_cells_kernel(KnnArgs A)
 // (cell+1)^2 are exact).  Left to the per-cell kernels: groups with more than GCAP candidates (dense scans) and
 // -- hybrid set only -- groups where some query has more than max_nn points inside the radius (the max_nn
 // nearest of them then need a selection).
-constexpr int GCAP = 1024;  // staged candidates per warp
+constexpr int GCAP = 512;   // staged candidates per warp
 constexpr int GKW = 4;      // warps per block
 
 struct GroupScratch {
@@ -1201,7 +1201,7 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
       G1.unres_flag = FROM_MID;
       for (int k = 0; k < 3; ++k) G1.gmax[k] = (uint32_t)(c->mx[k] - c->mn[k]) / (uint32_t)cell2;
     }
-    const unsigned gb = (unsigned)(c->num_sms * 3);
+    const unsigned gb = (unsigned)(c->num_sms * 6);
     if (p->K == 15) knn_groups_kernel<15><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1, mid ? 1 : 0);
     else knn_groups_kernel<16><<<gb, GKW * 32, gsmem, c->stream>>>(A, G0, G1, mid ? 1 : 0);
     KLAUNCH_CHECK(c);
