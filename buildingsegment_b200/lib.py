@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbseg.so")
+LIB_PATH = os.environ.get("BSEG_LIB_PATH") or os.path.join(HERE, "libbseg.so")  # (override: A/B runs of two builds)
 CSRC = os.path.join(HERE, "csrc")
 
 EXPORTS = [
