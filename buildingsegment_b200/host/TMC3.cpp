@@ -106,6 +106,22 @@ public:
     write_png_rgb(path + nameC, width, height, png.data() + 6 * npx, width * 3);
   }
 
+  // extension (include/bseg.h bseg_label_raster): the plane label of the highest point per pixel, in the colours
+  // set_plane_color gave the planes -- "labels.png" on the grid of the three images above
+  void save_label_image(std::string path)
+  {
+    bseg_host::ensure_cloud(pointcloud, false);
+    bseg_params p = bseg_host::params();
+    p.bin = bin;
+    p.bin_height = bin_height;
+    const size_t npx = size_t(width) * height;
+    std::vector<uint8_t> rgb(3 * npx);
+    const std::vector<uint16_t>& prgb = bseg_host::last_plane_rgb();
+    bseg_host::check(bseg_label_raster(bseg_host::context(), &p, prgb.empty() ? nullptr : prgb.data(), nullptr, rgb.data()),
+                     "bseg_label_raster");
+    write_png_rgb(path + "labels.png", width, height, rgb.data(), width * 3);
+  }
+
   double& pixel(int x, int y, int ch) { return image[(size_t(y) * width + x) * channels + ch]; }  // :123-125
 
   // TMC3.cpp:127-172 (+ groundTH :181-198): median-height cut, bilinear splat in point order, mean
@@ -171,6 +187,7 @@ int main(int argc, char* argv[])
       if (std::strncmp(argv[a], "--raster=", 9) == 0) {
         seg.compute_gird_picture();
         seg.save_image(std::string(argv[a] + 9));
+        seg.save_label_image(std::string(argv[a] + 9));
       }
     std::cout << "tmc3: " << pointCloud.getPointCount() << " points, " << plances.size() << " planes -> "
               << path.savePath << std::endl;

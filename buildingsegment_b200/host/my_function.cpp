@@ -106,6 +106,11 @@ bool seg_plane::Broad(int, int)
   throw std::runtime_error("seg_plane::Broad runs on the device inside get_planes(); it has no host implementation");
 }
 
+namespace bseg_host {
+static std::vector<uint16_t> g_last_rgb;
+const std::vector<uint16_t>& last_plane_rgb() { return g_last_rgb; }
+}  // namespace bseg_host
+
 void seg_plane::set_plane_color(std::vector<plane>& planes)
 {
   using namespace bseg_host;
@@ -116,6 +121,7 @@ void seg_plane::set_plane_color(std::vector<plane>& planes)
   for (size_t q = 0; q < planes.size(); ++q)
     for (int k = 0; k < 3; ++k) rgb[3 * q + k] = uint16_t(55 + rand() % 200);  // braced-init order, :268
   check(bseg_paint(context(), rgb.data(), Cloud.colorData()), "bseg_paint");
+  g_last_rgb = rgb;
   (void)n;
 }
 

@@ -51,6 +51,9 @@ void check(int rc, const char* what);
 bool ensure_cloud(PCCPointSet3& cloud, bool shift_caller_cloud);
 void note_shifted(const PCCPointSet3& cloud);
 
+// the colour sequence the last set_plane_color drew (55 + rand() % 200, three per plane): the label image uses it
+const std::vector<uint16_t>& last_plane_rgb();
+
 // device results -> the reference's host containers
 void fetch_knn(size_t n, int K, std::vector<Vec3<double>>& normal, std::vector<std::vector<int>>& neigh);
 

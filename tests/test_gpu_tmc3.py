@@ -42,6 +42,11 @@ def test_tmc3_driver_matches_oracle(tmp_path):
         raw = np.frombuffer(open(os.path.join(os.fsencode(rdir), name.encode("gbk")), "rb").read(), np.uint8)
         png = cv2.imdecode(raw, cv2.IMREAD_COLOR)[..., ::-1]
         assert np.array_equal(png, mine), name
+    # the label image (extension): plane label of the highest point per pixel in the planes' colours
+    raw = np.frombuffer(open(os.path.join(rdir, "labels.png"), "rb").read(), np.uint8)
+    lab_png = cv2.imdecode(raw, cv2.IMREAD_COLOR)[..., ::-1]
+    _, olab = O.label_raster(P["xyz"], g.label, W, H, O.libc_plane_colors(g.n_planes, seed=1))
+    assert np.array_equal(lab_png, olab)
 
 
 def test_tmc3_driver_reports_missing_input(tmp_path):

@@ -111,3 +111,21 @@ def test_synth_generators_are_deterministic():
     assert c2.shape == (20000, 3) and c2[:, 2].max() < 20000
     v = synth.make("C4", 3000, bits=6)
     assert len(np.unique(v, axis=0)) == len(v)  # voxelised: unique lattice points
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on the host cores alone (no GPU): one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--points", "300000",
+                        "--ref-sample", "6000", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "points/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config"):
+        assert k in line
