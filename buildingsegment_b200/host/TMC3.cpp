@@ -108,9 +108,10 @@ public:
 
   // extension (include/bseg.h bseg_label_raster): the plane label of the highest point per pixel, in the colours
   // set_plane_color gave the planes -- "labels.png" on the grid of the three images above
+  // (uses the segmentation the device holds: call it after get_planes and before compute_gird_picture, which
+  // uploads this object's own copy of the cloud again)
   void save_label_image(std::string path)
   {
-    bseg_host::ensure_cloud(pointcloud, false);
     bseg_params p = bseg_host::params();
     p.bin = bin;
     p.bin_height = bin_height;
@@ -185,9 +186,9 @@ int main(int argc, char* argv[])
     // here it is opt-in
     for (int a = 3; a < argc; ++a)
       if (std::strncmp(argv[a], "--raster=", 9) == 0) {
+        seg.save_label_image(std::string(argv[a] + 9));
         seg.compute_gird_picture();
         seg.save_image(std::string(argv[a] + 9));
-        seg.save_label_image(std::string(argv[a] + 9));
       }
     std::cout << "tmc3: " << pointCloud.getPointCount() << " points, " << plances.size() << " planes -> "
               << path.savePath << std::endl;
