@@ -108,6 +108,13 @@ def test_dense_groups_are_streamed_in_chunks(ctx):
     xyz = rng.integers(0, 300, (30000, 3)).astype(np.int32)
     _check_case(ctx, xyz, K=15, radius=100.0, max_nn=50, cell=100)
     _check_case(ctx, xyz, K=16, radius=100.0, max_nn=20, cell=100)
+    # max_nn below K: the group kernel leaves the hybrid sets of crowded radii to the per-cell kernels
+    _check_case(ctx, xyz, K=15, radius=100.0, max_nn=10, cell=100)
+
+
+def test_max_nn_below_k(ctx):
+    _check_case(ctx, cases.block(60000), K=15, radius=100.0, max_nn=10)
+    _check_case(ctx, cases.building(40000), K=16, radius=150.0, max_nn=5)
 
 
 def test_per_cell_kernels_alone(ctx, monkeypatch):
