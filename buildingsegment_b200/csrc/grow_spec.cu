@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
     int done = 0;
     while (done < n_eval && !stop) {
       const unsigned long long ti1 = gtimer();
+      bool state_changed = true;  // false after a roll-back: nothing the other threads know has moved
       if (tid == 0) {
         sh.first_special = SWEEP_T;
         sh.first_over = SWEEP_T;
@@ -679,6 +680,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
             A.ctl[CTL_PLANES] = pl + 1;
           }
         } else {  // roll back (:203-209): nothing persists
+          state_changed = false;
           for (int64_t e = 1 + tid; e < len; e += SWEEP_T) {
             const int32_t pt = S.pool.list_pages[at(e)];
             if (atomicCAS(A.res + pt, (uint32_t)Fs, RES_FREE) == (uint32_t)Fs) unreserve_notify(A.atby, A.slotof, A.doom, pt);
@@ -789,7 +791,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         if (done < n_eval) F = sh.last_open;
         t_fast += gtimer() - ti1;
       }
-      if (done < n_eval && !stop) {
+      if (done < n_eval && !stop && state_changed) {
         // ---- refresh: the states of what this thread already knows (one load level) ----
         if (valid && tid >= done) {
           const int32_t st_s = __ldcg(A.state + s);
