@@ -254,9 +254,12 @@ def run_ours(args):
             return None
         # tile origin -> halo exchange (NCCL P2P) -> kNN/normals + halo check -> grow -> cross-slab label merge
         r = slabs.segment_slab(backend, d_xyz, x_lo, x_hi, halo=args.halo)
-        ctx.run_device(p, lib.RUN_RASTER)
+        labels = r["labels"]
+        # the tile's raster: this rank's pixel columns, bit-identical to the undivided tile's (slabs.raster_slab)
+        img = slabs.raster_slab(backend, d_xyz, r["halo_l"], r["halo_r"], r["origin"], x_lo, x_hi, r["halo"], p.bin, p.bin_height)
         slab_info.update({k: r[k] for k in ("n_planes_total", "n_components", "halo", "n_halo")})
-        return r["labels"]
+        slab_info.update({"raster_tile": [img["W"], img["H"]], "raster_columns": [img["x0"], img["x0"] + int(img["image"].shape[1])]})
+        return labels
 
     # ---- device-resident leg ----
     for _ in range(args.warmup):
@@ -296,6 +299,7 @@ def run_ours(args):
     np_xyz, np_shift, np_label, np_a, np_b = (h_xyz.numpy(), h_shift.numpy(), h_label.numpy(), h_a.numpy(), h_b.numpy())
 
     d_stage = torch.empty((n, 3), dtype=torch.int32, device=dev) if world > 1 else None
+    png_host = [None]
 
     def step_host():
         if world == 1:
@@ -303,6 +307,8 @@ def run_ours(args):
         d_stage.copy_(h_xyz, non_blocking=True)  # H2D of the slab from pinned memory
         r = slabs.segment_slab(backend, d_stage, x_lo, x_hi, halo=args.halo)
         h_label.copy_(r["labels"].to(torch.int32))  # D2H of the canonical labels
+        img = slabs.raster_slab(backend, d_stage, r["halo_l"], r["halo_r"], r["origin"], x_lo, x_hi, r["halo"], p.bin, p.bin_height)
+        png_host[0] = (img["png_a"].cpu(), img["png_b"].cpu())  # D2H of this rank's columns of the two images
         torch.cuda.synchronize(dev)
         return r["n_planes_total"], 0, 0
 
@@ -320,7 +326,7 @@ def run_ours(args):
     ms_e2e = float(t_max.item())
     e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
     h2d = n * 12
-    d2h = n * 12 + n * 4 + 2 * 3 * W * H if world == 1 else n * 4
+    d2h = n * 12 + n * 4 + 2 * 3 * W * H if world == 1 else n * 4 + sum(int(t.numel()) for t in (png_host[0] or ()))
 
     if rank == 0:
         peak, peak_src = peaks()

@@ -339,6 +339,21 @@ BSEG_API int bseg_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int
   return stage_raster_size(c, p, W, H);
 }
 
+BSEG_API int bseg_raster_device(bseg_ctx* c, const bseg_params* p, const double* ground_th, const double** d_image,
+                                int32_t* W, int32_t* H)
+{
+  RC_CHECK(check_ctx(c));
+  RC_CHECK(check_params(c, p));
+  if (!c->have_points)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_raster_device before bseg_set_points");
+  RC_CHECK(stage_raster(c, p, nullptr, nullptr, nullptr, nullptr, nullptr, true, ground_th));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (d_image) *d_image = c->n > 0 ? dptr<double>(c->r_image) : nullptr;
+  if (W) *W = c->rW;
+  if (H) *H = c->rH;
+  return 0;
+}
+
 BSEG_API int bseg_label_raster(bseg_ctx* c, const bseg_params* p, const uint16_t* plane_rgb_Px3, int32_t* label_WxH,
                                uint8_t* rgb_WxHx3)
 {

@@ -187,7 +187,7 @@ int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* cent
 int stage_paint(bseg_ctx* c, const uint16_t* h_rgb, uint16_t* h_colors);
 int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H);
 int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* a, uint8_t* b, uint8_t* cc,
-                 double* th, bool device_only);
+                 double* th, bool device_only, const double* th_override = nullptr);
 int stage_label_raster(bseg_ctx* c, const bseg_params* p, const uint16_t* h_plane_rgb, int32_t* h_label, uint8_t* h_rgb);
 
 #define STAGE_BEGIN(c, which) cudaEventRecord((c)->ev[which], (c)->stream)

@@ -174,7 +174,7 @@ int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H)
 }
 
 int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_a, uint8_t* h_b, uint8_t* h_c,
-                 double* h_th, bool device_only)
+                 double* h_th, bool device_only, const double* th_override)
 {
   const int64_t n = c->n;
   RC_CHECK(stage_raster_size(c, p, nullptr, nullptr));
@@ -190,7 +190,12 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
   const int nb_bins = zext / p->bin_height + 1;
 
   STAGE_BEGIN(c, EV_RASTER);
-  // ---- groundTH: z histogram, first bin where the cumulative count exceeds N/2 ----
+  // ---- groundTH: z histogram, first bin where the cumulative count exceeds N/2 (or the caller's threshold:
+  //      the slabs of a tile share the tile's, bseg_raster_device) ----
+  int32_t th;
+  if (th_override) {
+    th = (int32_t)*th_override;
+  } else {
   RC_CHECK(dev_ensure(c, c->r_hist, (size_t)nb_bins * 4 + 64));
   uint32_t* d_hist = dptr<uint32_t>(c->r_hist);
   CU_CHECK(c, cudaMemsetAsync(d_hist, 0, (size_t)nb_bins * 4, c->stream));
@@ -204,7 +209,6 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
   }
   std::vector<uint32_t> hist((size_t)nb_bins);
   RC_CHECK(read_back(c, hist.data(), d_hist, (size_t)nb_bins * 4));
-  int32_t th;
   {
     const int TH = (int)(n / 2);
     int total = 0;
@@ -215,6 +219,7 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
         break;
     }
     th = i * p->bin_height;
+  }
   }
   if (h_th) *h_th = (double)th;
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "bseg_create", "bseg_destroy", "bseg_default_params", "bseg_last_error", "bseg_version",
     "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
-    "bseg_grow_planes", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_label_raster",
+    "bseg_grow_planes", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_raster_device", "bseg_label_raster",
     "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
     "bseg_point_count", "bseg_plane_count", "bseg_set_owned", "bseg_set_origin", "bseg_device_results", "bseg_halo_check", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
 ]
@@ -86,6 +86,7 @@ def lib():
         L.bseg_raster_size.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.bseg_raster.argtypes = [vp, C.POINTER(Params), vp, vp, vp, vp, vp]
         L.bseg_label_raster.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
+        L.bseg_raster_device.argtypes = [vp, C.POINTER(Params), vp, vp, vp, vp]
         L.bseg_run_device.argtypes = [vp, C.POINTER(Params), C.c_int]
         L.bseg_segment_host.argtypes = [vp, C.POINTER(Params), vp, i64, vp, vp, vp, vp, vp, vp, vp]
         L.bseg_get_timings.argtypes = [vp, C.POINTER(Timings)]
@@ -253,6 +254,16 @@ class Context:
         th = C.c_double(0.0)
         self._ck(lib().bseg_raster(self._h, C.byref(p), _ptr(img), _ptr(a), _ptr(b), _ptr(c), C.addressof(th)))
         return img, a, b, c, float(th.value)
+
+    def raster_device(self, p: Params, ground_th=None):
+        """bseg_raster_device: (device pointer of the W*H*3 doubles, W, H); ground_th overrides groundTH."""
+        th = C.c_double(0.0 if ground_th is None else float(ground_th))
+        d_img = C.c_void_p()
+        W = C.c_int32(0)
+        H = C.c_int32(0)
+        self._ck(lib().bseg_raster_device(self._h, C.byref(p), None if ground_th is None else C.addressof(th),
+                                          C.addressof(d_img), C.addressof(W), C.addressof(H)))
+        return int(d_img.value or 0), int(W.value), int(H.value)
 
     def label_raster(self, p: Params, plane_rgb=None):
         """Plane label of the highest point per pixel + its colour image (bseg_label_raster)."""

@@ -20,7 +20,14 @@ result means:
                       every plane the smallest global id of its component ("canonical minimum-index label").
                       Global id of local plane k on rank r = 1 + sum(planes of ranks < r) + (k - 1).
 
-The compute of steps 3-4 is a `backend` object: `CudaBackend` (libbseg, the product) or, in the CPU tests
+  6. raster           (raster_slab) the tile's height / count image, bit for bit: tile extent by all_reduce(MAX),
+                      the tile's ground threshold from the summed z histograms (TMC3.cpp:181-198), every rank
+                      rasters [left halo | owned | right halo] -- the tile's point order restricted to what can
+                      reach its pixel columns, so the in-order fp64 sums of TMC3.cpp:127-172 are the tile's own --
+                      keeps the pixel columns that start in its slab, and the per-channel maxima of save_image
+                      (TMC3.cpp:81-121) come from an all_reduce(MAX).
+
+The compute of steps 3-4 and 6 is a `backend` object: `CudaBackend` (libbseg, the product) or, in the CPU tests
 only, a stand-in built on the oracle.  Nothing here falls back to a CPU path by itself.
 """
 from __future__ import annotations
@@ -60,6 +67,24 @@ class CudaBackend:
         npl = ctx.n_planes()
         label = _wrap_device_int32(d_label, n, xyz_local.device)
         return label, npl, 0
+
+
+    def raster(self, xyz_local: torch.Tensor, origin, ground_th: float):
+        """Height / count image (doubles, before save_image) of `xyz_local` in ITS order with the tile's ground
+        threshold: float64 [H][W][3] tensor on the device."""
+        n = int(xyz_local.shape[0])
+        ctx = self.ctx
+        torch.cuda.current_stream(xyz_local.device).synchronize()
+        ctx.set_origin(origin)
+        ctx.set_points_device(xyz_local.data_ptr(), n)
+        d_img, W, H = ctx.raster_device(self.p, ground_th)
+
+        class _Holder:
+            pass
+
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f8", "data": (int(d_img), False), "version": 2}
+        return torch.as_tensor(h, device=xyz_local.device).clone()
 
 
 def _wrap_device_int32(ptr: int, n: int, device):
@@ -243,4 +268,67 @@ def segment_slab(backend, xyz_owned: torch.Tensor, x_lo: int, x_hi: int, halo: i
         raise RuntimeError(f"halo of {halo} units still insufficient after {max_tries} doublings")
     labels, total, ncomp = merge_labels(label, n_owned, npl, hl, hr, group)
     return {"labels": labels, "n_planes_total": total, "n_components": ncomp, "halo": halo,
-            "n_halo": int(hl.shape[0] + hr.shape[0]), "n_planes_local": npl}
+            "n_halo": int(hl.shape[0] + hr.shape[0]), "n_planes_local": npl, "halo_l": hl, "halo_r": hr, "origin": origin}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# step 6: the tile's raster
+def ground_threshold(xyz_owned: torch.Tensor, origin, zext: int, bin_height: int, group=None) -> int:
+    """buildingSeg::groundTH (TMC3.cpp:181-198) of the whole tile: z histogram in bins of bin_height summed over
+    the ranks, first bin whose cumulative count exceeds N/2 (N/2 in integers), times bin_height."""
+    dev = xyz_owned.device
+    nb = int(zext) // int(bin_height) + 1
+    z = (xyz_owned[:, 2].to(torch.int64) - int(origin[2])) // int(bin_height)
+    hist = torch.bincount(z, minlength=nb).to(torch.int64)[:nb] if xyz_owned.shape[0] else torch.zeros(nb, dtype=torch.int64, device=dev)
+    total = torch.tensor([xyz_owned.shape[0]], dtype=torch.int64, device=dev)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    th_count = int(total.item()) // 2
+    cum = torch.cumsum(hist, 0)
+    over = torch.nonzero(cum > th_count)
+    i = int(over[0].item()) if over.numel() else nb
+    return i * int(bin_height)
+
+
+def raster_slab(backend, xyz_owned: torch.Tensor, halo_l: torch.Tensor, halo_r: torch.Tensor, origin, x_lo: int, x_hi: int,
+                halo: int, bin: int = 100, bin_height: int = 1000, group=None):
+    """This rank's pixel columns of the tile's raster.  Returns a dict: image (float64 [H][cols][3], the doubles of
+    compute_gird_picture), png_a / png_b (uint8 [H][cols][3], the bytes of save_image), x0 (first column), W, H
+    (the tile's), ground_th, maxima (the tile's per-channel maxima)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = xyz_owned.device
+    if world > 1 and halo < 2 * bin:
+        raise ValueError("raster_slab: the halo must cover two raster bins")
+    # the tile's extent: width / height as TMC3.cpp:75-76, z extent for the ground threshold
+    mx = xyz_owned.max(dim=0).values.to(torch.int64) if xyz_owned.shape[0] else torch.full((3,), -2**31, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    ext = [int(mx[k].item()) - int(origin[k]) for k in range(3)]
+    W, H = ext[0] // bin + 2, ext[1] // bin + 2
+    th = ground_threshold(xyz_owned, origin, ext[2], bin_height, group)
+    # the tile's point order is rank-major: left halo (the left neighbour's points, in its order), owned, right halo
+    local = torch.cat([halo_l[:, :3], xyz_owned, halo_r[:, :3]], dim=0).contiguous()
+    img = backend.raster(local, origin, float(th))  # [H_l][W_l][3]
+    # pixel columns that START in this slab (a column on a face goes to the rank on its left edge)
+    c0 = 0 if rank == 0 else -((-(x_lo - int(origin[0]))) // bin)
+    c1 = W if rank == world - 1 else -((-(x_hi - int(origin[0]))) // bin)
+    c1 = max(c0, min(c1, W))
+    block = torch.zeros((H, c1 - c0, 3), dtype=torch.float64, device=dev)
+    hl_, wl_ = int(img.shape[0]), int(img.shape[1])
+    hh, ww = min(H, hl_), min(c1, wl_)
+    if ww > c0 and hh > 0:
+        block[:hh, : ww - c0] = img[:hh, c0:ww]
+    # save_image (TMC3.cpp:81-121): per-channel maximum over the tile, byte = (uint8)(255.0 * (v / max))
+    m = block.reshape(-1, 3).max(dim=0).values if block.numel() else torch.zeros(3, dtype=torch.float64, device=dev)
+    m = torch.clamp(m, min=0.0)
+    if world > 1:
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    png_a = torch.zeros(block.shape, dtype=torch.uint8, device=dev)
+    png_b = torch.zeros(block.shape, dtype=torch.uint8, device=dev)
+    if float(m[0]) != 0.0:
+        png_a[..., 0] = (255.0 * (1.0 * block[..., 0] / m[0])).to(torch.uint8)
+    if float(m[1]) != 0.0:
+        png_b[..., 1] = (255.0 * (1.0 * block[..., 1] / m[1])).to(torch.uint8)
+    return {"image": block, "png_a": png_a, "png_b": png_b, "x0": c0, "W": W, "H": H, "ground_th": th, "maxima": m}

@@ -140,6 +140,14 @@ BSEG_API int bseg_raster_size(bseg_ctx* ctx, const bseg_params* p, int32_t* W, i
 BSEG_API int bseg_raster(bseg_ctx* ctx, const bseg_params* p, double* image_WxHx3, uint8_t* png_a,
                          uint8_t* png_b, uint8_t* png_c, double* ground_th);
 
+/* ---- the raster of one slab of a tile (multi-GPU): same kernels as bseg_raster, but the ground
+ * threshold of TMC3.cpp:181-198 comes from the caller when ground_th is not NULL (the slabs share the tile's, found
+ * from the summed z histograms) and the W*H*3 doubles stay on the device (*d_image, valid until the next
+ * bseg_set_points / bseg_raster*).  Point order = the cloud's order, as always: buildingsegment_b200/slabs.py
+ * uploads [left halo | owned | right halo] so that it is the tile's order. */
+BSEG_API int bseg_raster_device(bseg_ctx* ctx, const bseg_params* p, const double* ground_th, const double** d_image,
+                                int32_t* W, int32_t* H);
+
 /* ---- label raster (north_star stage 5; extension: the reference rasters height and count only, TMC3.cpp:127-172,
  * and paints labels per point, my_function.cpp:260-275) ---------------------------------------
  * Same W x H grid as bseg_raster.  label_WxH[y*W+x] = plane label (1..P, 0 = none) of the highest point of

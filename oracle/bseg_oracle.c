@@ -386,11 +386,23 @@ ORC_API double orc_ground_th(const int32_t* xyz, int64_t n, int32_t zext, int bi
 }
 
 /* TMC3.cpp:127-164.  image is W*H*3 doubles, zero-initialised here. */
+static int orc_raster_impl(const int32_t* xyz, int64_t n, double th, int bin, double bias, int W, int H, double* image);
+
 ORC_API int orc_raster(const int32_t* xyz, int64_t n, int32_t zext, int bin, int bin_height, double bias,
                        int W, int H, double* image)
 {
+  return orc_raster_impl(xyz, n, orc_ground_th(xyz, n, zext, bin_height), bin, bias, W, H, image);
+}
+
+/* the same with the ground threshold given (a slab of a tile uses the tile's: include/bseg.h bseg_raster_device) */
+ORC_API int orc_raster_th(const int32_t* xyz, int64_t n, double th, int bin, double bias, int W, int H, double* image)
+{
+  return orc_raster_impl(xyz, n, th, bin, bias, W, H, image);
+}
+
+static int orc_raster_impl(const int32_t* xyz, int64_t n, double th, int bin, double bias, int W, int H, double* image)
+{
   memset(image, 0, (size_t)W * H * 3 * sizeof(double));
-  double th = orc_ground_th(xyz, n, zext, bin_height);
   for (int64_t i = 0; i < n; ++i) {
     int32_t p0 = xyz[3 * i], p1 = xyz[3 * i + 1], p2 = xyz[3 * i + 2];
     int x = p0 / bin, y = p1 / bin;

@@ -140,6 +140,28 @@ def test_raster_matches_oracle(ctx, case, kw):
     assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(c, oc)
 
 
+def test_raster_device_with_given_threshold(ctx):
+    """bseg_raster_device: the image stays on the device and the ground threshold is the caller's (slabs of a tile)."""
+    import torch
+
+    from buildingsegment_b200 import lib
+
+    xyz = cases.block(80000)
+    p = lib.default_params()
+    mn, mx, xs = ctx.set_points(xyz)
+    for th in (None, 0.0, 3000.0):
+        d_img, W, H = ctx.raster_device(p, th)
+
+        class _H:
+            pass
+
+        h = _H()
+        h.__cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f8", "data": (d_img, False), "version": 2}
+        img = torch.as_tensor(h, device="cuda:0").cpu().numpy()
+        want = O.raster(xs, mx[2] - mn[2], W, H) if th is None else O.raster_th(xs, th, W, H)
+        assert np.array_equal(img.view(np.int64), want.view(np.int64)), th
+
+
 def test_raster_bin_variants(ctx):
     from buildingsegment_b200 import lib
 

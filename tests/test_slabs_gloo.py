@@ -42,6 +42,11 @@ class OracleBackend:
         self.last = dict(xs=xs, neigh=neigh, nrm=nrm, grow=g)
         return torch.from_numpy(g.label.astype(np.int32)), int(g.n_planes), 0
 
+    def raster(self, xyz_local, origin, ground_th):
+        xs = np.ascontiguousarray(xyz_local.numpy().astype(np.int64) - np.asarray(origin, np.int64)).astype(np.int32)
+        W, H = int(xs[:, 0].max()) // 100 + 2, int(xs[:, 1].max()) // 100 + 2
+        return torch.from_numpy(O.raster_th(xs, ground_th, W, H))
+
 
 def _free_port():
     s = socket.socket()
@@ -139,3 +144,49 @@ def test_union_find_canonical_minimum():
 
     c = _union_find_min(6, np.array([[5, 2], [2, 6], [3, 4]]))
     assert c.tolist() == [0, 1, 2, 3, 3, 2, 2]
+
+
+def _raster_worker(rank, world, port, case, kw, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from buildingsegment_b200 import slabs
+
+        xyz = getattr(cases, case)(**kw)
+        cut = int(np.median(xyz[:, 0])) + 37  # a face that is not aligned with the raster bins
+        lo = [int(xyz[:, 0].min()), cut][rank]
+        hi = [cut, int(xyz[:, 0].max()) + 1][rank]
+        m = (xyz[:, 0] >= lo) & (xyz[:, 0] < hi)
+        owned = torch.from_numpy(np.ascontiguousarray(xyz[m]))
+        origin = slabs.tile_origin(owned)
+        hl, hr = slabs.exchange_halo(owned, lo, hi, 500)
+        r = slabs.raster_slab(OracleBackend(), owned, hl, hr, origin, lo, hi, 500)
+        np.savez(os.path.join(out_dir, f"raster{rank}.npz"), image=r["image"].numpy(), a=r["png_a"].numpy(), b=r["png_b"].numpy(),
+                 x0=r["x0"], W=r["W"], H=r["H"], th=r["ground_th"], owned=owned.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case,kw", [("building", dict(n=30000, order="shuffled")), ("block", dict(n=40000))])
+def test_two_slabs_raster_is_the_tiles_raster(case, kw, tmp_path):
+    """The stitched pixel columns of two slabs == the raster of the undivided tile (points in rank-major order),
+    bit for bit: doubles, ground threshold and the save_image bytes."""
+    port = _free_port()
+    mp.spawn(_raster_worker, args=(2, port, case, kw, str(tmp_path)), nprocs=2, join=True)
+    res = [np.load(os.path.join(tmp_path, f"raster{r}.npz")) for r in range(2)]
+    tile = np.concatenate([res[0]["owned"], res[1]["owned"]], axis=0)  # the tile's point order is rank-major
+    xs, mn, mx, wh = O.bbox_shift(tile)
+    W, H = int(wh[0]), int(wh[1])
+    assert (int(res[0]["W"]), int(res[0]["H"])) == (W, H) == (int(res[1]["W"]), int(res[1]["H"]))
+    th = O.orc().orc_ground_th(xs, len(xs), int(mx[2] - mn[2]), 1000)
+    assert float(res[0]["th"]) == th == float(res[1]["th"])
+    ref = O.raster(xs, mx[2] - mn[2], W, H)
+    oa, ob, _, _ = O.save_image(ref)
+    assert int(res[0]["x0"]) == 0 and int(res[1]["x0"]) == res[0]["image"].shape[1]
+    img = np.concatenate([res[0]["image"], res[1]["image"]], axis=1)
+    assert img.shape == ref.shape
+    assert np.array_equal(img.view(np.int64), ref.view(np.int64))
+    assert np.array_equal(np.concatenate([res[0]["a"], res[1]["a"]], axis=1), oa)
+    assert np.array_equal(np.concatenate([res[0]["b"], res[1]["b"]], axis=1), ob)
+    assert res[1]["image"].shape[1] > 3 and np.count_nonzero(img[..., 1]) > 0
