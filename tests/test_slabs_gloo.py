@@ -154,9 +154,10 @@ def _raster_worker(rank, world, port, case, kw, out_dir):
         from buildingsegment_b200 import slabs
 
         xyz = getattr(cases, case)(**kw)
-        cut = int(np.median(xyz[:, 0])) + 37  # a face that is not aligned with the raster bins
-        lo = [int(xyz[:, 0].min()), cut][rank]
-        hi = [cut, int(xyz[:, 0].max()) + 1][rank]
+        # faces that are not aligned with the raster bins; at world 3 the middle rank has two neighbours
+        qs = np.quantile(xyz[:, 0], [k / world for k in range(1, world)]).astype(np.int64) + 37
+        edges = [int(xyz[:, 0].min())] + [int(q) for q in qs] + [int(xyz[:, 0].max()) + 1]
+        lo, hi = edges[rank], edges[rank + 1]
         m = (xyz[:, 0] >= lo) & (xyz[:, 0] < hi)
         owned = torch.from_numpy(np.ascontiguousarray(xyz[m]))
         origin = slabs.tile_origin(owned)
@@ -168,25 +169,28 @@ def _raster_worker(rank, world, port, case, kw, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,kw", [("building", dict(n=30000, order="shuffled")), ("block", dict(n=40000))])
-def test_two_slabs_raster_is_the_tiles_raster(case, kw, tmp_path):
-    """The stitched pixel columns of two slabs == the raster of the undivided tile (points in rank-major order),
+@pytest.mark.parametrize("world,case,kw", [(2, "building", dict(n=30000, order="shuffled")), (2, "block", dict(n=40000)),
+                                           (3, "block", dict(n=40000))])
+def test_slabs_raster_is_the_tiles_raster(world, case, kw, tmp_path):
+    """The stitched pixel columns of the slabs == the raster of the undivided tile (points in rank-major order),
     bit for bit: doubles, ground threshold and the save_image bytes."""
     port = _free_port()
-    mp.spawn(_raster_worker, args=(2, port, case, kw, str(tmp_path)), nprocs=2, join=True)
-    res = [np.load(os.path.join(tmp_path, f"raster{r}.npz")) for r in range(2)]
-    tile = np.concatenate([res[0]["owned"], res[1]["owned"]], axis=0)  # the tile's point order is rank-major
+    mp.spawn(_raster_worker, args=(world, port, case, kw, str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(os.path.join(tmp_path, f"raster{r}.npz")) for r in range(world)]
+    tile = np.concatenate([r["owned"] for r in res], axis=0)  # the tile's point order is rank-major
     xs, mn, mx, wh = O.bbox_shift(tile)
     W, H = int(wh[0]), int(wh[1])
-    assert (int(res[0]["W"]), int(res[0]["H"])) == (W, H) == (int(res[1]["W"]), int(res[1]["H"]))
     th = O.orc().orc_ground_th(xs, len(xs), int(mx[2] - mn[2]), 1000)
-    assert float(res[0]["th"]) == th == float(res[1]["th"])
+    col = 0
+    for r in res:
+        assert (int(r["W"]), int(r["H"])) == (W, H) and float(r["th"]) == th
+        assert int(r["x0"]) == col
+        col += r["image"].shape[1]
     ref = O.raster(xs, mx[2] - mn[2], W, H)
     oa, ob, _, _ = O.save_image(ref)
-    assert int(res[0]["x0"]) == 0 and int(res[1]["x0"]) == res[0]["image"].shape[1]
-    img = np.concatenate([res[0]["image"], res[1]["image"]], axis=1)
+    img = np.concatenate([r["image"] for r in res], axis=1)
     assert img.shape == ref.shape
     assert np.array_equal(img.view(np.int64), ref.view(np.int64))
-    assert np.array_equal(np.concatenate([res[0]["a"], res[1]["a"]], axis=1), oa)
-    assert np.array_equal(np.concatenate([res[0]["b"], res[1]["b"]], axis=1), ob)
-    assert res[1]["image"].shape[1] > 3 and np.count_nonzero(img[..., 1]) > 0
+    assert np.array_equal(np.concatenate([r["a"] for r in res], axis=1), oa)
+    assert np.array_equal(np.concatenate([r["b"] for r in res], axis=1), ob)
+    assert all(r["image"].shape[1] > 3 for r in res) and np.count_nonzero(img[..., 1]) > 0
