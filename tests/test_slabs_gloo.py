@@ -65,9 +65,9 @@ def _worker(rank, world, port, case, kw, halo, out_dir):
 
         xyz = getattr(cases, case)(**kw)
         gid = np.arange(len(xyz))
-        cut = int(np.median(xyz[:, 0]))
-        lo = [int(xyz[:, 0].min()), cut][rank]
-        hi = [cut, int(xyz[:, 0].max()) + 1][rank]
+        qs = np.quantile(xyz[:, 0], [k / world for k in range(1, world)]).astype(np.int64)
+        edges = [int(xyz[:, 0].min())] + [int(q) for q in qs] + [int(xyz[:, 0].max()) + 1]
+        lo, hi = edges[rank], edges[rank + 1]
         m = (xyz[:, 0] >= lo) & (xyz[:, 0] < hi)
         owned = torch.from_numpy(np.ascontiguousarray(xyz[m]))
         be = OracleBackend()
@@ -75,11 +75,11 @@ def _worker(rank, world, port, case, kw, halo, out_dir):
         # local index -> global index: owned first, then the halo copies (re-run the exchange to learn them)
         hl, hr = slabs.exchange_halo(owned, lo, hi, r["halo"])
         gid_own = gid[m]
-        other = [None, None]
+        other = [None] * world
         dist.all_gather_object(other, gid_own)
-        src = np.concatenate([hl.numpy()[:, 3], hr.numpy()[:, 3]]).astype(np.int64)
-        gid_halo = other[1 - rank][src] if len(src) else np.empty(0, np.int64)
-        l2g = np.concatenate([gid_own, gid_halo])
+        gl = other[rank - 1][hl.numpy()[:, 3].astype(np.int64)] if rank > 0 and len(hl) else np.empty(0, np.int64)
+        gr = other[rank + 1][hr.numpy()[:, 3].astype(np.int64)] if rank < world - 1 and len(hr) else np.empty(0, np.int64)
+        l2g = np.concatenate([gid_own, gl, gr])
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), gid_own=gid_own, l2g=l2g, neigh=be.last["neigh"][: len(gid_own)],
                  nrm=be.last["nrm"][: len(gid_own)], labels=r["labels"].numpy(), total=r["n_planes_total"],
                  ncomp=r["n_components"], n_local=r["n_planes_local"], halo=r["halo"], n_halo=r["n_halo"],
@@ -88,10 +88,10 @@ def _worker(rank, world, port, case, kw, halo, out_dir):
         dist.destroy_process_group()
 
 
-def _run(case, kw, halo, tmp_path):
+def _run(case, kw, halo, tmp_path, world=2):
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, case, kw, halo, str(tmp_path)), nprocs=2, join=True)
-    return [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(2)]
+    mp.spawn(_worker, args=(world, port, case, kw, halo, str(tmp_path)), nprocs=world, join=True)
+    return [np.load(os.path.join(tmp_path, f"r{r}.npz")) for r in range(world)]
 
 
 @pytest.mark.parametrize("case,kw", [("building", dict(n=30000, order="shuffled"))])
@@ -117,6 +117,28 @@ def test_two_slabs_match_undivided_knn_and_merge(case, kw, tmp_path):
         assert np.array_equal(r["labels"] == 0, loc == 0)
         assert np.all(r["labels"][loc > 0] <= loc[loc > 0] + off)
     assert n_lab > 0
+
+
+def test_three_slabs_middle_rank_has_two_neighbours(tmp_path):
+    """World 3: the middle rank exchanges halos on both faces; owned kNN rows / normals still equal the undivided
+    cloud's (a cloud without exact distance ties: ties between an owned point and a halo copy go by local index)."""
+    kw = dict(n=30000, order="shuffled")
+    res = _run("building", kw, 400, tmp_path, world=3)
+    P = O.pipeline(cases.building(**kw))
+    for r in res:
+        g = r["gid_own"]
+        assert np.array_equal(r["l2g"][r["neigh"]], P["neigh"][g])
+        assert np.array_equal(r["nrm"].view(np.int64), P["normals"][g].view(np.int64))
+    assert int(res[1]["n_halo"]) > int(res[0]["n_halo"]) > 0  # two faces against one
+    assert len({int(r["total"]) for r in res}) == 1 and len({int(r["ncomp"]) for r in res}) == 1
+
+
+def test_plane_across_two_faces_gets_one_id(tmp_path):
+    """One flat plane cut in three: the big plane carries the same canonical id on all three ranks."""
+    res = _run("grid_plane", dict(nx=180, ny=50, order="shuffled"), 400, tmp_path, world=3)
+    big = [np.bincount(r["labels"][r["labels"] > 0]).argmax() for r in res]
+    assert big[0] == big[1] == big[2] == 1, big
+    assert int(res[0]["ncomp"]) < int(res[0]["total"])
 
 
 def test_plane_across_the_face_gets_one_id(tmp_path):
