@@ -196,20 +196,19 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
   if (th_override) {
     th = (int32_t)*th_override;
   } else {
-  RC_CHECK(dev_ensure(c, c->r_hist, (size_t)nb_bins * 4 + 64));
-  uint32_t* d_hist = dptr<uint32_t>(c->r_hist);
-  CU_CHECK(c, cudaMemsetAsync(d_hist, 0, (size_t)nb_bins * 4, c->stream));
-  {
-    int g = (int)ceil_div64(n, TPB * 8);
-    if (g > c->num_sms * 8) g = c->num_sms * 8;
-    if (g < 1) g = 1;
-    size_t sh = nb_bins <= 4096 ? (size_t)nb_bins * 4 : 0;
-    zhist_kernel<<<g, TPB, sh, c->stream>>>(dptr<int32_t>(c->xyz_raw), n, p->bin_height, d_hist, nb_bins);
-    KLAUNCH_CHECK(c);
-  }
-  std::vector<uint32_t> hist((size_t)nb_bins);
-  RC_CHECK(read_back(c, hist.data(), d_hist, (size_t)nb_bins * 4));
-  {
+    RC_CHECK(dev_ensure(c, c->r_hist, (size_t)nb_bins * 4 + 64));
+    uint32_t* d_hist = dptr<uint32_t>(c->r_hist);
+    CU_CHECK(c, cudaMemsetAsync(d_hist, 0, (size_t)nb_bins * 4, c->stream));
+    {
+      int g = (int)ceil_div64(n, TPB * 8);
+      if (g > c->num_sms * 8) g = c->num_sms * 8;
+      if (g < 1) g = 1;
+      size_t sh = nb_bins <= 4096 ? (size_t)nb_bins * 4 : 0;
+      zhist_kernel<<<g, TPB, sh, c->stream>>>(dptr<int32_t>(c->xyz_raw), n, p->bin_height, d_hist, nb_bins);
+      KLAUNCH_CHECK(c);
+    }
+    std::vector<uint32_t> hist((size_t)nb_bins);
+    RC_CHECK(read_back(c, hist.data(), d_hist, (size_t)nb_bins * 4));
     const int TH = (int)(n / 2);
     int total = 0;
     int i;
@@ -219,7 +218,6 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
         break;
     }
     th = i * p->bin_height;
-  }
   }
   if (h_th) *h_th = (double)th;
 
