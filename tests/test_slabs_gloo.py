@@ -141,6 +141,19 @@ def test_plane_across_two_faces_gets_one_id(tmp_path):
     assert int(res[0]["ncomp"]) < int(res[0]["total"])
 
 
+def test_insufficient_halo_is_doubled_until_it_suffices(tmp_path):
+    """A halo narrower than some K-th neighbour distance: the sufficiency check (bseg_halo_check) fails on some rank,
+    every rank doubles the halo and exchanges again; the rows of the owned points are the undivided cloud's."""
+    kw = dict(n=30000, order="shuffled")
+    res = _run("building", kw, 100, tmp_path)
+    P = O.pipeline(cases.building(**kw))
+    assert int(res[0]["halo"]) == int(res[1]["halo"]) > 100
+    for r in res:
+        g = r["gid_own"]
+        assert np.array_equal(r["l2g"][r["neigh"]], P["neigh"][g])
+        assert np.array_equal(r["nrm"].view(np.int64), P["normals"][g].view(np.int64))
+
+
 def test_plane_across_the_face_gets_one_id(tmp_path):
     """One flat plane cut in two: every labelled point of the big plane carries the same canonical id on both ranks."""
     res = _run("grid_plane", dict(nx=120, ny=60, order="shuffled"), 400, tmp_path)
