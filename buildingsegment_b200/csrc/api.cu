@@ -128,15 +128,17 @@ BSEG_API void bseg_destroy(bseg_ctx* c)
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->xyz_raw, &c->minmax, &c->keys[0], &c->keys[1], &c->vals[0], &c->vals[1], &c->sort_cnt,
                    &c->scan_tmp, &c->pts, &c->inv, &c->flags, &c->cell_key, &c->cell_start, &c->hash_keys,
-                   &c->hash_vals, &c->cell_key2, &c->cell_start2, &c->hash_keys2, &c->hash_vals2, &c->nbr, &c->nrm, &c->curv, &c->worklist, &c->counters, &c->out_tmp,
+                   &c->hash_vals, &c->cell_key2, &c->cell_start2, &c->hash_keys2, &c->hash_vals2, &c->nbr, &c->nrm, &c->curv, &c->worklist, &c->counters, &c->out_tmp, &c->x_neigh, &c->x_normals,
                    &c->g_state, &c->g_res, &c->g_spec, &c->g_pool, &c->g_planes, &c->g_tx, &c->g_queue, &c->g_rowdup, &c->g_marklog,
-                   &c->g_stack, &c->g_label, &c->g_pidx, &c->r_hist, &c->r_image, &c->r_png, &c->r_pix};
+                   &c->g_stack, &c->g_label, &c->g_pidx, &c->g_pts_raw, &c->r_hist, &c->r_image, &c->r_png, &c->r_pix};
   for (DevBuf* b : all)
     dev_free(*b);
   for (int i = 0; i < EV_COUNT; ++i) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
   }
+  for (auto& e : c->grow_ev)
+    if (e) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
   grow_host_free(c);
   cudaStreamDestroy(c->stream);
@@ -158,7 +160,7 @@ static int set_points_common(bseg_ctx* c, int64_t n, int32_t out_min[3], int32_t
   c->n = n;
   c->n_owned = n;
   c->have_points = true;
-  c->have_knn = c->have_grow = false;
+  c->have_knn = c->have_grow = c->have_bin = false;
   RC_CHECK(stage_bbox_shift(c));
   for (int k = 0; k < 3; ++k) {
     if (out_min) out_min[k] = c->mn[k];
@@ -220,6 +222,14 @@ BSEG_API int bseg_set_origin(bseg_ctx* c, const int32_t* origin)
   return 0;
 }
 
+BSEG_API int bseg_set_grow_offset(bseg_ctx* c, const int32_t* offset)
+{
+  RC_CHECK(check_ctx(c));
+  for (int k = 0; k < 3; ++k) c->grow_off[k] = offset ? offset[k] : 0;
+  c->have_grow = false;
+  return 0;
+}
+
 BSEG_API int bseg_device_results(bseg_ctx* c, const int32_t** d_label, const int32_t** d_plane_idx,
                                  const int32_t** d_xyz_shifted)
 {
@@ -269,6 +279,7 @@ BSEG_API int bseg_knn_normals(bseg_ctx* c, const bseg_params* p, int32_t* neigh_
   if (!c->have_points)
     return bseg_fail(c, BSEG_E_STATE, "bseg_knn_normals before bseg_set_points");
   RC_CHECK(stage_bin(c, p));
+  c->have_bin = true;
   RC_CHECK(stage_knn(c, p));
   c->have_knn = true;
   c->have_grow = false;
@@ -286,11 +297,41 @@ BSEG_API int bseg_override_neigh_normals(bseg_ctx* c, const bseg_params* p, cons
     return bseg_fail(c, BSEG_E_STATE, "bseg_override_neigh_normals before bseg_set_points");
   if (!c->have_knn || c->K != p->K) {
     RC_CHECK(stage_bin(c, p));
+    c->have_bin = true;
     RC_CHECK(stage_knn(c, p));
     c->have_knn = true;
   }
   c->have_grow = false;
-  return stage_override(c, p, neigh_NxK, normals_Nx3);
+  return stage_override(c, p, neigh_NxK, normals_Nx3, false);
+}
+
+BSEG_API int bseg_knn_device_results(bseg_ctx* c, const bseg_params* p, const int32_t** d_neigh_NxK,
+                                     const double** d_normals_Nx3)
+{
+  RC_CHECK(check_ctx(c));
+  RC_CHECK(check_params(c, p));
+  if (!c->have_knn || c->K != p->K)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_knn_device_results: run bseg_knn_normals / bseg_run_device(KNN) with this K first");
+  return stage_export_knn_device(c, p, d_neigh_NxK, d_normals_Nx3);
+}
+
+BSEG_API int bseg_import_neigh_normals_device(bseg_ctx* c, const bseg_params* p, const int32_t* d_neigh_NxK,
+                                              const double* d_normals_Nx3)
+{
+  RC_CHECK(check_ctx(c));
+  RC_CHECK(check_params(c, p));
+  if (!c->have_points)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_import_neigh_normals_device before bseg_set_points");
+  if (!d_neigh_NxK || !d_normals_Nx3)
+    return bseg_fail(c, BSEG_E_ARG, "bseg_import_neigh_normals_device: both arrays are required");
+  if (!c->have_bin || c->K != p->K) {
+    RC_CHECK(stage_bin(c, p));
+    c->have_bin = true;
+  }
+  RC_CHECK(stage_alloc_knn_outputs(c, p));
+  c->have_knn = true;
+  c->have_grow = false;
+  return stage_override(c, p, d_neigh_NxK, d_normals_Nx3, true);
 }
 
 BSEG_API int bseg_grow_planes(bseg_ctx* c, const bseg_params* p, int32_t* plane_idx_N, int32_t* label_N,
@@ -320,14 +361,22 @@ BSEG_API int bseg_get_planes(bseg_ctx* c, int32_t* seeds_P, double* normals_Px3,
   return stage_get_planes(c, seeds_P, normals_Px3, centers_Px3, offsets_Pp1, point_idx);
 }
 
-BSEG_API int bseg_paint(bseg_ctx* c, const uint16_t* plane_rgb_Px3, uint16_t* colors_Nx3)
+BSEG_API int bseg_paint(bseg_ctx* c, const int32_t* plane_ids_Q, int32_t n_listed, const uint16_t* plane_rgb_Qx3,
+                        uint16_t* colors_Nx3)
 {
   RC_CHECK(check_ctx(c));
   if (!c->have_grow)
     return bseg_fail(c, BSEG_E_STATE, "bseg_paint before bseg_grow_planes");
-  if (!colors_Nx3 || (c->n_planes > 0 && !plane_rgb_Px3))
-    return bseg_fail(c, BSEG_E_ARG, "bseg_paint: NULL buffer");
-  return stage_paint(c, plane_rgb_Px3, colors_Nx3);
+  if (!colors_Nx3 || n_listed < 0 || (n_listed > 0 && !plane_rgb_Qx3))
+    return bseg_fail(c, BSEG_E_ARG, "bseg_paint: NULL buffer or negative count");
+  if (!plane_ids_Q && n_listed != c->n_planes)
+    return bseg_fail(c, BSEG_E_ARG, "bseg_paint: %d colours for %d planes (pass plane ids to paint a subset)", n_listed,
+                     c->n_planes);
+  if (plane_ids_Q)
+    for (int32_t q = 0; q < n_listed; ++q)
+      if (plane_ids_Q[q] < 1 || plane_ids_Q[q] > c->n_planes)
+        return bseg_fail(c, BSEG_E_ARG, "bseg_paint: plane id %d outside 1..%d", plane_ids_Q[q], c->n_planes);
+  return stage_paint(c, plane_ids_Q, n_listed, plane_rgb_Qx3, colors_Nx3);
 }
 
 BSEG_API int bseg_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H)
@@ -382,6 +431,7 @@ BSEG_API int bseg_run_device(bseg_ctx* c, const bseg_params* p, int stages)
     return bseg_fail(c, BSEG_E_STATE, "bseg_run_device before bseg_set_points");
   if (stages & BSEG_RUN_KNN) {
     RC_CHECK(stage_bin(c, p));
+    c->have_bin = true;
     RC_CHECK(stage_knn(c, p));
     c->have_knn = true;
     c->have_grow = false;
@@ -486,7 +536,7 @@ BSEG_API int bseg_debug_sort_pairs(bseg_ctx* c, uint64_t* keys, uint32_t* vals, 
   CU_CHECK(c, cudaMemcpyAsync(keys, c->keys[sel].p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(c, cudaMemcpyAsync(vals, c->vals[sel].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
-  c->have_knn = c->have_grow = false;
+  c->have_knn = c->have_grow = c->have_bin = false;
   return 0;
 }
 

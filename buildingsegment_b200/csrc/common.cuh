@@ -55,8 +55,11 @@ struct bseg_ctx {
   int64_t n_owned = 0;  // points this rank owns (== n on one GPU)
   int32_t mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
   bool have_points = false, have_knn = false, have_grow = false;
+  bool normals_nonunit = false;  // caller-supplied normals that are not unit length (bseg_override_neigh_normals)
+  bool have_bin = false;     // sorted cloud / cell tables valid for the current points and parameters
   bool have_origin = false;  // bseg_set_origin: shift by origin[] instead of the cloud's own minimum
   int32_t origin[3] = {0, 0, 0};
+  int32_t grow_off[3] = {0, 0, 0};  // bseg_set_grow_offset: added to the shifted coordinates the grower sees
 
   // ---- binning state (valid after the knn stage) ----
   int32_t cell = 0;     // kNN cell edge
@@ -100,6 +103,7 @@ struct bseg_ctx {
   DevBuf worklist;    // u32 lists: overflow cells, unresolved queries
   DevBuf counters;    // u64 [64] misc counters
   DevBuf out_tmp;     // staging for original-order exports
+  DevBuf x_neigh, x_normals;  // rows / normals in original order kept on the device (bseg_knn_device_results)
   // grower (sorted-position space unless noted)
   DevBuf g_state;     // int32 [n]: -1 free, else original index of the owning seed
   DevBuf g_res;       // u32 [n]: reservation = min original seed index that accepted the point
@@ -113,6 +117,7 @@ struct bseg_ctx {
   DevBuf g_marklog;   // uint2 [n]: orphan marks of the current sweep (point, seed)
   DevBuf g_label;     // int32 [n] label in original order
   DevBuf g_pidx;      // int32 [n] planeIdx in original order
+  DevBuf g_pts_raw;   // int4 [n]: pts + grow_off (only when an offset is set)
   // raster
   DevBuf r_hist;
   DevBuf r_image;     // double [W*H*3]
@@ -127,6 +132,9 @@ struct bseg_ctx {
   size_t pinned_cap = 0;
   bseg_timings tm;
   int64_t launches = 0;
+  // per-device one-time setup (cudaFuncSetAttribute is per device, a context is bound to one)
+  bool attr_sweep_set = false, attr_knn_set = false;
+  cudaEvent_t grow_ev[5] = {nullptr};  // phase events of the speculative grower (created on first use)
 };
 
 int bseg_fail(bseg_ctx* c, int code, const char* fmt, ...);
@@ -178,13 +186,15 @@ int stage_bin(bseg_ctx* c, const bseg_params* p);            // bin.cu
 int stage_knn(bseg_ctx* c, const bseg_params* p);            // knn.cu
 int stage_export_knn(bseg_ctx* c, const bseg_params* p, int32_t* h_neigh, double* h_normals, double* h_curv);
 int stage_halo_check(bseg_ctx* c, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved);  // knn.cu
-int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* h_neigh, const double* h_normals);
+int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* neigh, const double* normals, bool on_device);
+int stage_export_knn_device(bseg_ctx* c, const bseg_params* p, const int32_t** d_neigh, const double** d_normals);
+int stage_alloc_knn_outputs(bseg_ctx* c, const bseg_params* p);
 int stage_grow(bseg_ctx* c, const bseg_params* p);           // grow.cu
 void grow_host_free(bseg_ctx* c);
 int stage_export_grow(bseg_ctx* c, int32_t* h_plane_idx, int32_t* h_label);
 int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* centers, int64_t* offsets,
                      int32_t* point_idx);
-int stage_paint(bseg_ctx* c, const uint16_t* h_rgb, uint16_t* h_colors);
+int stage_paint(bseg_ctx* c, const int32_t* h_ids, int32_t n_listed, const uint16_t* h_rgb, uint16_t* h_colors);
 int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H);
 int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* a, uint8_t* b, uint8_t* cc,
                  double* th, bool device_only, const double* th_override = nullptr);

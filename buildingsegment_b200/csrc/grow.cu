@@ -152,6 +152,20 @@ __global__ void rowdup_kernel(const int32_t* __restrict__ nbr, int K, int64_t n,
   rowdup[s] = dup ? 1 : 0;
 }
 
+// the grower's int32 arithmetic in the CALLER's coordinates (bseg_set_grow_offset): pts + offset, wrapping as int32 does
+__global__ void offset_pts_kernel(const int4* __restrict__ pts, int64_t n, int32_t o0, int32_t o1, int32_t o2,
+                                  int4* __restrict__ out)
+{
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n)
+    return;
+  int4 p = pts[s];
+  p.x = (int32_t)((uint32_t)p.x + (uint32_t)o0);
+  p.y = (int32_t)((uint32_t)p.y + (uint32_t)o1);
+  p.z = (int32_t)((uint32_t)p.z + (uint32_t)o2);
+  out[s] = p;
+}
+
 // ---- finalize: plane ids, planeIdx and label in original order ------------------------------------------
 // id(owner) = 1 + #plane seeds < owner; label = id when the owner IS a plane seed, else the id of the
 // plane seeded at the point itself (a seed is in its own pointIdx without being marked), else 0.
@@ -214,6 +228,35 @@ __global__ void paint_kernel(const int32_t* __restrict__ label, const uint16_t* 
   colors[3 * o] = r;
   colors[3 * o + 1] = g;
   colors[3 * o + 2] = b;
+}
+
+// set_plane_color of a filtered / reordered plane vector (my_function.cpp:268-274): the planes are painted in the
+// order listed and a later one overwrites, so a point gets the colour of the LAST listed plane whose pointIdx
+// holds it.  rank_of[s] = 1 + highest list position among those planes (0 = none), by atomicMax over the entries.
+__global__ void paint_rank_kernel(const int32_t* __restrict__ pool, int64_t src_off, int64_t len, int32_t rank,
+                                  int32_t* __restrict__ rank_of)
+{
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < len)
+    atomicMax(rank_of + pool[src_off + t], rank);
+}
+
+__global__ void paint_by_rank_kernel(const int32_t* __restrict__ rank_of, const uint32_t* __restrict__ inv,
+                                     const uint16_t* __restrict__ rgb, int64_t n, uint16_t* __restrict__ colors)
+{
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n)
+    return;
+  const int32_t r = rank_of[inv[o]];
+  uint16_t c0 = 0, c1 = 0, c2 = 0;
+  if (r > 0) {
+    c0 = rgb[3 * (r - 1)];
+    c1 = rgb[3 * (r - 1) + 1];
+    c2 = rgb[3 * (r - 1) + 2];
+  }
+  colors[3 * o] = c0;
+  colors[3 * o + 1] = c1;
+  colors[3 * o + 2] = c2;
 }
 
 }  // namespace
@@ -290,12 +333,20 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   {
     const char* gf = getenv("BSEG_GROW_FLAGS");  // tuning switches of the step engine (grow.cuh GF_*)
     A.flags = gf ? atoi(gf) : (GF_ROWDUP | GF_FASTDIV | GF_ROW_L1);
-    if (getenv("BSEG_DEBUG")) A.flags |= GF_TIMING;  // per-phase cycle counters of the head slot (they cost ~10 %)
+    if (getenv("BSEG_DEBUG")) A.flags |= GF_TIMING;
+    if (c->normals_nonunit) A.flags |= GF_EXACT_MODEL;  // the margins of the approximate model assume unit normals  // per-phase cycle counters of the head slot (they cost ~10 %)
   }
   RC_CHECK(dev_ensure(c, c->g_rowdup, (size_t)n + 64));
   A.rowdup = dptr<uint8_t>(c->g_rowdup);
 
   STAGE_BEGIN(c, EV_GROW);
+  if (c->grow_off[0] | c->grow_off[1] | c->grow_off[2]) {
+    RC_CHECK(dev_ensure(c, c->g_pts_raw, (size_t)n * 16));
+    offset_pts_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<int4>(c->pts), n, c->grow_off[0], c->grow_off[1],
+                                                                          c->grow_off[2], dptr<int4>(c->g_pts_raw));
+    KLAUNCH_CHECK(c);
+    A.pts = dptr<int4>(c->g_pts_raw);
+  }
   rowdup_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(A.nbr, A.K, n, dptr<uint8_t>(c->g_rowdup));
   KLAUNCH_CHECK(c);
   CU_CHECK(c, cudaMemsetAsync(A.state, 0xff, (size_t)n * 4, c->stream));
@@ -395,19 +446,34 @@ int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* cent
   return 0;
 }
 
-int stage_paint(bseg_ctx* c, const uint16_t* h_rgb, uint16_t* h_colors)
+int stage_paint(bseg_ctx* c, const int32_t* h_ids, int32_t n_listed, const uint16_t* h_rgb, uint16_t* h_colors)
 {
   const int64_t n = c->n;
   if (n == 0)
     return 0;
-  const size_t rgb_bytes = (size_t)c->n_planes * 6;
-  RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * 6 + rgb_bytes + 64));
+  const size_t rgb_bytes = (size_t)n_listed * 6;
+  RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * 6 + rgb_bytes + (h_ids ? (size_t)n * 4 : 0) + 128));
   uint16_t* d_colors = dptr<uint16_t>(c->out_tmp);
   uint16_t* d_rgb = d_colors + 3 * n + 8;
   if (rgb_bytes)
     CU_CHECK(c, cudaMemcpyAsync(d_rgb, h_rgb, rgb_bytes, cudaMemcpyHostToDevice, c->stream));
-  paint_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->g_label), d_rgb, n, d_colors);
-  KLAUNCH_CHECK(c);
+  if (!h_ids) {
+    // all planes in id order: the label (last plane holding the point) names the colour
+    paint_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->g_label), d_rgb, n, d_colors);
+    KLAUNCH_CHECK(c);
+  } else {
+    std::vector<PlaneRec>& hp = host_planes(c);
+    int32_t* d_rank = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(d_rgb) + ((rgb_bytes + 15) & ~(size_t)15));
+    CU_CHECK(c, cudaMemsetAsync(d_rank, 0, (size_t)n * 4, c->stream));
+    for (int32_t q = 0; q < n_listed; ++q) {
+      const PlaneRec& r = hp[(size_t)h_ids[q] - 1];
+      paint_rank_kernel<<<(unsigned)ceil_div64(r.len, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->g_pool), r.off, r.len, q + 1,
+                                                                                d_rank);
+      KLAUNCH_CHECK(c);
+    }
+    paint_by_rank_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(d_rank, dptr<uint32_t>(c->inv), d_rgb, n, d_colors);
+    KLAUNCH_CHECK(c);
+  }
   CU_CHECK(c, cudaMemcpyAsync(h_colors, d_colors, (size_t)n * 6, cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   return 0;

@@ -922,19 +922,19 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     spec_alive_init_kernel<<<(unsigned)ceil_div64(alive_words, TPB), TPB, 0, c->stream>>>(S.alive, n, alive_words);
     KLAUNCH_CHECK(c);
   }
-  static bool attr_set = false;
   const size_t sweep_smem = (size_t)HT * 8;
-  if (!attr_set) {
+  if (!c->attr_sweep_set) {
     CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
     CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
-    attr_set = true;
+    c->attr_sweep_set = true;
   }
 
   int64_t F = 0, rounds = 0, stalls = 0, fallbacks = 0;
   const bool dbg = getenv("BSEG_DEBUG") != nullptr;
-  cudaEvent_t pe[5];
+  cudaEvent_t* pe = c->grow_ev;  // owned by the context: no leak on the error returns below
   float pt[4] = {0, 0, 0, 0};
-  for (auto& e : pe) cudaEventCreate(&e);
+  for (int k = 0; k < 5; ++k)
+    if (!pe[k]) cudaEventCreate(&pe[k]);
   unsigned long long ctl[64] = {0};
   uint32_t* d_ncand = reinterpret_cast<uint32_t*>(&S.sc[SC_NCAND]);
   const unsigned sb = (unsigned)((S.G + GW - 1) / GW);
@@ -1025,7 +1025,6 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     fprintf(stderr, "[bseg] rounds %lld: release %.1f ms, scout+assign %.1f ms, slices %.1f ms, sweep+apply %.1f ms\n", (long long)rounds,
             pt[0], pt[1], pt[2], pt[3]);
   }
-  for (auto& e : pe) cudaEventDestroy(e);
   c->tm.grow_slice_ms = pt[2];
   c->tm.grow_sweep_ms = pt[3];
   if (dbg)

@@ -1106,15 +1106,19 @@ __global__ void import_rows_kernel(const int32_t* __restrict__ in, const uint32_
 }
 
 __global__ void import_normals_kernel(const double* __restrict__ in, const uint32_t* __restrict__ inv, int64_t n,
-                                      double* __restrict__ nrm)
+                                      double* __restrict__ nrm, unsigned long long* __restrict__ n_nonunit)
 {
   int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n)
     return;
   int64_t s = inv[o];
-  nrm[3 * s] = in[3 * o];
-  nrm[3 * s + 1] = in[3 * o + 1];
-  nrm[3 * s + 2] = in[3 * o + 2];
+  const double a = in[3 * o], b = in[3 * o + 1], cc = in[3 * o + 2];
+  nrm[3 * s] = a;
+  nrm[3 * s + 1] = b;
+  nrm[3 * s + 2] = cc;
+  // the grower's approximate-model margins (grow.cuh geo_test_margin) assume |n_i| ~ 1: count the others
+  const double q = a * a + b * b + cc * cc;
+  if (!(q > 0.999 && q < 1.001)) atomicAdd(n_nonunit, 1ull);
 }
 
 }  // namespace
@@ -1122,6 +1126,7 @@ __global__ void import_normals_kernel(const double* __restrict__ in, const uint3
 int stage_knn(bseg_ctx* c, const bseg_params* p)
 {
   const int64_t n = c->n;
+  c->normals_nonunit = false;
   if (n == 0)
     return 0;
   RC_CHECK(dev_ensure(c, c->nbr, (size_t)n * p->K * 4));
@@ -1177,13 +1182,12 @@ int stage_knn(bseg_ctx* c, const bseg_params* p)
   const bool groups = groups_on && (p->K == 15 || p->K == 16);
   if (groups) {
     const size_t gsmem = (size_t)GKW * GCAP * 16 + GKW * sizeof(GroupScratch);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->attr_knn_set) {
       CU_CHECK(c, cudaFuncSetAttribute(knn_groups_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
       CU_CHECK(c, cudaFuncSetAttribute(knn_groups_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
       CU_CHECK(c, cudaFuncSetAttribute(knn_dense_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
       CU_CHECK(c, cudaFuncSetAttribute(knn_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-      attr_set = true;
+      c->attr_knn_set = true;
     }
     GridLevel G0, G1;
     G0.cell_start = A.cell_start; G0.hk = A.hk; G0.hv = A.hv; G0.hmask = A.hmask; G0.guar2 = A.guar2;
@@ -1246,16 +1250,29 @@ __global__ void halo_check_kernel(const int4* __restrict__ pts, const int32_t* _
     return;
   const int4 q = __ldg(pts + s);
   if (q.w >= n_owned)
-    return;  // a halo copy: only a neighbour
-  if ((int64_t)q.x - x_lo >= halo && (int64_t)x_hi - q.x > halo)
-    return;  // deep inside the slab: its neighbourhood cannot reach past the halo
+    return;  // declared a halo copy (bseg_set_owned): only a neighbour
+  // a face without a neighbour rank (outer face of the tile) is INT32_MIN / INT32_MAX: nothing lies beyond it
+  const bool has_l = x_lo != INT32_MIN, has_r = x_hi != INT32_MAX;
+  if ((has_l && q.x < x_lo) || (has_r && q.x >= x_hi))
+    return;  // outside the slab: a halo copy by position
+  // the points this rank does NOT hold lie more than `halo` beyond a face: at least reach = halo + (distance of q
+  // to that face) away from q
+  int64_t reach = INT64_MAX;
+  if (has_l) reach = (int64_t)q.x - x_lo + halo;
+  if (has_r) {
+    const int64_t r = (int64_t)x_hi - 1 - q.x + halo;
+    reach = r < reach ? r : reach;
+  }
+  if (reach == INT64_MAX)
+    return;
   int32_t last = -1;
   for (int j = K - 1; j >= 0 && last < 0; --j) last = __ldg(nbr + s * K + j);
   bool bad = last < 0;  // fewer than K points in reach at all
   if (!bad) {
+    bad = __ldg(nbr + s * K + (K - 1)) < 0;  // a short row: the missing entries may lie beyond the halo
     const int4 r = __ldg(pts + last);
     const int64_t dx = (int64_t)r.x - q.x, dy = (int64_t)r.y - q.y, dz = (int64_t)r.z - q.z;
-    bad = dx * dx + dy * dy + dz * dz > (int64_t)halo * halo;
+    bad = bad || dx * dx + dy * dy + dz * dz > reach * reach;
   }
   if (bad) atomicAdd(count, 1ull);
 }
@@ -1311,28 +1328,75 @@ int stage_export_knn(bseg_ctx* c, const bseg_params* p, int32_t* h_neigh, double
   return 0;
 }
 
-int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* h_neigh, const double* h_normals)
+int stage_override(bseg_ctx* c, const bseg_params* p, const int32_t* neigh, const double* normals, bool on_device)
 {
   const int64_t n = c->n;
   if (n == 0)
     return 0;
   const int K = p->K;
-  if (h_neigh) {
-    RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * K * 4));
-    CU_CHECK(c, cudaMemcpyAsync(c->out_tmp.p, h_neigh, (size_t)n * K * 4, cudaMemcpyHostToDevice, c->stream));
-    import_rows_kernel<<<(unsigned)ceil_div64(n * K, 256), 256, 0, c->stream>>>(
-        dptr<int32_t>(c->out_tmp), dptr<uint32_t>(c->inv), n, K, dptr<int32_t>(c->nbr));
+  if (neigh) {
+    const int32_t* src = neigh;
+    if (!on_device) {
+      RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * K * 4));
+      CU_CHECK(c, cudaMemcpyAsync(c->out_tmp.p, neigh, (size_t)n * K * 4, cudaMemcpyHostToDevice, c->stream));
+      src = dptr<int32_t>(c->out_tmp);
+    }
+    import_rows_kernel<<<(unsigned)ceil_div64(n * K, 256), 256, 0, c->stream>>>(src, dptr<uint32_t>(c->inv), n, K,
+                                                                              dptr<int32_t>(c->nbr));
     KLAUNCH_CHECK(c);
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
   }
-  if (h_normals) {
-    RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * 24));
-    CU_CHECK(c, cudaMemcpyAsync(c->out_tmp.p, h_normals, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
-    import_normals_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<double>(c->out_tmp),
-                                                                             dptr<uint32_t>(c->inv), n,
-                                                                             dptr<double>(c->nrm));
+  if (normals) {
+    const double* src = normals;
+    if (!on_device) {
+      RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n * 24));
+      CU_CHECK(c, cudaMemcpyAsync(c->out_tmp.p, normals, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
+      src = dptr<double>(c->out_tmp);
+    }
+    RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 189;
+    CU_CHECK(c, cudaMemsetAsync(cnt, 0, sizeof(*cnt), c->stream));
+    import_normals_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(src, dptr<uint32_t>(c->inv), n,
+                                                                             dptr<double>(c->nrm), cnt);
+    KLAUNCH_CHECK(c);
+    unsigned long long h = 0;
+    RC_CHECK(read_back(c, &h, cnt, sizeof(h)));
+    c->normals_nonunit = h != 0;  // un-normalised caller normals: the grower decides with the exact model only
+  }
+  return 0;
+}
+
+// rows / normals of the last kNN stage in ORIGINAL index space, left on the device (multi-GPU: the rows of a slab
+// travel to the rank that grows the tile without a host round trip)
+int stage_export_knn_device(bseg_ctx* c, const bseg_params* p, const int32_t** d_neigh, const double** d_normals)
+{
+  const int64_t n = c->n;
+  const int K = p->K;
+  RC_CHECK(dev_ensure(c, c->x_neigh, (size_t)n * K * 4));
+  RC_CHECK(dev_ensure(c, c->x_normals, (size_t)n * 24));
+  if (n > 0) {
+    export_rows_kernel<<<(unsigned)ceil_div64(n * K, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->nbr), dptr<int4>(c->pts),
+                                                                              n, K, dptr<int32_t>(c->x_neigh));
+    KLAUNCH_CHECK(c);
+    export_normals_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<double>(c->nrm), dptr<double>(c->curv),
+                                                                             dptr<int4>(c->pts), n,
+                                                                             dptr<double>(c->x_normals), nullptr);
     KLAUNCH_CHECK(c);
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
   }
+  if (d_neigh) *d_neigh = dptr<int32_t>(c->x_neigh);
+  if (d_normals) *d_normals = dptr<double>(c->x_normals);
+  return 0;
+}
+
+// binning only + room for rows / normals that arrive from elsewhere (bseg_import_neigh_normals_device)
+int stage_alloc_knn_outputs(bseg_ctx* c, const bseg_params* p)
+{
+  const int64_t n = c->n;
+  RC_CHECK(dev_ensure(c, c->nbr, (size_t)n * p->K * 4));
+  RC_CHECK(dev_ensure(c, c->nrm, (size_t)n * 24));
+  RC_CHECK(dev_ensure(c, c->curv, (size_t)n * 8));
+  if (n > 0)
+    CU_CHECK(c, cudaMemsetAsync(c->curv.p, 0, (size_t)n * 8, c->stream));
   return 0;
 }

@@ -12,6 +12,19 @@ bseg_params g_params;
 bool g_params_init = false;
 const int32_t* g_cloud_ptr = nullptr;
 size_t g_cloud_n = 0;
+uint64_t g_cloud_sum = 0;       // checksum of the positions the device holds (the caller may edit the cloud in place)
+bool g_cloud_shifted = false;   // the host cloud carries the shifted coordinates (buildingSeg ran on it)
+int32_t g_cloud_min[3] = {0, 0, 0};
+
+uint64_t checksum(const int32_t* p, size_t n)
+{
+  uint64_t a = 1469598103934665603ull, b = 0;
+  for (size_t i = 0; i < 3 * n; ++i) {
+    a += (uint32_t)p[i];
+    b += a;
+  }
+  return a ^ (b << 1);
+}
 }  // namespace
 
 void check(int rc, const char* what)
@@ -44,14 +57,17 @@ bseg_ctx* context()
 bool ensure_cloud(PCCPointSet3& cloud, bool shift_caller_cloud)
 {
   const size_t n = cloud.getPointCount();
-  if (!shift_caller_cloud && g_cloud_ptr == cloud.positionData() && g_cloud_n == n && n > 0)
+  const uint64_t sum = checksum(cloud.positionData(), n);
+  if (!shift_caller_cloud && g_cloud_ptr == cloud.positionData() && g_cloud_n == n && g_cloud_sum == sum && n > 0)
     return false;
-  int32_t mn[3], mx[3];
-  check(bseg_set_points(context(), cloud.positionData(), (int64_t)n, mn, mx,
+  int32_t mx[3];
+  check(bseg_set_points(context(), cloud.positionData(), (int64_t)n, g_cloud_min, mx,
                         shift_caller_cloud ? cloud.positionData() : nullptr),
         "bseg_set_points");
   g_cloud_ptr = cloud.positionData();
   g_cloud_n = n;
+  g_cloud_shifted = shift_caller_cloud;
+  g_cloud_sum = shift_caller_cloud ? checksum(cloud.positionData(), n) : sum;
   return true;
 }
 
@@ -59,7 +75,13 @@ void note_shifted(const PCCPointSet3& cloud)
 {
   g_cloud_ptr = cloud.positionData();
   g_cloud_n = cloud.getPointCount();
+  g_cloud_sum = checksum(cloud.positionData(), g_cloud_n);
+  g_cloud_shifted = true;
 }
+
+// seg_plane works in the coordinates of the cloud it is given (my_function.cpp:190,227,242-250): when that cloud is
+// not the shifted one, the device adds the subtracted minimum back for the grower's int32 arithmetic
+const int32_t* grow_offset() { return g_cloud_shifted ? nullptr : g_cloud_min; }
 
 }  // namespace bseg_host
 
@@ -78,6 +100,7 @@ std::vector<plane> seg_plane::get_planes()
     for (size_t k = 0; k < Neigh[i].size() && k < (size_t)K; ++k) flat[i * K + k] = Neigh[i][k];
   check(bseg_override_neigh_normals(context(), &p, flat.data(), n ? &Normal[0][0] : nullptr),
         "bseg_override_neigh_normals");
+  check(bseg_set_grow_offset(context(), grow_offset()), "bseg_set_grow_offset");
   int32_t np = 0;
   std::vector<int32_t> label(n);
   Cloud.planeIdx.resize(n);
@@ -114,27 +137,50 @@ const std::vector<uint16_t>& last_plane_rgb() { return g_last_rgb; }
 void seg_plane::set_plane_color(std::vector<plane>& planes)
 {
   using namespace bseg_host;
-  const size_t n = Cloud.getPointCount();
   if (!Cloud.hasColors())
     Cloud.addColors();  // the reference requires colours (PCCPointSet.h:289-293 asserts)
+  // my_function.cpp:260-275 paints the pointIdx of exactly the planes it is handed, in their order: the caller may
+  // have filtered or reordered the vector.  The device holds the lists of the last get_planes(); a plane is named
+  // by its id, and a plane whose pointIdx was edited on the host is refused (nothing here paints on the CPU).
+  const int32_t device_planes = bseg_plane_count(context());
+  std::vector<int64_t> off((size_t)(device_planes > 0 ? device_planes : 0) + 1, 0);
+  if (device_planes > 0)
+    check(bseg_get_planes(context(), nullptr, nullptr, nullptr, off.data(), nullptr), "bseg_get_planes");
+  std::vector<int32_t> ids(planes.size());
   std::vector<uint16_t> rgb(planes.size() * 3);
-  for (size_t q = 0; q < planes.size(); ++q)
+  bool canonical = (int64_t)planes.size() == (int64_t)device_planes;
+  for (size_t q = 0; q < planes.size(); ++q) {
+    const int id = planes[q].id;
+    if (id < 1 || id > device_planes)
+      throw std::runtime_error("set_plane_color: plane id " + std::to_string(id) + " is not a plane of the last get_planes()");
+    if ((int64_t)planes[q].pointIdx.size() != off[id] - off[id - 1])
+      throw std::runtime_error("set_plane_color: pointIdx of plane " + std::to_string(id) + " was modified on the host");
+    ids[q] = id;
+    canonical = canonical && id == (int)q + 1;
     for (int k = 0; k < 3; ++k) rgb[3 * q + k] = uint16_t(55 + rand() % 200);  // braced-init order, :268
-  check(bseg_paint(context(), rgb.data(), Cloud.colorData()), "bseg_paint");
-  g_last_rgb = rgb;
-  (void)n;
+  }
+  check(bseg_paint(context(), canonical ? nullptr : ids.data(), (int32_t)planes.size(), rgb.data(), Cloud.colorData()),
+        "bseg_paint");
+  // colour table by plane id for the label image (black for planes that were not listed)
+  g_last_rgb.assign((size_t)(device_planes > 0 ? device_planes : 0) * 3, 0);
+  for (size_t q = 0; q < planes.size(); ++q)
+    for (int k = 0; k < 3; ++k) g_last_rgb[3 * (size_t)(ids[q] - 1) + k] = rgb[3 * q + k];
 }
 
 vector<string> Split(const string& s, const string& seperator)
 {
+  // my_function.cpp:147-160: cut at every occurrence of the whole separator STRING; empty tokens are kept and
+  // the remainder (possibly empty) is always the last token
   vector<string> out;
   size_t pos = 0;
-  while (pos <= s.size()) {
-    size_t next = s.find_first_of(seperator, pos);
-    if (next == string::npos) next = s.size();
-    if (next > pos) out.push_back(s.substr(pos, next - pos));
-    pos = next + 1;
+  for (;;) {
+    const size_t next = seperator.empty() ? string::npos : s.find(seperator, pos);
+    if (next == string::npos)
+      break;
+    out.push_back(s.substr(pos, next - pos));
+    pos = next + seperator.length();
   }
+  out.push_back(s.substr(pos));
   return out;
 }
 
@@ -142,11 +188,13 @@ param analyse_path(char* argv[])
 {
   param p;
   p.frame = 0;
-  // flag names are ignored: only the text after '=' of argv[1] (input) and argv[2] (output) counts
+  // my_function.cpp:163-178: flag names are ignored, the path is token [1] of Split(arg, "=") -- the text between
+  // the first and the second '='.  The reference indexes [1] unchecked; an argument without '=' is an error here.
   auto value = [](const char* a) {
-    string s(a ? a : "");
-    size_t eq = s.find('=');
-    return eq == string::npos ? s : s.substr(eq + 1);
+    const vector<string> t = Split(string(a ? a : ""), "=");
+    if (t.size() < 2)
+      throw std::runtime_error("tmc3: expected -<flag>=<path>, got '" + string(a ? a : "") + "'");
+    return t[1];
   };
   p.readPath = value(argv[1]);
   p.savePath = value(argv[2]);

@@ -50,6 +50,7 @@ void check(int rc, const char* what);
 // positions were last written by us).  Returns true when an upload happened.
 bool ensure_cloud(PCCPointSet3& cloud, bool shift_caller_cloud);
 void note_shifted(const PCCPointSet3& cloud);
+const int32_t* grow_offset();  // minimum the device subtracted from an unshifted cloud, NULL for a shifted one
 
 // the colour sequence the last set_plane_color drew (55 + rand() % 200, three per plane): the label image uses it
 const std::vector<uint16_t>& last_plane_rgb();

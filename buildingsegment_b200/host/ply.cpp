@@ -73,7 +73,9 @@ T loadAs(const uint8_t* p, bool swap)
 
 double loadReal(const Prop& pr, const uint8_t* rec, bool swap)
 {
-  return pr.type == Ty::F32 ? double(loadAs<float>(rec + pr.offset, swap)) : loadAs<double>(rec + pr.offset, swap);
+  // by width, as the reference does (ply.cpp:437-465): a 4-byte position property is read as a float whatever its
+  // declared type (int / uint32 bit patterns are reinterpreted, not converted), an 8-byte one as a double
+  return pr.bytes == 4 ? double(loadAs<float>(rec + pr.offset, swap)) : loadAs<double>(rec + pr.offset, swap);
 }
 
 }  // namespace

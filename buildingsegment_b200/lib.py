@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "bseg_create", "bseg_destroy", "bseg_default_params", "bseg_last_error", "bseg_version",
     "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
-    "bseg_grow_planes", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_raster_device", "bseg_label_raster",
+    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_raster_device", "bseg_label_raster",
     "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
     "bseg_point_count", "bseg_plane_count", "bseg_set_owned", "bseg_set_origin", "bseg_device_results", "bseg_halo_check", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
 ]
@@ -82,7 +82,7 @@ def lib():
         L.bseg_override_neigh_normals.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.bseg_grow_planes.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
         L.bseg_get_planes.argtypes = [vp, vp, vp, vp, vp, vp]
-        L.bseg_paint.argtypes = [vp, vp, vp]
+        L.bseg_paint.argtypes = [vp, vp, C.c_int32, vp, vp]
         L.bseg_raster_size.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.bseg_raster.argtypes = [vp, C.POINTER(Params), vp, vp, vp, vp, vp]
         L.bseg_label_raster.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
@@ -101,6 +101,9 @@ def lib():
         L.bseg_set_origin.argtypes = [vp, vp]
         L.bseg_device_results.argtypes = [vp, vp, vp, vp]
         L.bseg_halo_check.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.bseg_set_grow_offset.argtypes = [vp, vp]
+        L.bseg_knn_device_results.argtypes = [vp, C.POINTER(Params), vp, vp]
+        L.bseg_import_neigh_normals_device.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.bseg_debug_sort_pairs.argtypes = [vp, vp, vp, i64, C.c_int]
         L.bseg_debug_exclusive_scan.argtypes = [vp, vp, i64]
         _LIB = L
@@ -211,6 +214,23 @@ class Context:
             assert normals.shape == (self.n, 3)
         self._ck(lib().bseg_override_neigh_normals(self._h, C.byref(p), _ptr(neigh), _ptr(normals)))
 
+    def knn_device_results(self, p: Params):
+        """Device addresses of the rows [n][K] (int32, original indices) and normals [n][3] (float64) of the last kNN stage."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(lib().bseg_knn_device_results(self._h, C.byref(p), C.addressof(a), C.addressof(b)))
+        return a.value, b.value
+
+    def import_neigh_normals_device(self, p: Params, d_neigh, d_normals):
+        """Rows / normals computed elsewhere (device pointers, original indexing) become the grower's input; no kNN runs."""
+        self._ck(lib().bseg_import_neigh_normals_device(self._h, C.byref(p), int(d_neigh), int(d_normals)))
+
+    def set_grow_offset(self, offset):
+        if offset is None:
+            self._ck(lib().bseg_set_grow_offset(self._h, None))
+        else:
+            o = np.ascontiguousarray(offset, np.int32)
+            self._ck(lib().bseg_set_grow_offset(self._h, o.ctypes.data))
+
     # -- a7-a9 ------------------------------------------------------------------------------------
     def grow_planes(self, p: Params, want_arrays=True):
         n = self.n
@@ -232,10 +252,12 @@ class Context:
         return seeds, normals, centers, off, idx
 
     # -- a10 --------------------------------------------------------------------------------------
-    def paint(self, plane_rgb):
-        plane_rgb = np.ascontiguousarray(plane_rgb, np.uint16)
+    def paint(self, plane_rgb, plane_ids=None):
+        """set_plane_color: all planes in id order (plane_ids None), or the listed planes in the listed order."""
+        plane_rgb = np.ascontiguousarray(plane_rgb, np.uint16).reshape(-1, 3)
         colors = np.empty((self.n, 3), np.uint16)
-        self._ck(lib().bseg_paint(self._h, _ptr(plane_rgb), _ptr(colors)))
+        ids = None if plane_ids is None else np.ascontiguousarray(plane_ids, np.int32)
+        self._ck(lib().bseg_paint(self._h, None if ids is None else _ptr(ids), len(plane_rgb), _ptr(plane_rgb), _ptr(colors)))
         return colors
 
     # -- a13-a15 ----------------------------------------------------------------------------------

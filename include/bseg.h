@@ -15,7 +15,7 @@
  *   - a context is bound to one CUDA device and one stream, and is not thread-safe;
  *   - there is no CPU fallback: without a CUDA device bseg_create fails with BSEG_E_NODEVICE.
  *   - coordinates are int32 (millimetres after ply::read's x1000); after the shift to the cloud
- *     minimum every extent must be < 2^21 kNN cells and < 2^25 units.
+ *     minimum every extent must be < 2^21 kNN cells and < 2^23 units (BSEG_E_ARG otherwise).
  */
 #ifndef BSEG_H
 #define BSEG_H
@@ -122,6 +122,13 @@ BSEG_API int bseg_override_neigh_normals(bseg_ctx* ctx, const bseg_params* p, co
 BSEG_API int bseg_grow_planes(bseg_ctx* ctx, const bseg_params* p, int32_t* plane_idx_N, int32_t* label_N,
                               int32_t* n_planes);
 
+/* seg_plane on a cloud that buildingSeg has NOT shifted (my_function.h:98 takes any cloud): the device copy is
+ * always shifted to min = 0 for the binning, but the reference's int32 centroid sums (and where they wrap, SURVEY
+ * A.2-Q6) are in the caller's coordinates.  offset (normally out_min of bseg_set_points) is added back, with int32
+ * wrap, to every coordinate the grower's model arithmetic sees; NULL or zeros = the shifted coordinates (default,
+ * what TMC3.cpp:210-218 feeds seg_plane).  plane centres are reported in the same coordinates. */
+BSEG_API int bseg_set_grow_offset(bseg_ctx* ctx, const int32_t offset[3]);
+
 /* std::vector<plane> of get_planes (my_function.h:25-30): ids are 1..P in order;
  * offsets_Pp1/point_idx are pointIdx in the reference's order, duplicates kept.
  * Call with point_idx == NULL to size the buffers (total entries = offsets[P]). */
@@ -129,8 +136,14 @@ BSEG_API int bseg_get_planes(bseg_ctx* ctx, int32_t* seeds_P, double* normals_Px
                              int64_t* offsets_Pp1, int32_t* point_idx);
 
 /* ---- stage a10: seg_plane::set_plane_color (my_function.cpp:260-275) --------------------------
- * plane_rgb_Px3 is the host's rand() sequence (55 + rand() % 200, three per plane). */
-BSEG_API int bseg_paint(bseg_ctx* ctx, const uint16_t* plane_rgb_Px3, uint16_t* colors_Nx3);
+ * Paints exactly the pointIdx of the planes it is given, in the order given (later planes overwrite, :268-274),
+ * black everywhere else.  plane_ids_Q names the planes (ids 1..P of the last bseg_grow_planes, any subset in any
+ * order -- a caller may filter or reorder the vector before colouring); NULL means all planes in id order, and
+ * then n_listed must equal the plane count.  plane_rgb_Qx3 is the host's rand() sequence (55 + rand() % 200,
+ * three per LISTED plane, drawn in the listed order).  A count that disagrees is BSEG_E_ARG, never a read past
+ * the caller's buffer. */
+BSEG_API int bseg_paint(bseg_ctx* ctx, const int32_t* plane_ids_Q, int32_t n_listed, const uint16_t* plane_rgb_Qx3,
+                        uint16_t* colors_Nx3);
 
 /* ---- stages a13-a15: groundTH + compute_gird_picture + save_image pixels (TMC3.cpp:81-198) -----
  * image_WxHx3: doubles, pixel(x,y,ch) = image[(y*W+x)*3+ch]; png_rgb[0..2]: the three W*H*3
@@ -189,9 +202,23 @@ BSEG_API int bseg_set_origin(bseg_ctx* ctx, const int32_t origin[3]);
 BSEG_API int bseg_device_results(bseg_ctx* ctx, const int32_t** d_label, const int32_t** d_plane_idx,
                                  const int32_t** d_xyz_shifted);
 /* Halo sufficiency: counts owned points within `halo` of the slab faces x_lo / x_hi (shifted units) whose
- * K-th neighbour is farther than `halo` -- a closer point beyond the halo could exist; 0 = kNN rows and
- * normals of all owned points equal those of the undivided cloud (given halo >= params.radius). */
+ * K-th neighbour is farther than the nearest point this rank may be missing (halo + its distance to the face) --
+ * a closer point beyond the halo could exist; 0 = kNN rows and normals of all owned points equal those of the
+ * undivided cloud (given halo >= params.radius).  A point is owned when x_lo <= x < x_hi (and, if bseg_set_owned
+ * was called, its index is below n_owned).  An outer face of the tile, which has no neighbour rank and nothing
+ * beyond it, is passed as INT32_MIN (x_lo) / INT32_MAX (x_hi) and is not checked. */
 BSEG_API int bseg_halo_check(bseg_ctx* ctx, int32_t x_lo, int32_t x_hi, int32_t halo, int64_t* n_unresolved);
+
+/* Rows and normals of the last kNN stage in ORIGINAL index space, left in device memory (valid until the next
+ * bseg_set_points / kNN stage): the slab's share of get_Normal_and_K_neighbor (my_function.h:48-85) travels to the
+ * rank that grows the tile over NVLink, no host round trip. */
+BSEG_API int bseg_knn_device_results(bseg_ctx* ctx, const bseg_params* p, const int32_t** d_neigh_NxK,
+                                     const double** d_normals_Nx3);
+/* The device-pointer form of bseg_override_neigh_normals that does NOT run the kNN stage: the cloud is binned
+ * (sorted order only) and the rows / normals -- computed elsewhere, e.g. by the slabs of a tile -- become the
+ * input of bseg_grow_planes, as seg_plane's constructor takes any vectors (my_function.h:98). */
+BSEG_API int bseg_import_neigh_normals_device(bseg_ctx* ctx, const bseg_params* p, const int32_t* d_neigh_NxK,
+                                              const double* d_normals_Nx3);
 
 /* ---- self-test hooks used by tests/ (exercise the hand-written primitives in isolation) ------- */
 BSEG_API int bseg_debug_sort_pairs(bseg_ctx* ctx, uint64_t* keys, uint32_t* vals, int64_t n, int key_bits);
