@@ -21,13 +21,15 @@
  * PARITY PINNING
  *   - orc_grow / orc_paint / orc_ground_th / orc_raster / orc_save_image are pinned: tests compare
  *     them bit-for-bit with the reference's own lines compiled verbatim into oracle/_ref
- *     (oracle/build_ref.sh).  The only non-identical op is log(): the oracle uses the shared
- *     fdlibm-style bseg_log, the reference glibc's; they agree to <= 1 ulp.
+ *     (oracle/build_ref.sh), doubles included: log() is the platform libm's on both sides (the product
+ *     finalises the count channel on the host with the same libm, csrc/raster.cu).
  *   - orc_knn / orc_normals are "parity unpinned": the arithmetic lives in Open3D 0.19.0 /
  *     nanoflann, which are not under /root/reference and not installable here, and the reference
  *     has no tests or golden vectors.  They restate the published algorithms (Open3D
  *     EstimateNormals.cpp, KDTreeFlann.cpp, utility/Eigen.cpp) and are cross-checked against
- *     scipy cKDTree and numpy eigh in tests/.  nanoflann's tie order is tree-traversal order
+ *     scipy cKDTree, numpy eigh and an INDEPENDENT numpy transcription of ComputeCovariance /
+ *     FastEigen3x3 / ComputeEigenvector0/1 (tests/open3d_restated.py, which does not include the
+ *     shared header below) on 10^6 covariances, degenerate families included.  nanoflann's tie order is tree-traversal order
  *     (implementation-defined), so ties are canonicalised to (d^2 ascending, index ascending).
  *
  * Build: gcc -O2 -ffp-contract=off -fwrapv -fopenmp -shared -fPIC (oracle/Makefile).
@@ -422,7 +424,7 @@ static int orc_raster_impl(const int32_t* xyz, int64_t n, double th, int bin, do
     if (image[3 * px + 1] != 0)
       image[3 * px] = image[3 * px] / image[3 * px + 1];
   for (size_t px = 0; px < (size_t)W * H; ++px) {
-    image[3 * px + 1] = bseg_log(image[3 * px + 1] + 1);
+    image[3 * px + 1] = log(image[3 * px + 1] + 1); /* the platform's libm, as the reference's std::log (TMC3.cpp:161) */
     if (image[3 * px + 1] != 0)
       image[3 * px + 1] += bias;
   }
@@ -459,6 +461,22 @@ ORC_API double orc_acos(double x) { return bseg_acos(x); }
 ORC_API double orc_cos(double x) { return bseg_cos(x); }
 ORC_API double orc_log(double x) { return bseg_log(x); }
 ORC_API void orc_eigen(const double cov[6], double out[3], double ev[3]) { bseg_fast_eigen3x3(cov, out, ev); }
+/* vector forms for the independent-restatement tests: which = 0 acos, 1 cos (the shared polynomial kernels) */
+ORC_API void orc_trig_vec(const double* x, int64_t n, int which, double* out)
+{
+  for (int64_t i = 0; i < n; ++i) out[i] = which == 0 ? bseg_acos(x[i]) : bseg_cos(x[i]);
+}
+ORC_API void orc_eigen_vec(const double* cov6, int64_t n, double* out3)
+{
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) bseg_fast_eigen3x3(cov6 + 6 * i, out3 + 3 * i, NULL);
+}
+/* covariance -> oriented normal exactly as orc_normals finishes a point (zero rule, +z orientation) */
+ORC_API void orc_normal_from_sums_vec(const double* sums9, const int32_t* cnt, int64_t n, double* out3)
+{
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) bseg_normal_from_sums(sums9 + 9 * i, cnt[i], out3 + 3 * i, NULL);
+}
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP
