@@ -125,12 +125,14 @@ BSEG_API void bseg_destroy(bseg_ctx* c)
   if (!c)
     return;
   cudaSetDevice(c->device);
+  raster_host_join(c);
   cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   DevBuf* all[] = {&c->xyz_raw, &c->minmax, &c->keys[0], &c->keys[1], &c->vals[0], &c->vals[1], &c->sort_cnt,
                    &c->scan_tmp, &c->pts, &c->inv, &c->flags, &c->cell_key, &c->cell_start, &c->hash_keys,
                    &c->hash_vals, &c->cell_key2, &c->cell_start2, &c->hash_keys2, &c->hash_vals2, &c->nbr, &c->nrm, &c->curv, &c->worklist, &c->counters, &c->out_tmp, &c->x_neigh, &c->x_normals,
                    &c->g_state, &c->g_res, &c->g_spec, &c->g_pool, &c->g_planes, &c->g_tx, &c->g_queue, &c->g_rowdup, &c->g_marklog,
-                   &c->g_stack, &c->g_label, &c->g_pidx, &c->g_pts_raw, &c->r_hist, &c->r_image, &c->r_png, &c->r_pix};
+                   &c->g_stack, &c->g_label, &c->g_pidx, &c->g_pts_raw, &c->r_hist, &c->r_image, &c->r_png, &c->r_pix, &c->r_cnt};
   for (DevBuf* b : all)
     dev_free(*b);
   for (int i = 0; i < EV_COUNT; ++i) {
@@ -140,6 +142,10 @@ BSEG_API void bseg_destroy(bseg_ctx* c)
   for (auto& e : c->grow_ev)
     if (e) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  if (c->raster_done) cudaEventDestroy(c->raster_done);
+  if (c->raster_copied) cudaEventDestroy(c->raster_copied);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   grow_host_free(c);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -160,6 +166,7 @@ static int set_points_common(bseg_ctx* c, int64_t n, int32_t out_min[3], int32_t
   c->n = n;
   c->n_owned = n;
   c->have_points = true;
+  raster_host_join(c);
   c->have_knn = c->have_grow = c->have_bin = false;
   RC_CHECK(stage_bbox_shift(c));
   for (int k = 0; k < 3; ++k) {
@@ -395,7 +402,7 @@ BSEG_API int bseg_raster_device(bseg_ctx* c, const bseg_params* p, const double*
   RC_CHECK(check_params(c, p));
   if (!c->have_points)
     return bseg_fail(c, BSEG_E_STATE, "bseg_raster_device before bseg_set_points");
-  RC_CHECK(stage_raster(c, p, nullptr, nullptr, nullptr, nullptr, nullptr, true, ground_th));
+  RC_CHECK(stage_raster(c, p, nullptr, nullptr, nullptr, nullptr, nullptr, RASTER_DEVICE_ONLY, ground_th));
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   if (d_image) *d_image = c->n > 0 ? dptr<double>(c->r_image) : nullptr;
   if (W) *W = c->rW;
@@ -420,7 +427,7 @@ BSEG_API int bseg_raster(bseg_ctx* c, const bseg_params* p, double* image_WxHx3,
   RC_CHECK(check_params(c, p));
   if (!c->have_points)
     return bseg_fail(c, BSEG_E_STATE, "bseg_raster before bseg_set_points");
-  return stage_raster(c, p, image_WxHx3, png_a, png_b, png_c, ground_th, false);
+  return stage_raster(c, p, image_WxHx3, png_a, png_b, png_c, ground_th, RASTER_SYNC);
 }
 
 BSEG_API int bseg_run_device(bseg_ctx* c, const bseg_params* p, int stages)
@@ -436,14 +443,23 @@ BSEG_API int bseg_run_device(bseg_ctx* c, const bseg_params* p, int stages)
     c->have_knn = true;
     c->have_grow = false;
   }
+  // the raster does not depend on the planes: its device pass goes first and the host half of its count channel
+  // (libm log, raster.cu) runs on a worker thread while the grower occupies the GPU
+  if (stages & BSEG_RUN_RASTER)
+    RC_CHECK(stage_raster(c, p, nullptr, nullptr, nullptr, nullptr, nullptr, RASTER_ASYNC));
   if (stages & BSEG_RUN_GROW) {
-    if (!c->have_knn)
+    if (!c->have_knn) {
+      raster_host_join(c);
       return bseg_fail(c, BSEG_E_STATE, "grow stage requested before knn");
-    RC_CHECK(stage_grow(c, p));
+    }
+    const int rc = stage_grow(c, p);
+    if (rc != 0) {
+      raster_host_join(c);
+      return rc;
+    }
     c->have_grow = true;
   }
-  if (stages & BSEG_RUN_RASTER)
-    RC_CHECK(stage_raster(c, p, nullptr, nullptr, nullptr, nullptr, nullptr, true));
+  RC_CHECK(raster_host_join(c));
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -457,13 +473,24 @@ BSEG_API int bseg_segment_host(bseg_ctx* c, const bseg_params* p, const int32_t*
   int32_t mn[3], mx[3];
   RC_CHECK(bseg_set_points(c, xyz_aos, n, mn, mx, xyz_shifted_out));
   RC_CHECK(bseg_knn_normals(c, p, nullptr, nullptr, nullptr));
-  RC_CHECK(bseg_grow_planes(c, p, nullptr, label_N, n_planes));
   if (png_a || png_b || W || H) {
     RC_CHECK(stage_raster_size(c, p, W, H));
-    if (png_a || png_b)
-      RC_CHECK(stage_raster(c, p, nullptr, png_a, png_b, nullptr, nullptr, false));
+    if (png_a || png_b)  // device pass now, host half (count channel, image B) overlapped with the grower
+      RC_CHECK(stage_raster(c, p, nullptr, png_a, png_b, nullptr, nullptr, RASTER_ASYNC));
   }
+  const int rc = bseg_grow_planes(c, p, nullptr, label_N, n_planes);
+  RC_CHECK(raster_host_join(c));
+  RC_CHECK(rc);
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+BSEG_API int bseg_count_channel(double* values, int64_t n, double bias, double* max_out)
+{
+  if (n < 0 || (n > 0 && !values))
+    return bseg_fail(nullptr, BSEG_E_ARG, "bseg_count_channel: bad arguments");
+  const double m = bseg_count_channel_host(values, n, bias);
+  if (max_out) *max_out = m;
   return 0;
 }
 
@@ -495,6 +522,7 @@ BSEG_API int bseg_get_timings(bseg_ctx* c, bseg_timings* out)
     total += ms;
   }
   c->tm.normals = 0.f;  // fused into the kNN kernel's epilogue
+  c->tm.raster_host = c->tm_raster_host_ms;
   c->tm.total = total;
   c->tm.kernel_launches = c->launches;
   *out = c->tm;

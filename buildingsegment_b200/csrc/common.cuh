@@ -123,6 +123,14 @@ struct bseg_ctx {
   DevBuf r_image;     // double [W*H*3]
   DevBuf r_png;       // u8 [3][W*H*3]
   DevBuf r_pix;       // u32 [W*H+1] pixel starts
+  DevBuf r_cnt;       // double [W*H] weight sums of the count channel (finalised on the host)
+  double* h_cnt = nullptr;  // pinned host copy of r_cnt, then log(count + 1) + bias
+  size_t h_cnt_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t raster_done = nullptr, raster_copied = nullptr;
+  void* raster_worker = nullptr;  // std::thread* of an asynchronous host half
+  double raster_max1 = 0.0;       // maximum of channel 1 after the host half
+  float tm_raster_host_ms = 0.f;
 
   // ---- timing ----
   cudaEvent_t ev[EV_COUNT] = {nullptr};      // stage begin
@@ -196,8 +204,13 @@ int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* cent
                      int32_t* point_idx);
 int stage_paint(bseg_ctx* c, const int32_t* h_ids, int32_t n_listed, const uint16_t* h_rgb, uint16_t* h_colors);
 int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H);
+// mode: host part of the count channel done before returning (SYNC), on a worker thread that raster_host_join()
+// waits for (ASYNC: overlaps the grower), or left to the caller (DEVICE_ONLY: bseg_raster_device)
+enum { RASTER_SYNC = 0, RASTER_ASYNC = 1, RASTER_DEVICE_ONLY = 2 };
 int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* a, uint8_t* b, uint8_t* cc,
-                 double* th, bool device_only, const double* th_override = nullptr);
+                 double* th, int mode, const double* th_override = nullptr);
+int raster_host_join(bseg_ctx* c);
+double bseg_count_channel_host(double* v, int64_t n, double bias);
 int stage_label_raster(bseg_ctx* c, const bseg_params* p, const uint16_t* h_plane_rgb, int32_t* h_label, uint8_t* h_rgb);
 
 #define STAGE_BEGIN(c, which) cudaEventRecord((c)->ev[which], (c)->stream)

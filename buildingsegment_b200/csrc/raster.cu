@@ -8,11 +8,19 @@
 // (y/bin * W + x/bin), which leaves every pixel's points in original index order; one thread per
 // OUTPUT pixel then merges the four source pixels that splat into it (taps (0,0) (1,0) (0,1) (1,1))
 // by ascending point index and adds s and s*z exactly as the reference does.  Bit-exact, no atomics
-// on doubles.  Then mean height, log(count+1)+bias (shared fdlibm log, bseg_arith.h), per-channel max
-// and the three uint8 images.
+// on doubles.  Then mean height, per-channel max and the uint8 images.
+//
+// The count channel is finalised on the HOST: log(count + 1) is std::log of the platform's libm in the reference
+// (TMC3.cpp:161), no device polynomial reproduces another libm's last bit, and a 1-ulp move can flip
+// (uint8)(255.0 * v / max).  The device produces the exact weight sums; raster_count_channel_host() takes them
+// through the same libm the reference links, on worker threads, and -- in the whole-path calls -- while the plane
+// grower runs on the GPU.  The doubles and bytes are then the reference's, bit for bit.
 //
 // Traffic: histogram R 4 B/pt; keys R 12 W 8 B/pt; sort 4 passes x 16 B/pt; accumulate gathers
 // 12 B per tap (4 taps/pt) and writes 24 B/pixel; PNG pass R 24 W 9 B/pixel.
+#include <cmath>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -76,7 +84,8 @@ struct Run {
 
 __global__ void __launch_bounds__(TPB) accumulate_kernel(const int32_t* __restrict__ xyz, const uint32_t* __restrict__ vals,
                                                          const uint32_t* __restrict__ start, int32_t W, int32_t H,
-                                                         int32_t bin, double bias, double* __restrict__ image,
+                                                         int32_t bin, double* __restrict__ image,
+                                                         double* __restrict__ counts,
                                                          unsigned long long* __restrict__ maxbits)
 {
   int64_t px = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -118,27 +127,23 @@ __global__ void __launch_bounds__(TPB) accumulate_kernel(const int32_t* __restri
       head[best] = r[best].cur < r[best].end ? vals[r[best].cur] : 0xffffffffu;
     }
     if (c1 != 0) c0 = c0 / c1;          // :152-157
-    c1 = bseg_log(c1 + 1);              // :161
-    if (c1 != 0) c1 += bias;            // :162-163
     image[3 * px] = c0;
-    image[3 * px + 1] = c1;
+    image[3 * px + 1] = c1;             // the exact weight sum: log(c1 + 1) (+ bias) is taken on the host (:161-163)
     image[3 * px + 2] = 0.0;
+    counts[px] = c1;
   }
   // per-channel maximum (values are >= 0, so the bit patterns order like the doubles)
   unsigned long long b0 = (unsigned long long)__double_as_longlong(c0 > 0 ? c0 : 0.0);
-  unsigned long long b1 = (unsigned long long)__double_as_longlong(c1 > 0 ? c1 : 0.0);
   for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long t0 = __shfl_xor_sync(FULL_MASK, b0, o), t1 = __shfl_xor_sync(FULL_MASK, b1, o);
+    unsigned long long t0 = __shfl_xor_sync(FULL_MASK, b0, o);
     b0 = t0 > b0 ? t0 : b0;
-    b1 = t1 > b1 ? t1 : b1;
   }
   if ((threadIdx.x & 31) == 0) {
     if (b0) atomicMax(&maxbits[0], b0);
-    if (b1) atomicMax(&maxbits[1], b1);
   }
 }
 
-// TMC3.cpp:93-119: three W*H*3 uint8 images
+// TMC3.cpp:93-98,112-119: images A (mean height -> byte 0) and C (always zero); image B comes from the host
 __global__ void __launch_bounds__(TPB) png_kernel(const double* __restrict__ image, int64_t npx,
                                                   const unsigned long long* __restrict__ maxbits,
                                                   uint8_t* __restrict__ a, uint8_t* __restrict__ b,
@@ -148,13 +153,86 @@ __global__ void __launch_bounds__(TPB) png_kernel(const double* __restrict__ ima
   if (px >= npx)
     return;
   const double m0 = __longlong_as_double((long long)maxbits[0]);
-  const double m1 = __longlong_as_double((long long)maxbits[1]);
-  uint8_t va = 0, vb = 0;
+  uint8_t va = 0;
   if (m0 != 0) va = (uint8_t)(255.0 * (1.0 * image[3 * px] / m0));
-  if (m1 != 0) vb = (uint8_t)(255.0 * (1.0 * image[3 * px + 1] / m1));
   a[3 * px] = va; a[3 * px + 1] = 0; a[3 * px + 2] = 0;
-  b[3 * px] = 0; b[3 * px + 1] = vb; b[3 * px + 2] = 0;
+  b[3 * px] = 0; b[3 * px + 1] = 0; b[3 * px + 2] = 0;
   cimg[3 * px] = 0; cimg[3 * px + 1] = 0; cimg[3 * px + 2] = 0;
+}
+
+// ---- host side of the count channel ------------------------------------------------------------------------------
+template <class F>
+void parallel_ranges(int64_t n, F f)
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = hw ? (int)hw : 4;
+  if (nt > 32) nt = 32;
+  if (n < 65536) nt = 1;
+  if (nt <= 1) {
+    f(0, (int64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t per = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t lo = t * per, hi = lo + per < n ? lo + per : n;
+    if (lo >= hi)
+      break;
+    th.emplace_back(f, t, lo, hi);
+  }
+  for (auto& x : th) x.join();
+}
+
+}  // namespace
+
+// v[i] = log(v[i] + 1); if (v[i] != 0) v[i] += bias   (TMC3.cpp:159-164) with the platform's std::log; returns the maximum
+double bseg_count_channel_host(double* v, int64_t n, double bias)
+{
+  double part[32];
+  for (double& x : part) x = 0.0;
+  parallel_ranges(n, [&](int t, int64_t lo, int64_t hi) {
+    double m = 0.0;
+    for (int64_t i = lo; i < hi; ++i) {
+      double x = v[i];
+      if (x != 0.0) {  // log(0 + 1) == 0 exactly and stays 0 (:162)
+        x = std::log(x + 1);
+        if (x != 0) x += bias;
+        v[i] = x;
+      }
+      if (m < x) m = x;
+    }
+    part[t] = m;
+  });
+  double m = 0.0;
+  for (double x : part)
+    if (m < x) m = x;
+  return m;
+}
+
+namespace {
+
+// everything after the device pass, on the calling thread or a worker: wait for the sums, libm log, maximum,
+// image B bytes (TMC3.cpp:101-108) and channel 1 of the caller's double image
+void raster_host_job(bseg_ctx* c, int64_t npx, double bias, double* h_image, uint8_t* h_b)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  cudaSetDevice(c->device);
+  cudaEventSynchronize(c->raster_copied);
+  double* v = c->h_cnt;
+  const double mx = bseg_count_channel_host(v, npx, bias);
+  c->raster_max1 = mx;
+  if (h_image || h_b)
+    parallel_ranges(npx, [&](int, int64_t lo, int64_t hi) {
+      for (int64_t px = lo; px < hi; ++px) {
+        if (h_image) h_image[3 * px + 1] = v[px];
+        if (h_b) {
+          h_b[3 * px] = 0;
+          h_b[3 * px + 1] = mx != 0 ? (uint8_t)(255.0 * (1.0 * v[px] / mx)) : (uint8_t)0;
+          h_b[3 * px + 2] = 0;
+        }
+      }
+    });
+  c->tm_raster_host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // namespace
@@ -174,7 +252,7 @@ int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H)
 }
 
 int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_a, uint8_t* h_b, uint8_t* h_c,
-                 double* h_th, bool device_only, const double* th_override)
+                 double* h_th, int mode, const double* th_override)
 {
   const int64_t n = c->n;
   RC_CHECK(stage_raster_size(c, p, nullptr, nullptr));
@@ -252,9 +330,10 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
   RC_CHECK(dev_ensure(c, c->counters, 192 * sizeof(uint64_t)));
   unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(dptr<uint64_t>(c->counters)) + 56;
   CU_CHECK(c, cudaMemsetAsync(maxbits, 0, 2 * sizeof(unsigned long long), c->stream));
+  RC_CHECK(dev_ensure(c, c->r_cnt, (size_t)npx * 8));
   accumulate_kernel<<<(unsigned)ceil_div64(npx, TPB), TPB, 0, c->stream>>>(
-      dptr<int32_t>(c->xyz_raw), vals, dptr<uint32_t>(c->r_pix), W, H, p->bin, p->count_bias, dptr<double>(c->r_image),
-      maxbits);
+      dptr<int32_t>(c->xyz_raw), vals, dptr<uint32_t>(c->r_pix), W, H, p->bin, dptr<double>(c->r_image),
+      dptr<double>(c->r_cnt), maxbits);
   KLAUNCH_CHECK(c);
   uint8_t* da = dptr<uint8_t>(c->r_png);
   uint8_t* db = da + 3 * npx;
@@ -263,12 +342,48 @@ int stage_raster(bseg_ctx* c, const bseg_params* p, double* h_image, uint8_t* h_
   KLAUNCH_CHECK(c);
   STAGE_END(c, EV_RASTER);
 
-  if (!device_only) {
-    if (h_image) CU_CHECK(c, cudaMemcpyAsync(h_image, c->r_image.p, (size_t)npx * 24, cudaMemcpyDeviceToHost, c->stream));
-    if (h_a) CU_CHECK(c, cudaMemcpyAsync(h_a, da, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->stream));
-    if (h_b) CU_CHECK(c, cudaMemcpyAsync(h_b, db, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->stream));
-    if (h_c) CU_CHECK(c, cudaMemcpyAsync(h_c, dc, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  // ---- the count channel: sums -> pinned host memory on the copy stream, then libm log on the host ----
+  RC_CHECK(raster_host_join(c));  // a previous job still owns h_cnt
+  if ((size_t)npx * 8 > c->h_cnt_cap) {
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    c->h_cnt = nullptr;
+    c->h_cnt_cap = 0;
+    const size_t want = (size_t)npx * 8 + (size_t)npx / 2 + 4096;
+    CU_CHECK(c, cudaMallocHost((void**)&c->h_cnt, want));
+    c->h_cnt_cap = want;
+  }
+  if (!c->copy_stream) CU_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!c->raster_copied) CU_CHECK(c, cudaEventCreateWithFlags(&c->raster_copied, cudaEventDisableTiming));
+  if (!c->raster_done) CU_CHECK(c, cudaEventCreateWithFlags(&c->raster_done, cudaEventDisableTiming));
+  CU_CHECK(c, cudaEventRecord(c->raster_done, c->stream));
+  CU_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->raster_done, 0));
+  CU_CHECK(c, cudaMemcpyAsync(c->h_cnt, c->r_cnt.p, (size_t)npx * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (h_image) CU_CHECK(c, cudaMemcpyAsync(h_image, c->r_image.p, (size_t)npx * 24, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (h_a) CU_CHECK(c, cudaMemcpyAsync(h_a, da, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (h_c) CU_CHECK(c, cudaMemcpyAsync(h_c, dc, (size_t)npx * 3, cudaMemcpyDeviceToHost, c->copy_stream));
+  CU_CHECK(c, cudaEventRecord(c->raster_copied, c->copy_stream));
+  if (mode == RASTER_DEVICE_ONLY) {
+    // bseg_raster_device: the caller finishes the count channel itself (the slabs of a tile share one maximum)
+    CU_CHECK(c, cudaEventSynchronize(c->raster_copied));
+    return 0;
+  }
+  const double bias = p->count_bias;
+  if (mode == RASTER_ASYNC) {
+    c->raster_worker = new std::thread(raster_host_job, c, npx, bias, h_image, h_b);
+    return 0;
+  }
+  raster_host_job(c, npx, bias, h_image, h_b);
+  return 0;
+}
+
+// wait for the host half of an asynchronous raster (bseg_run_device / bseg_segment_host overlap it with the grower)
+int raster_host_join(bseg_ctx* c)
+{
+  if (c->raster_worker) {
+    std::thread* t = static_cast<std::thread*>(c->raster_worker);
+    t->join();
+    delete t;
+    c->raster_worker = nullptr;
   }
   return 0;
 }

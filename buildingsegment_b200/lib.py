@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "bseg_create", "bseg_destroy", "bseg_default_params", "bseg_last_error", "bseg_version",
     "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
-    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_raster_device", "bseg_label_raster",
+    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_count_channel", "bseg_raster_device", "bseg_label_raster",
     "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
     "bseg_point_count", "bseg_plane_count", "bseg_set_owned", "bseg_set_origin", "bseg_device_results", "bseg_halo_check", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
 ]
@@ -36,7 +36,7 @@ class Params(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_float) for k in
                 ("h2d", "bbox_keys", "sort", "cells", "knn", "knn_fallback", "normals", "grow", "finalize",
-                 "raster", "d2h", "total", "grow_slice_ms", "grow_sweep_ms")] + \
+                 "raster", "d2h", "total", "grow_slice_ms", "grow_sweep_ms", "raster_host")] + \
                [(k, C.c_int64) for k in ("n_unresolved", "grow_steps", "grow_rounds", "kernel_launches",
                                          "n_big_cells", "grow_wasted_steps", "grow_sweep_iters",
                                          "grow_tiny_tx", "grow_seq_fallbacks", "grow_head_steps", "grow_head_ns",
@@ -101,6 +101,7 @@ def lib():
         L.bseg_set_origin.argtypes = [vp, vp]
         L.bseg_device_results.argtypes = [vp, vp, vp, vp]
         L.bseg_halo_check.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.bseg_count_channel.argtypes = [vp, i64, C.c_double, vp]
         L.bseg_set_grow_offset.argtypes = [vp, vp]
         L.bseg_knn_device_results.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.bseg_import_neigh_normals_device.argtypes = [vp, C.POINTER(Params), vp, vp]
@@ -118,6 +119,16 @@ def default_params(**kw) -> Params:
             raise TypeError(f"unknown parameter {k}")
         setattr(p, k, v)
     return p
+
+
+def count_channel(values: np.ndarray, bias: float) -> float:
+    """bseg_count_channel in place on a C-contiguous float64 array; returns the maximum."""
+    assert values.dtype == np.float64 and values.flags.c_contiguous
+    m = C.c_double(0.0)
+    rc = lib().bseg_count_channel(values.ctypes.data, values.size, float(bias), C.addressof(m))
+    if rc != 0:
+        raise BsegError(rc, lib().bseg_last_error(None).decode())
+    return float(m.value)
 
 
 def _ptr(a):

@@ -65,6 +65,7 @@ typedef struct bseg_params {
 typedef struct bseg_timings {
   float h2d, bbox_keys, sort, cells, knn, knn_fallback, normals, grow, finalize, raster, d2h, total;
   float grow_slice_ms, grow_sweep_ms; /* parallel engine: device time of the grower slices / of sweeper + mark log */
+  float raster_host;      /* host half of the raster's count channel (libm log, image B), wall ms; overlaps the grower */
   int64_t n_unresolved;   /* queries that needed the ring-expansion fallback */
   int64_t grow_steps;     /* Broad() calls executed (committed work)          */
   int64_t grow_rounds;    /* rounds of the speculative engine                 */
@@ -153,10 +154,16 @@ BSEG_API int bseg_raster_size(bseg_ctx* ctx, const bseg_params* p, int32_t* W, i
 BSEG_API int bseg_raster(bseg_ctx* ctx, const bseg_params* p, double* image_WxHx3, uint8_t* png_a,
                          uint8_t* png_b, uint8_t* png_c, double* ground_th);
 
+/* The host half of the count channel, for callers that hold the weight sums themselves (bseg_raster_device leaves
+ * them in channel 1): values[i] = log(values[i] + 1), plus bias when that is non-zero (TMC3.cpp:159-164), with the
+ * platform's std::log on worker threads; *max_out = the channel maximum save_image needs (TMC3.cpp:85-90). */
+BSEG_API int bseg_count_channel(double* values, int64_t n, double bias, double* max_out);
+
 /* ---- the raster of one slab of a tile (multi-GPU): same kernels as bseg_raster, but the ground
  * threshold of TMC3.cpp:181-198 comes from the caller when ground_th is not NULL (the slabs share the tile's, found
  * from the summed z histograms) and the W*H*3 doubles stay on the device (*d_image, valid until the next
- * bseg_set_points / bseg_raster*).  Point order = the cloud's order, as always: buildingsegment_b200/slabs.py
+ * bseg_set_points / bseg_raster*).  Channel 1 holds the exact weight SUMS: the caller takes them through
+ * bseg_count_channel on the host (the log is the platform libm's, as in the reference).  Point order = the cloud's order, as always: buildingsegment_b200/slabs.py
  * uploads [left halo | owned | right halo] so that it is the tile's order. */
 BSEG_API int bseg_raster_device(bseg_ctx* ctx, const bseg_params* p, const double* ground_th, const double** d_image,
                                 int32_t* W, int32_t* H);

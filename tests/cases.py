@@ -60,3 +60,22 @@ def far_offset(n=None, seed=5):
     2^31 after ~7000 points and the int32 centroid wraps."""
     p = grid_plane(150, 150, 30, tilt=0.01, offset=(300000, 0, 0), order="row", seed=seed)
     return np.ascontiguousarray(np.concatenate([np.zeros((1, 3), np.int32), p], 0))
+
+
+def count_sweep(kmax=1200, seed=11):
+    """Pixel k of a row holds exactly k points at its corner (bilinear weight 1.0 on one tap), k = 1..kmax, plus a
+    second row with fractional weights: the count channel log(count + 1) + 20 then sweeps densely through the uint8
+    truncation boundaries of save_image's (uint8)(255.0 * v / max) (TMC3.cpp:159-164, 101-108)."""
+    rng = np.random.default_rng(seed)
+    xs, ys, zs = [], [], []
+    for k in range(1, kmax + 1):
+        xs.append(np.full(k, k * 100, np.int64))
+        ys.append(np.zeros(k, np.int64))
+        zs.append(rng.integers(5000, 9000, k))
+        m = max(1, k // 3)
+        xs.append(k * 100 + rng.integers(0, 100, m))
+        ys.append(300 + rng.integers(0, 100, m))
+        zs.append(rng.integers(5000, 9000, m))
+    p = np.stack([np.concatenate(xs), np.concatenate(ys), np.concatenate(zs)], 1)
+    p = p[rng.permutation(len(p))]
+    return np.ascontiguousarray(p, np.int32)

@@ -42,6 +42,7 @@ def test_oracle_raster_matches_reference_vectors(name):
     assert np.array_equal(G.sha(img[..., 0]), g["image_ch0_sha"]) and np.array_equal(G.sha(img[..., 2]), g["image_ch2_sha"])
     if "image" in g:
         ref = g["image"]
-        assert np.all(np.abs(img[..., 1] - ref[..., 1]) <= np.spacing(ref[..., 1]))  # std::log: <= 1 ulp
+        # std::log (TMC3.cpp:161) is the platform libm's on both sides: the doubles are identical
+        assert np.array_equal(img[..., 1].view(np.int64), ref[..., 1].view(np.int64))
     a, b, c, _ = O.save_image(img)
     assert np.array_equal(a, g["png_height"]) and np.array_equal(b, g["png_count"]) and np.array_equal(c, g["png_both"])

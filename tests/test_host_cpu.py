@@ -40,6 +40,26 @@ def test_no_cpu_fallback():
     assert "no CPU path" in str(e.value)
 
 
+def test_count_channel_is_the_platform_libm():
+    """bseg_count_channel (the host half of the raster, TMC3.cpp:159-164): log(v + 1) of the platform's libm --
+    math.log calls the same function -- plus the bias when non-zero; zero stays zero; the maximum is returned."""
+    import math
+
+    from buildingsegment_b200 import lib
+
+    rng = np.random.default_rng(5)
+    v = np.concatenate([np.zeros(100), rng.random(5000) * 4, rng.integers(1, 3000, 5000).astype(np.float64),
+                        10.0 ** rng.uniform(-12, 6, 5000)])
+    want = np.array([0.0 if x == 0 else (lambda y: y + 20.0 if y != 0 else y)(math.log(x + 1)) for x in v])
+    got = v.copy()
+    m = lib.count_channel(got, 20.0)
+    assert np.array_equal(got.view(np.int64), want.view(np.int64))
+    assert m == want.max()
+    big = np.tile(v, 20)  # above the threading threshold
+    m2 = lib.count_channel(big, 20.0)
+    assert np.array_equal(big.view(np.int64), np.tile(want, 20).view(np.int64)) and m2 == m
+
+
 def test_product_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "buildingsegment_b200")
     for dirpath, _, files in os.walk(pkg):
