@@ -402,7 +402,21 @@ ORC_API int orc_raster_th(const int32_t* xyz, int64_t n, double th, int bin, dou
   return orc_raster_impl(xyz, n, th, bin, bias, W, H, image);
 }
 
+static int orc_raster_impl2(const int32_t* xyz, int64_t n, double th, int bin, double bias, int W, int H, double* image,
+                            int sums_only);
 static int orc_raster_impl(const int32_t* xyz, int64_t n, double th, int bin, double bias, int W, int H, double* image)
+{
+  return orc_raster_impl2(xyz, n, th, bin, bias, W, H, image, 0);
+}
+
+/* channel 1 left as the weight sums (before TMC3.cpp:159-164): what a slab hands to the host half of the product */
+ORC_API int orc_raster_th_sums(const int32_t* xyz, int64_t n, double th, int bin, int W, int H, double* image)
+{
+  return orc_raster_impl2(xyz, n, th, bin, 0.0, W, H, image, 1);
+}
+
+static int orc_raster_impl2(const int32_t* xyz, int64_t n, double th, int bin, double bias, int W, int H, double* image,
+                            int sums_only)
 {
   memset(image, 0, (size_t)W * H * 3 * sizeof(double));
   for (int64_t i = 0; i < n; ++i) {
@@ -423,6 +437,8 @@ static int orc_raster_impl(const int32_t* xyz, int64_t n, double th, int bin, do
   for (size_t px = 0; px < (size_t)W * H; ++px)
     if (image[3 * px + 1] != 0)
       image[3 * px] = image[3 * px] / image[3 * px + 1];
+  if (sums_only)
+    return 0;
   for (size_t px = 0; px < (size_t)W * H; ++px) {
     image[3 * px + 1] = log(image[3 * px + 1] + 1); /* the platform's libm, as the reference's std::log (TMC3.cpp:161) */
     if (image[3 * px + 1] != 0)

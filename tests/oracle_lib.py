@@ -43,6 +43,7 @@ def orc():
         L.orc_ground_th.restype = C.c_double
         L.orc_raster.argtypes = [i32p, C.c_int64, C.c_int32, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, f64p]
         L.orc_raster_th.argtypes = [i32p, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, f64p]
+        L.orc_raster_th_sums.argtypes = [i32p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int, f64p]
         L.orc_save_image.argtypes = [f64p, C.c_int, C.c_int, u8p, u8p, u8p, f64p]
         for f in ("orc_acos", "orc_cos", "orc_log"):
             getattr(L, f).argtypes = [C.c_double]
@@ -191,6 +192,14 @@ def raster_th(xyz_shifted, th, W, H, bin=100, bias=20.0):
     img = np.empty((H, W, 3), np.float64)
     orc().orc_raster_th(np.ascontiguousarray(xyz_shifted, np.int32), len(xyz_shifted), float(th), bin, bias, int(W), int(H),
                         img.reshape(-1))
+    return img
+
+
+def raster_th_sums(xyz_shifted, th, W, H, bin=100):
+    """The raster with channel 1 left as the weight sums (what bseg_raster_device leaves on the device)."""
+    img = np.empty((H, W, 3), np.float64)
+    orc().orc_raster_th_sums(np.ascontiguousarray(xyz_shifted, np.int32), len(xyz_shifted), float(th), bin, int(W), int(H),
+                             img.reshape(-1))
     return img
 
 

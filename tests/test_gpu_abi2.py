@@ -169,37 +169,48 @@ def test_halo_check_origin_owned_device_results(ctx):
     full = cases.block(150000)
     origin = full.min(axis=0).astype(np.int32)
     x = full[:, 0]
-    x_lo, x_hi, halo = int(origin[0]) + 12000, int(origin[0]) + 26000, 400
+    x_lo, x_hi = int(origin[0]) + 12000, int(origin[0]) + 26000
     own = (x >= x_lo) & (x < x_hi)
-    hal = ~own & (x >= x_lo - halo) & (x < x_hi + halo)
-    local = np.ascontiguousarray(np.concatenate([full[own], full[hal]]))
     n_owned = int(own.sum())
     p = lib.default_params()
     ctx.set_origin(origin)
     try:
-        mn, mx, xs = ctx.set_points(local)
-        assert np.array_equal(mn, origin)                                   # the shared origin was subtracted ...
-        assert np.array_equal(xs, local - origin[None, :])                  # ... from every point
-        ctx.set_owned(n_owned)
-        neigh, nrm, _ = ctx.knn_normals(p)
-        last = neigh[:, -1]
-        d = xs[np.clip(last, 0, len(xs) - 1)].astype(np.int64) - xs.astype(np.int64)
-        d2k = (d * d).sum(axis=1)
-        owned_mask = np.arange(len(local)) < n_owned
-        lo_s, hi_s = x_lo - int(origin[0]), x_hi - int(origin[0])
-        for h in (50, 150, 400, 3000):
-            got = ctx.halo_check(lo_s, hi_s, h)
-            assert got == _halo_rule(xs, neigh, d2k, owned_mask, lo_s, hi_s, h, True, True), h
-            # outer faces (no neighbour rank): only the other face is checked; both outer = nothing to check
-            assert ctx.halo_check(-2**31, hi_s, h) == _halo_rule(xs, neigh, d2k, owned_mask, lo_s, hi_s, h, False, True)
-            assert ctx.halo_check(lo_s, 2**31 - 1, h) == _halo_rule(xs, neigh, d2k, owned_mask, lo_s, hi_s, h, True, False)
-            assert ctx.halo_check(-2**31, 2**31 - 1, h) == 0
-        assert ctx.halo_check(lo_s, hi_s, 50) > 0 and ctx.halo_check(lo_s, hi_s, halo) == 0
+        halo = 200
+        while True:  # as slabs.segment_tile does: double the halo until the check passes (sparse clutter needs metres)
+            hal = ~own & (x >= x_lo - halo) & (x < x_hi + halo)
+            idx_full = np.nonzero(own | hal)[0]  # global-index order: the tie order of the rows is the cloud's
+            local = np.ascontiguousarray(full[idx_full])
+            mn, mx, xs = ctx.set_points(local)
+            assert np.array_equal(mn, origin)                                   # the shared origin was subtracted ...
+            assert np.array_equal(xs, local - origin[None, :])                  # ... from every point
+            neigh, nrm, _ = ctx.knn_normals(p)
+            last = neigh[:, -1]
+            d = xs[np.clip(last, 0, len(xs) - 1)].astype(np.int64) - xs.astype(np.int64)
+            d2k = (d * d).sum(axis=1)
+            owned_mask = own[idx_full]
+            lo_s, hi_s = x_lo - int(origin[0]), x_hi - int(origin[0])
+            for h in (50, 150, halo, 10 * halo):
+                got = ctx.halo_check(lo_s, hi_s, h)
+                assert got == _halo_rule(xs, neigh, d2k, owned_mask, lo_s, hi_s, h, True, True), h
+                # outer faces (no neighbour rank): only the other face is checked; both outer = nothing to check
+                assert ctx.halo_check(-2**31, hi_s, h) == _halo_rule(xs, neigh, d2k, owned_mask, lo_s, hi_s, h, False, True)
+                assert ctx.halo_check(lo_s, 2**31 - 1, h) == _halo_rule(xs, neigh, d2k, owned_mask, lo_s, hi_s, h, True, False)
+                assert ctx.halo_check(-2**31, 2**31 - 1, h) == 0
+            # bseg_set_owned: indices at or above n_owned are halo copies whatever their position
+            k = len(local) // 3
+            ctx.set_owned(k)
+            assert ctx.halo_check(lo_s, hi_s, 50) == _halo_rule(xs, neigh, d2k, owned_mask & (np.arange(len(local)) < k),
+                                                                lo_s, hi_s, 50, True, True)
+            ctx.set_owned(len(local))
+            if ctx.halo_check(lo_s, hi_s, halo) == 0:
+                break
+            assert halo < 50000
+            halo *= 2
+        assert halo > 200  # the first width was NOT sufficient: the loop was exercised
         # with the halo sufficient, owned rows / normals are the undivided cloud's
         Pf = O.pipeline(full)
-        idx_full = np.concatenate([np.nonzero(own)[0], np.nonzero(hal)[0]])
-        assert np.array_equal(idx_full[neigh[:n_owned]], Pf["neigh"][own])
-        assert np.array_equal(nrm[:n_owned].view(np.int64), Pf["normals"][own].view(np.int64))
+        assert np.array_equal(idx_full[neigh[owned_mask]], Pf["neigh"][own])
+        assert np.array_equal(nrm[owned_mask].view(np.int64), Pf["normals"][own].view(np.int64))
         # device result pointers
         pidx, label, npl = ctx.grow_planes(p)
         d_label, d_pidx, d_xyz = ctx.device_results()
