@@ -74,6 +74,7 @@ BSEG_API int bseg_default_params(bseg_params* p)
   p->count_bias = 20.0;
   p->cell = 0;
   p->grow_mode = 0;
+  p->grow_radius = 0.0;
   return 0;
 }
 
@@ -132,7 +133,7 @@ BSEG_API void bseg_destroy(bseg_ctx* c)
                    &c->scan_tmp, &c->pts, &c->inv, &c->flags, &c->cell_key, &c->cell_start, &c->hash_keys,
                    &c->hash_vals, &c->cell_key2, &c->cell_start2, &c->hash_keys2, &c->hash_vals2, &c->nbr, &c->nrm, &c->curv, &c->worklist, &c->counters, &c->out_tmp, &c->x_neigh, &c->x_normals,
                    &c->g_state, &c->g_res, &c->g_spec, &c->g_pool, &c->g_planes, &c->g_tx, &c->g_queue, &c->g_rowdup, &c->g_marklog,
-                   &c->g_stack, &c->g_label, &c->g_pidx, &c->g_pts_raw, &c->r_hist, &c->r_image, &c->r_png, &c->r_pix, &c->r_cnt};
+                   &c->g_stack, &c->g_label, &c->g_pidx, &c->g_pts_raw, &c->g_nbr_masked, &c->r_hist, &c->r_image, &c->r_png, &c->r_pix, &c->r_cnt};
   for (DevBuf* b : all)
     dev_free(*b);
   for (int i = 0; i < EV_COUNT; ++i) {
@@ -273,6 +274,8 @@ static int check_params(bseg_ctx* c, const bseg_params* p)
     return bseg_fail(c, BSEG_E_ARG, "cell = %d must be 0 (auto) or in [radius, %d]", p->cell, BSEG_MAX_CELL);
   if (p->bin < 1 || p->bin_height < 1)
     return bseg_fail(c, BSEG_E_ARG, "bin / bin_height must be positive");
+  if (!(p->grow_radius >= 0.0) || p->grow_radius > 3.0e4)
+    return bseg_fail(c, BSEG_E_ARG, "grow_radius = %g outside [0, 30000]", p->grow_radius);
   if (p->th_thickness < 0 || p->th_point_count < 0)
     return bseg_fail(c, BSEG_E_ARG, "negative threshold");
   return 0;

@@ -118,6 +118,7 @@ struct bseg_ctx {
   DevBuf g_label;     // int32 [n] label in original order
   DevBuf g_pidx;      // int32 [n] planeIdx in original order
   DevBuf g_pts_raw;   // int4 [n]: pts + grow_off (only when an offset is set)
+  DevBuf g_nbr_masked;  // int32 [n][K]: rows cut at grow_radius (only when the radius-search variant is on)
   // raster
   DevBuf r_hist;
   DevBuf r_image;     // double [W*H*3]

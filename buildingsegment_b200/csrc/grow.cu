@@ -166,6 +166,25 @@ __global__ void offset_pts_kernel(const int4* __restrict__ pts, int64_t n, int32
   out[s] = p;
 }
 
+// "radius-search growing" (bseg_params.grow_radius): the grower's list of a point = the entries of its K-row with
+// d^2 < r^2 (column 0 is kept whatever it is: Broad skips it blindly, my_function.cpp:224); the rest do not exist
+__global__ void mask_rows_kernel(const int32_t* __restrict__ nbr, const int4* __restrict__ pts, int64_t n, int K,
+                                 unsigned long long r2, int32_t* __restrict__ out)
+{
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * K)
+    return;
+  const int64_t s = e / K;
+  const int j = (int)(e - s * K);
+  int32_t id = nbr[e];
+  if (j > 0 && id >= 0) {
+    const int4 a = __ldg(pts + s), b = __ldg(pts + id);
+    const long long dx = (long long)a.x - b.x, dy = (long long)a.y - b.y, dz = (long long)a.z - b.z;
+    if ((unsigned long long)(dx * dx + dy * dy + dz * dz) >= r2) id = -1;
+  }
+  out[e] = id;
+}
+
 // ---- finalize: plane ids, planeIdx and label in original order ------------------------------------------
 // id(owner) = 1 + #plane seeds < owner; label = id when the owner IS a plane seed, else the id of the
 // plane seeded at the point itself (a seed is in its own pointIdx without being marked), else 0.
@@ -340,6 +359,16 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.rowdup = dptr<uint8_t>(c->g_rowdup);
 
   STAGE_BEGIN(c, EV_GROW);
+  if (p->grow_radius > 0.0) {
+    RC_CHECK(dev_ensure(c, c->g_nbr_masked, (size_t)n * p->K * 4));
+    const double r2d = p->grow_radius * p->grow_radius;
+    unsigned long long r2 = (unsigned long long)r2d;
+    if ((double)r2 < r2d) ++r2;  // d2 < r2  <=>  d2 < ceil(r2) for integer d2
+    mask_rows_kernel<<<(unsigned)ceil_div64(n * p->K, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->nbr), dptr<int4>(c->pts), n, p->K,
+                                                                              r2, dptr<int32_t>(c->g_nbr_masked));
+    KLAUNCH_CHECK(c);
+    A.nbr = dptr<int32_t>(c->g_nbr_masked);
+  }
   if (c->grow_off[0] | c->grow_off[1] | c->grow_off[2]) {
     RC_CHECK(dev_ensure(c, c->g_pts_raw, (size_t)n * 16));
     offset_pts_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<int4>(c->pts), n, c->grow_off[0], c->grow_off[1],

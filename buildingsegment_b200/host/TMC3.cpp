@@ -2,8 +2,6 @@
 // struct Box, class buildingSeg (constructor, compute_gird_picture, save_image, pixel, groundTH)
 // and main.  Same CLI: `tmc3 -a=<in.ply> -s=<out.ply>` (flag names ignored, readme.txt:12).
 // Every computation runs on the GPU through libbseg's C ABI; this file only marshals.
-#include <zlib.h>
-
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -19,49 +17,12 @@ struct Box {
 
 namespace {
 
-// minimal PNG writer (8-bit RGB, zlib deflate): the reference hands the same pixel buffers to
-// stbi_write_png (TMC3.cpp:98,108,119); the decoded images are identical, the file bytes need not be
-void put32(std::vector<uint8_t>& v, uint32_t x)
+// The reference hands the three byte images to stbi_write_png (TMC3.cpp:98,108,119).  libbseg's writer produces
+// the same bytes (include/bseg.h bseg_png_*) and encodes on worker threads: save_image returns once the pixels are
+// copied, the files are complete after bseg_png_wait() (end of main), off the segmentation's critical path.
+void write_png_rgb(const std::string& path, int w, int h, const uint8_t* rgb, int stride)
 {
-  for (int s = 24; s >= 0; s -= 8) v.push_back(uint8_t(x >> s));
-}
-
-void chunk(std::vector<uint8_t>& out, const char tag[4], const std::vector<uint8_t>& data)
-{
-  put32(out, uint32_t(data.size()));
-  std::vector<uint8_t> body(tag, tag + 4);
-  body.insert(body.end(), data.begin(), data.end());
-  out.insert(out.end(), body.begin(), body.end());
-  put32(out, uint32_t(crc32(0L, body.data(), uInt(body.size()))));
-}
-
-bool write_png_rgb(const std::string& path, int w, int h, const uint8_t* rgb, int stride)
-{
-  std::vector<uint8_t> raw;
-  raw.reserve(size_t(h) * (size_t(w) * 3 + 1));
-  for (int y = 0; y < h; ++y) {
-    raw.push_back(0);  // filter: none
-    raw.insert(raw.end(), rgb + size_t(y) * stride, rgb + size_t(y) * stride + size_t(w) * 3);
-  }
-  uLongf clen = compressBound(uLong(raw.size()));
-  std::vector<uint8_t> comp(clen);
-  if (compress2(comp.data(), &clen, raw.data(), uLong(raw.size()), 6) != Z_OK)
-    return false;
-  comp.resize(clen);
-  std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-  std::vector<uint8_t> ihdr;
-  put32(ihdr, uint32_t(w));
-  put32(ihdr, uint32_t(h));
-  const uint8_t tail[5] = {8, 2, 0, 0, 0};  // 8 bit, colour type 2 (RGB)
-  ihdr.insert(ihdr.end(), tail, tail + 5);
-  chunk(out, "IHDR", ihdr);
-  chunk(out, "IDAT", comp);
-  chunk(out, "IEND", {});
-  FILE* f = std::fopen(path.c_str(), "wb");
-  if (!f)
-    return false;
-  const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
-  return (std::fclose(f) == 0) && ok;
+  bseg_host::check(bseg_png_write_async(path.c_str(), rgb, w, h, 3, stride), "bseg_png_write_async");
 }
 
 }  // namespace
@@ -190,6 +151,7 @@ int main(int argc, char* argv[])
         seg.compute_gird_picture();
         seg.save_image(std::string(argv[a] + 9));
       }
+    bseg_host::check(bseg_png_wait(), "bseg_png_wait");  // the images encoded on worker threads are on disk now
     std::cout << "tmc3: " << pointCloud.getPointCount() << " points, " << plances.size() << " planes -> "
               << path.savePath << std::endl;
   } catch (const std::exception& e) {

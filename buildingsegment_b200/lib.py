@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "bseg_create", "bseg_destroy", "bseg_default_params", "bseg_last_error", "bseg_version",
     "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
-    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_count_channel", "bseg_raster_device", "bseg_label_raster",
+    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_count_channel", "bseg_png_encode", "bseg_png_write", "bseg_png_write_async", "bseg_png_wait", "bseg_raster_device", "bseg_label_raster",
     "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
     "bseg_point_count", "bseg_plane_count", "bseg_set_owned", "bseg_set_origin", "bseg_device_results", "bseg_halo_check", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
 ]
@@ -29,7 +29,7 @@ class Params(C.Structure):
         ("K", C.c_int32), ("max_nn", C.c_int32), ("radius", C.c_double),
         ("th_thickness", C.c_int32), ("th_point_count", C.c_int32), ("th_dot", C.c_double),
         ("bin", C.c_int32), ("bin_height", C.c_int32), ("count_bias", C.c_double),
-        ("cell", C.c_int32), ("grow_mode", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("cell", C.c_int32), ("grow_mode", C.c_int32), ("grow_radius", C.c_double), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -102,6 +102,10 @@ def lib():
         L.bseg_device_results.argtypes = [vp, vp, vp, vp]
         L.bseg_halo_check.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
         L.bseg_count_channel.argtypes = [vp, i64, C.c_double, vp]
+        L.bseg_png_encode.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp]
+        L.bseg_png_write.argtypes = [C.c_char_p, vp, i32, i32, i32, i32]
+        L.bseg_png_write_async.argtypes = [C.c_char_p, vp, i32, i32, i32, i32]
+        L.bseg_png_wait.argtypes = []
         L.bseg_set_grow_offset.argtypes = [vp, vp]
         L.bseg_knn_device_results.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.bseg_import_neigh_normals_device.argtypes = [vp, C.POINTER(Params), vp, vp]
@@ -129,6 +133,22 @@ def count_channel(values: np.ndarray, bias: float) -> float:
     if rc != 0:
         raise BsegError(rc, lib().bseg_last_error(None).decode())
     return float(m.value)
+
+
+def png_encode(img: np.ndarray) -> bytes:
+    """bseg_png_encode of a uint8 [H][W][comp] (or [H][W]) image: the bytes stbi_write_png would write."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    comp = 1 if img.ndim == 2 else img.shape[2]
+    n = C.c_int64(0)
+    rc = lib().bseg_png_encode(img.ctypes.data, w, h, comp, 0, None, 0, C.addressof(n))
+    if rc != 0:
+        raise BsegError(rc, lib().bseg_last_error(None).decode())
+    out = np.empty(n.value, np.uint8)
+    rc = lib().bseg_png_encode(img.ctypes.data, w, h, comp, 0, out.ctypes.data, out.size, C.addressof(n))
+    if rc != 0:
+        raise BsegError(rc, lib().bseg_last_error(None).decode())
+    return out.tobytes()
 
 
 def _ptr(a):

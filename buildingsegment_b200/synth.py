@@ -167,42 +167,84 @@ def aerial_tile(n=50_000_000, seed=1003, size=1000.0):
     return to_mm(q)
 
 
-def voxel_scan(n=100_000_000, seed=1004, bits=10):
-    """C4: dense building scan voxelised to a 2^bits lattice (unique voxels, 3-voxel shells).
-
-    Coordinates are already integers (voxel units, scale 1); returned in Morton-ish raster order.
-    """
+def _voxel_block(seed, n, bits, ox, oy):
+    """One scanned building voxelised to a 2^bits lattice: unique voxels of 3-voxel-thick shells (walls, roof, floor)."""
     rng = np.random.default_rng(seed)
     side = float(2 ** bits)
-    patches = _building_patches(side / 2, side / 2, 0.1 * side, 0.7 * side, 0.45 * side, 0.35 * side, 30.0, 20.0)
+    patches = _building_patches(side / 2, side / 2, 0.1 * side, rng.uniform(0.6, 0.75) * side, rng.uniform(0.4, 0.5) * side,
+                                rng.uniform(0.3, 0.4) * side, rng.uniform(20.0, 40.0), rng.uniform(0.0, 90.0))
     patches.append((np.array([0.0, 0.0, 0.1 * side]), np.array([side - 1, 0, 0.0]), np.array([0, side - 1, 0.0]), False,
                     side * side))
-    out = np.zeros((0, 3), dtype=np.int32)
-    want = n
-    while len(out) < n:
-        pts = _sample_patches(rng, patches, int(want * 1.6) + 1000, 1.0)
-        v = np.clip(np.round(pts), 0, side - 1).astype(np.int32)
-        out = np.unique(np.concatenate([out, v], axis=0), axis=0)
-        want = n - len(out)
-        if want <= 0 or len(out) > 0.95 * sum(p[4] for p in patches) * 3:
+    cap = int(0.9 * 3 * sum(p[4] for p in patches))  # what 3-voxel shells of these surfaces can hold
+    want = min(n, cap)
+    keys = np.zeros(0, np.int64)
+    for _ in range(12):
+        need = want - len(keys)
+        if need <= 0:
             break
-    out = out[:n]
-    key = np.lexsort((out[:, 0], out[:, 1], out[:, 2]))
-    return np.ascontiguousarray(out[key])
+        pts = _sample_patches(rng, patches, int(need * 1.7) + 1000, 1.0)
+        v = np.clip(np.round(pts), 0, side - 1).astype(np.int64)
+        k = (v[:, 2] << (2 * bits)) | (v[:, 1] << bits) | v[:, 0]  # z-major raster order
+        keys = np.unique(np.concatenate([keys, k]))
+    if len(keys) > want:
+        keys = np.sort(rng.choice(keys, want, replace=False))
+    mask = (1 << bits) - 1
+    out = np.stack([(keys & mask) + ox, ((keys >> bits) & mask) + oy, keys >> (2 * bits)], axis=1)
+    return np.ascontiguousarray(out, np.int32)
 
 
-def city_tile(n=200_000_000, seed=1005, blocks_per_side=4, block=500.0):
-    """C5: city tile = blocks_per_side^2 suburban blocks, block-major, shuffled inside a block."""
-    rng = np.random.default_rng(seed)
+def voxel_scan(n=100_000_000, seed=1004, bits=10, workers=1):
+    """C4: dense building scans voxelised to 2^bits integer lattices (unique voxels, 3-voxel shells), one scan per
+    block, blocks side by side (block-major, raster order inside a block).  Coordinates are voxel units (scale 1)."""
+    side = 2 ** bits
+    per_block = int(0.9 * 3 * 2.2 * side * side)  # ~ what one block can hold (see _voxel_block)
+    nb = max(1, -(-n // per_block))
+    g = int(np.ceil(np.sqrt(nb)))
+    counts = [n // nb + (1 if b < n % nb else 0) for b in range(nb)]
+    jobs = [(seed + 1000 * b, counts[b], bits, (b % g) * side, (b // g) * side) for b in range(nb)]
+    return np.concatenate(_map(_voxel_block_job, jobs, workers), axis=0)
+
+
+def _voxel_block_job(a):
+    return _voxel_block(*a)
+
+
+def _map(fn, jobs, workers):
+    """Blocks are independent (own seed each): generate them on `workers` processes.  fork()s -- call before CUDA is
+    initialised in this process."""
+    if workers <= 1 or len(jobs) <= 1:
+        return [fn(j) for j in jobs]
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+        return pool.map(fn, jobs, chunksize=1)
+
+
+def city_block(b, n_block, seed=1005, blocks_per_side=4, block=500.0):
+    """Block b of the C5 tile (own seed: the tile does not depend on who generates which block)."""
+    rng = np.random.default_rng(seed + 1000 * b)
+    bx, by = b % blocks_per_side, b // blocks_per_side
+    nbld = max(4, int(40 * (block / 200.0) ** 2))
+    return to_mm(_block(rng, n_block, bx * block, by * block, block, nbld, 0.15, "shuffled"))
+
+
+def _city_block_job(a):
+    return city_block(*a)
+
+
+def city_tile_counts(n, blocks_per_side=4):
     nb = blocks_per_side * blocks_per_side
     per = n // nb
-    chunks = []
-    for b in range(nb):
-        bx, by = b % blocks_per_side, b // blocks_per_side
-        k = per if b < nb - 1 else n - per * (nb - 1)
-        nbld = max(4, int(40 * (block / 200.0) ** 2))
-        chunks.append(to_mm(_block(rng, k, bx * block, by * block, block, nbld, 0.15, "shuffled")))
-    return np.concatenate(chunks, axis=0)
+    return [per if b < nb - 1 else n - per * (nb - 1) for b in range(nb)]
+
+
+def city_tile(n=200_000_000, seed=1005, blocks_per_side=4, block=500.0, blocks=None, workers=1):
+    """C5: city tile = blocks_per_side^2 suburban blocks, block-major, shuffled inside a block.  `blocks` selects a
+    contiguous run of blocks (a rank's chunk of the tile: the tile's index order is block-major)."""
+    counts = city_tile_counts(n, blocks_per_side)
+    sel = range(len(counts)) if blocks is None else blocks
+    jobs = [(b, counts[b], seed, blocks_per_side, block) for b in sel]
+    return np.concatenate(_map(_city_block_job, jobs, workers), axis=0)
 
 
 CONFIGS = {

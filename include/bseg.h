@@ -58,7 +58,11 @@ typedef struct bseg_params {
   double count_bias;      /* 20.0  added to log(count+1) when non-zero TMC3.cpp:163            */
   int32_t cell;           /* 0 = auto: kNN grid cell edge, >= ceil(radius)                      */
   int32_t grow_mode;      /* 0 = speculative parallel engine, 1 = single-warp sequential engine */
-  int32_t reserved[5];
+  double grow_radius;     /* 0 = off (the reference).  > 0: "radius-search growing" (BASELINE config C2): the grower's
+                             neighbour list of a point is the prefix of its K-row with d^2 < grow_radius^2 -- entries
+                             beyond the radius do not exist (they are never accepted, Broad at depth 0 still wants
+                             all K-1, my_function.cpp:238).  Rows exported by bseg_knn_normals stay the full kNN rows. */
+  int32_t reserved[3];
 } bseg_params;
 
 /* Per-stage device time of the last call, milliseconds (CUDA events on the context's stream). */
@@ -158,6 +162,19 @@ BSEG_API int bseg_raster(bseg_ctx* ctx, const bseg_params* p, double* image_WxHx
  * them in channel 1): values[i] = log(values[i] + 1), plus bias when that is non-zero (TMC3.cpp:159-164), with the
  * platform's std::log on worker threads; *max_out = the channel maximum save_image needs (TMC3.cpp:85-90). */
 BSEG_API int bseg_count_channel(double* values, int64_t n, double bias, double* max_out);
+
+/* ---- the PNG files of save_image (TMC3.cpp:98,108,119 call stbi_write_png, stb_image_write.h:1215) --------------
+ * Host-only.  The file is BYTE-identical to what stbi_write_png of the reference's vendored stb_image_write v1.16
+ * writes with its default settings (per-row filter choice, its own deflate at level 8): comp = bytes per pixel (1..4),
+ * stride_bytes = 0 means w * comp.  bseg_png_encode returns the length in *len (out may be NULL to size the buffer).
+ * bseg_png_write_async copies the pixels and encodes on a worker thread -- the three images of save_image are
+ * encoded concurrently and off the caller's critical path; bseg_png_wait joins every pending write. */
+BSEG_API int bseg_png_encode(const uint8_t* pixels, int32_t w, int32_t h, int32_t comp, int32_t stride_bytes, uint8_t* out,
+                             int64_t cap, int64_t* len);
+BSEG_API int bseg_png_write(const char* path, const uint8_t* pixels, int32_t w, int32_t h, int32_t comp, int32_t stride_bytes);
+BSEG_API int bseg_png_write_async(const char* path, const uint8_t* pixels, int32_t w, int32_t h, int32_t comp,
+                                  int32_t stride_bytes);
+BSEG_API int bseg_png_wait(void);
 
 /* ---- the raster of one slab of a tile (multi-GPU): same kernels as bseg_raster, but the ground
  * threshold of TMC3.cpp:181-198 comes from the caller when ground_th is not NULL (the slabs share the tile's, found

@@ -68,13 +68,15 @@ def ref():
                                C.c_int64, C.c_int64, u16p]
         L.ref_grow.restype = C.c_int64
         L.ref_raster.argtypes = [i32p, C.c_int64, i32p, f64p, C.c_int64, C.c_char_p]
+        L.ref_png_encode.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int64]
+        L.ref_png_encode.restype = C.c_int64
         _REF = L
     return _REF
 
 
 # ---------------------------------------------------------------------------------------------
 DEFAULTS = dict(K=15, radius=100.0, max_nn=50, th_thickness=300, th_point_count=400, th_dot=0.88,
-                bin=100, bin_height=1000, count_bias=20.0)
+                bin=100, bin_height=1000, count_bias=20.0, grow_radius=0.0)
 
 
 def bbox_shift(xyz, bin=100):
@@ -227,6 +229,18 @@ def ref_raster(xyz_unshifted, out_dir=None):
     return xyz, int(wh[0]), int(wh[1]), img.reshape(int(wh[1]), int(wh[0]), 3)
 
 
+def ref_png(img):
+    """stbi_write_png_to_mem of the reference's vendored stb on a uint8 [H][W][comp] image."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    comp = 1 if img.ndim == 2 else img.shape[2]
+    cap = img.size * 2 + 4096
+    out = np.empty(cap, np.uint8)
+    n = ref().ref_png_encode(img.reshape(-1), w, h, comp, 0, out, cap)
+    assert n > 0, n
+    return out[:n].tobytes()
+
+
 def pipeline(xyz_unshifted, **kw):
     """Whole reference path on the CPU oracle: shift -> kNN -> normals -> grow.  Returns a dict."""
     p = dict(DEFAULTS)
@@ -236,7 +250,12 @@ def pipeline(xyz_unshifted, **kw):
     idx, d2 = knn(xyz, kq, cell=max(1, int(p["radius"])))
     nrm, curv, nh = normals(xyz, idx, d2, p["radius"], p["max_nn"])
     neigh = np.ascontiguousarray(idx[:, : p["K"]])
-    g = grow(xyz, nrm, neigh, p["K"], p["th_thickness"], p["th_point_count"], p["th_dot"])
+    grow_rows = neigh
+    if p["grow_radius"] > 0:  # "radius-search growing" (BASELINE config C2): entries beyond the radius do not exist
+        cut = (d2[:, : p["K"]].astype(np.float64) >= p["grow_radius"] ** 2)
+        cut[:, 0] = False
+        grow_rows = np.ascontiguousarray(np.where(cut, -1, neigh).astype(np.int32))
+    g = grow(xyz, nrm, grow_rows, p["K"], p["th_thickness"], p["th_point_count"], p["th_dot"])
     return dict(xyz=xyz, mn=mn, mx=mx, wh=wh, knn=idx, d2=d2, normals=nrm, curvature=curv, n_hyb=nh, neigh=neigh, grow=g)
 
 

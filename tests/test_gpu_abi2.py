@@ -242,3 +242,28 @@ def test_kernel_attributes_on_a_second_context():
         _, label, npl = c.grow_planes(p)
         assert npl == P["grow"].n_planes and np.array_equal(label, P["grow"].label)
         c.close()
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("case,kw,r", [("block", dict(n=150000), 260.0), ("building", dict(n=80000), 150.0)])
+def test_radius_search_growing(ctx, case, kw, r, mode):
+    """BASELINE config C2's variant (bseg_params.grow_radius): the grower's neighbour list is the part of the K-row
+    inside the radius; the exported rows stay the full kNN rows."""
+    from buildingsegment_b200 import lib
+
+    xyz = getattr(cases, case)(**kw)
+    P = O.pipeline(xyz, grow_radius=r)
+    P0 = O.pipeline(xyz)
+    assert not np.array_equal(P["grow"].plane_idx, P0["grow"].plane_idx)  # the variant changes the result here
+    p = lib.default_params(grow_mode=mode, grow_radius=r)
+    ctx.set_points(xyz)
+    neigh, nrm, _ = ctx.knn_normals(p)
+    assert np.array_equal(neigh, P0["neigh"])
+    g = P["grow"]
+    pidx, label, npl = ctx.grow_planes(p)
+    assert npl == g.n_planes and np.array_equal(pidx, g.plane_idx) and np.array_equal(label, g.label)
+    seeds, normals, centers, off, idx = ctx.get_planes(npl)
+    assert np.array_equal(idx, g.point_idx) and np.array_equal(normals.view(np.int64), g.plane_normal.view(np.int64))
+    # and back to the reference's rows with the radius off
+    pidx, label, npl = ctx.grow_planes(lib.default_params(grow_mode=mode))
+    assert npl == P0["grow"].n_planes and np.array_equal(pidx, P0["grow"].plane_idx)
