@@ -20,7 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="nccl")
     ap.add_argument("--case", default="block")
-    ap.add_argument("--n", type=int, default=200000)
+    ap.add_argument("--points", dest="n", type=int, default=200000)
     ap.add_argument("--halo", type=int, default=400)
     ap.add_argument("--out", required=True)
     a = ap.parse_args()

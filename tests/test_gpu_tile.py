@@ -31,7 +31,7 @@ def _free_port():
 def _launch(world, backend, case, n, halo, out):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(HERE, "gpu_tile_worker.py"), "--backend", backend, "--case", case,
-           "--n", str(n), "--halo", str(halo), "--out", str(out)]
+           "--points", str(n), "--halo", str(halo), "--out", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return [np.load(os.path.join(out, f"r{k}.npz")) for k in range(world)]
