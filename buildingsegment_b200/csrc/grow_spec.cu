@@ -39,12 +39,17 @@ namespace {
 
 constexpr int TPB = 256;
 constexpr int GW = 4;          // warps per block in slot kernels
-constexpr int SWEEP_T = 1024;  // seeds per sweeper batch == threads of the sweeper block
+constexpr int SWEEP_T = 512;   // seeds per sweeper batch == threads of the sweeper block (128 registers each: ids and reservations stay in registers)
 constexpr int SWEEP_WORDS = 128;  // bitmap words (4096 seeds) scanned per batch for up to SWEEP_T live seeds
-constexpr int PT_CACHE = 256;      // sweeper: cached page-table entries of the slot being committed
-constexpr int HT = 16384;      // sweeper hash table slots (keys + vals = 128 KB of shared memory)
 
-enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING = 4, ST_DONE = 5 };  // DONE: committed by the sweeper, slot and pages still to be returned
+constexpr int PEND_CAP = 64;       // assumed-taken points of a finished slot that were still free when it was verified
+constexpr int CSET_BITS = 11, CSET = 1 << CSET_BITS;  // sweeper: hash set of the seeds whose planes this sweep committed (<= G of them)
+constexpr int GSET_BITS = 11, GSET = 1 << GSET_BITS;  // sweeper: seeds of the grower-looking threads of a segment (<= SWEEP_T of them)
+constexpr int DSET_BITS = 10, DSET = 1 << DSET_BITS;  // sweeper: seeds it doomed during this sweep
+
+// DONE: slot and pages still to be returned; COMMIT: the sweeper accepted the plane, its list is still in the slot
+// (spec_apply_commits_kernel copies it out); ROLLED: rolled back at its turn, the reservations are still to be dropped
+enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING = 4, ST_DONE = 5, ST_COMMIT = 6, ST_ROLLED = 7 };
 // spec control block (A.ctl + 8)
 enum {
   SC_NFREE = 0,       // free slots
@@ -63,6 +68,8 @@ enum {
   SC_SWEEP_NS = 13,   // time inside the sweeper
   SC_ATFAIL = 14,     // finished slots whose assumed-taken points were not all taken
   SC_NLOG = 19,       // entries of the mark log
+  SC_N_SER = 22,      // serial stretches of the sweeper
+  SC_N_GROW = 23,     // growers the sweeper decided
   SC_HEAD_ITERS = 21, // warp iterations of the head slot (two-node engine: <= steps)
   SC_POOL0 = 20,      // pool fill at the start of the sweep (planes committed since: [SC_POOL0, CTL_POOL))
   SC_SKIP_DBG = 24,   // [24, 29): head skip batches, cycles in enumerate / row+state / geometry, pairs tested
@@ -82,7 +89,10 @@ struct Slot {
   int32_t status;
   int32_t started;   // 0 = tx_begin still to be done
   int32_t n_pages;   // pages of the pool this slot owns
+  int32_t n_pend;    // verified slots: assumed-taken points that were still free then (first PEND_CAP in S.pend)
+  int32_t verified;  // spec_preverify_kernel has checked the list of this finished slot
   int32_t pad;
+  int64_t pool_off;  // ST_COMMIT: where the list goes in the committed pool
   unsigned long long steps;
   TxState t;
 };
@@ -99,6 +109,7 @@ struct SpecArgs {
   uint32_t* free_ids;
   uint8_t* hinted;    // [n] original index space: this tiny transaction has published hints
   uint32_t* alive;    // [ceil(n/32)] original index space: bit = the point may still be free (filter)
+  int32_t* pend;      // [G][PEND_CAP] see Slot::n_pend
   uint2* marklog;     // (point, seed) of the orphan marks the sweeper made this round: side effects applied later
   unsigned long long marklog_cap;
   unsigned long long* sc;
@@ -174,9 +185,14 @@ __global__ void __launch_bounds__(TPB) spec_mark_release_kernel(SpecArgs S)
   if (g >= S.G)
     return;
   Slot& sl = S.slots[g];
-  if (sl.status == ST_FREE || sl.status == ST_DONE)
+  if (sl.status == ST_FREE || sl.status == ST_DONE || sl.status == ST_ROLLED)
     return;
+  if (sl.status == ST_COMMIT) {  // its list has been copied out by spec_apply_commits_kernel
+    sl.status = ST_DONE;
+    return;
+  }
   if (sl.status == ST_DEAD || S.A.doom[sl.seed_i]) sl.status = ST_RELEASING;
+  else if (sl.status == ST_FINISHED) sl.n_pend = 0;  // recounted by this round's spec_preverify_kernel
 }
 
 __global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
@@ -184,7 +200,7 @@ __global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
   const GrowArgs& A = S.A;
   const int g = blockIdx.y;
   const Slot& sl = S.slots[g];
-  if (sl.status != ST_RELEASING)
+  if (sl.status != ST_RELEASING && sl.status != ST_ROLLED)  // ROLLED: my_function.cpp:203-209 at its turn, nothing persists
     return;
   const int32_t i = sl.seed_i;
   const PagedStore st = slot_store(S, g);
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(TPB) spec_release_slots_kernel(SpecArgs S)
   if (g >= S.G)
     return;
   Slot& sl = S.slots[g];
-  if (sl.status != ST_RELEASING && sl.status != ST_DONE)
+  if (sl.status != ST_RELEASING && sl.status != ST_DONE && sl.status != ST_ROLLED)
     return;
   if (sl.status == ST_RELEASING) atomicAdd(&S.sc[SC_WASTED], sl.steps);
   slot_free(S, g);
@@ -216,6 +232,8 @@ __global__ void __launch_bounds__(TPB) spec_apply_marks_kernel(SpecArgs S)
   for (unsigned long long k = (unsigned long long)blockIdx.x * TPB + threadIdx.x; k < nlog;
        k += (unsigned long long)gridDim.x * TPB) {
     const uint2 e = S.marklog[k];
+    if (e.x == 0xffffffffu)
+      continue;  // log space a serial stretch reserved and did not need
     const uint32_t r = __ldcg(A.res + e.x);
     if (r != RES_FREE) {
       if (r != e.y) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
@@ -227,14 +245,68 @@ __global__ void __launch_bounds__(TPB) spec_apply_marks_kernel(SpecArgs S)
   }
 }
 
-// alive bits of the points of the planes this sweep committed: pool entries [SC_POOL0, CTL_POOL)
-__global__ void __launch_bounds__(TPB) spec_apply_planes_kernel(SpecArgs S)
+// ---- finished slots: the list is checked ONCE, in parallel, when the slot has finished ----------------------------
+// A finished, un-doomed slot holds the sequential result iff at its turn (V1) every point it accepted is still free
+// and (V2) every point it assumed taken is taken.  V1 holds at its turn iff it holds now AND the slot still owns every
+// reservation AND nothing marks one of its points later -- and whoever does that (a lower grower stealing the
+// reservation, the scout publishing a lower hint, the sweeper marking the point for a tiny transaction) dooms the
+// holder at that moment.  So the list is walked here by the whole GPU instead of by the sweeper's one block; V2 is
+// reduced to the (few) assumed-taken points that are still free now, which the sweeper looks at when the turn comes.
+__global__ void __launch_bounds__(TPB) spec_preverify_kernel(SpecArgs S)
 {
   const GrowArgs& A = S.A;
-  const unsigned long long lo = S.sc[SC_POOL0], hi = A.ctl[CTL_POOL];
-  for (unsigned long long k = lo + (unsigned long long)blockIdx.x * TPB + threadIdx.x; k < hi;
-       k += (unsigned long long)gridDim.x * TPB) {
-    const int32_t w = __ldg(&A.pts[A.pool[k]].w);
+  const int g = blockIdx.y;
+  Slot& sl = S.slots[g];
+  if (sl.status != ST_FINISHED)
+    return;
+  const int32_t i = sl.seed_i;
+  if (((volatile uint8_t*)A.doom)[i])
+    return;
+  const PagedStore st = slot_store(S, g);
+  const int64_t len = sl.verified == 2 ? 0 : sl.t.len, n_at = sl.t.n_at;  // the list once, the open assumptions every round
+  bool bad = false;
+  for (int64_t e = 1 + (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB) {
+    const int32_t pt = st.get(e);
+    bad |= __ldcg(A.state + pt) != -1 || __ldcg(A.res + pt) != (uint32_t)i;
+  }
+  for (int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x; k < n_at; k += (int64_t)RCH * TPB) {
+    const int32_t pt = st.get_at(k);
+    if (__ldcg(A.state + pt) == -1) {
+      const int idx = atomicAdd(&sl.n_pend, 1);
+      if (idx < PEND_CAP) S.pend[(size_t)g * PEND_CAP + idx] = pt;
+    }
+  }
+  if (bad) A.doom[i] = 1;
+  if (threadIdx.x == 0 && blockIdx.x == 0 && sl.verified == 0) sl.verified = 1;  // (2 after the kernel: the other blocks of the slot test it)
+}
+
+__global__ void __launch_bounds__(TPB) spec_preverify_done_kernel(SpecArgs S)
+{
+  const int g = blockIdx.x * TPB + threadIdx.x;
+  if (g < S.G && S.slots[g].verified == 1) S.slots[g].verified = 2;
+}
+
+// ---- planes the sweep accepted: list -> committed pool, owner marks, reservations dropped, alive bits ---------------
+// (the sweeper itself only records the plane and names its seed in the set of committed seeds: for the rest of the
+// sweep a point reserved by such a seed counts as taken)
+__global__ void __launch_bounds__(TPB) spec_apply_commits_kernel(SpecArgs S)
+{
+  const GrowArgs& A = S.A;
+  const int g = blockIdx.y;
+  const Slot& sl = S.slots[g];
+  if (sl.status != ST_COMMIT)
+    return;
+  const int32_t i = sl.seed_i;
+  const PagedStore st = slot_store(S, g);
+  const int64_t len = sl.t.len, off = sl.pool_off;
+  for (int64_t e = (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB) {
+    const int32_t id = st.get(e);
+    A.pool[off + e] = id;
+    if (e >= 1) {  // the seed's own entry is not a mark (:191)
+      A.state[id] = i;
+      A.res[id] = RES_FREE;
+    }
+    const int32_t w = __ldg(&A.pts[id].w);
     atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
   }
 }
@@ -358,6 +430,8 @@ __global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t F,
   sl.started = 0;
   sl.steps = 0;
   sl.n_pages = 0;
+  sl.n_pend = 0;
+  sl.verified = 0;
   S.A.slotof[F + t] = (int32_t)g;
   S.A.doom[F + t] = 0;
 }
@@ -430,30 +504,108 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
 }
 
 // ---- K3: the sweeper ------------------------------------------------------------------------------------------
+// One thread block walks the seeds in index order, SWEEP_T live seeds per batch.  A batch is resolved in sub-steps; one
+// sub-step decides a SEGMENT [done, seg_end) of the batch -- tiny transactions and growers together -- in parallel:
+//   * every live seed is classified against the committed state: tiny-looking (marks its free depth-0 neighbours) or
+//     grower-looking (all K-1 are free: :238 does not fire);
+//   * a shared-memory hash table maps every point a tiny-looking seed wants to the lowest thread wanting it, a second
+//     one maps the seeds of the grower-looking threads to their threads;
+//   * a seed is in CONFLICT when its outcome depends on a lower seed of the same segment in a way the tables cannot
+//     settle: its own point is wanted by a lower tiny seed or reserved by a lower grower-looking one; a grower-looking
+//     seed has a neighbour wanted by a lower tiny seed; any of its wanted points is reserved by a lower grower-looking
+//     seed.  The segment ends at the first conflict (the seed is re-classified after the segment has committed);
+//   * tiny seeds of the segment doom the holder of every point they are about to mark (a grower ahead of the sweeper),
+//     then the grower-looking seeds decide, each on its own thread: the slot must be finished, verified
+//     (spec_preverify_kernel) and un-doomed, and the assumed-taken points that were still free at verification must
+//     be taken now.  The first grower that cannot be decided ends the segment AND the sweep;
+//   * commit: orphan marks (atomicMin on the owner: the lower seed keeps a shared point) and the mark log; a plane is
+//     only RECORDED (pool range, PlaneRec, status) and its seed enters the set of committed seeds -- for the rest of
+//     the sweep a point reserved by a committed seed counts as taken; the list is copied out by the whole GPU after
+//     the sweep (spec_apply_commits_kernel).  A roll-back (:203-209) is a status change.
+// Clouds in scan order make nearly every seed depend on the one before it; there the block switches to SERIAL
+// STRETCHES: the seeds are resolved one after the other, a warp at a time, against a shared-memory set of the points
+// marked so far in the stretch (~200 cycles per live seed instead of one block-wide sub-step per conflict).
+// Nothing on the block's path waits for global memory except one gather level per sub-step (states + reservations).
 struct SweepShared {
-  int first_special;  // lowest thread whose seed needs the slow path (or lies beyond the cloud)
   int first_over;     // lowest thread beyond the hash-table budget
-  int first_conf;     // lowest thread whose seed a lower seed of the batch wants
-  int stop;
-  int sp_slot, sp_np, sp_bad;
-  unsigned long long c_off, c_pl;
+  int first_conf;     // lowest thread in conflict with a lower seed of the segment
+  int first_fail;     // lowest grower-looking thread that cannot be decided (the sweep stops there)
+  int first_g;        // lowest unfinished grower-looking thread
+  int ser_end, ser_ins;  // serial stretch: first thread it did not reach, points in the taken set
+  int n_cset, n_dset, dset_over;
+  int n_conf;         // threads of the segment in conflict
+  int sp_big, sp_bad, sp_slot;
+  unsigned long long c_off, c_pl, c_steps, c_tx;
   int warp_sum[32];
   int n_live;
-  int64_t last_seed, last_open, sp_seed;
-  uint32_t ptc[PT_CACHE];  // page table of the slot being committed
+  int64_t last_seed, last_open;
   uint32_t words[SWEEP_WORDS];
   int pref[SWEEP_WORDS];
+  uint32_t cset[CSET];    // seeds whose planes this sweep committed (open addressing, 0xffffffff = empty)
+  uint32_t dset[DSET];    // seeds this sweep doomed
+  uint32_t gkey[GSET];    // seeds of the grower-looking threads of the segment ...
+  uint32_t gval[GSET];    // ... and their threads
 };
 
-__device__ __forceinline__ uint32_t sweep_hash(uint32_t p) { return (p * 2654435761u) >> 18; }  // 14 bits
+template <int BITS>
+__device__ __forceinline__ bool set_has(const uint32_t* tab, uint32_t key)
+{
+  uint32_t h = (key * 2654435761u) >> (32 - BITS);
+  for (;;) {
+    const uint32_t k = tab[h];
+    if (k == key)
+      return true;
+    if (k == 0xffffffffu)
+      return false;
+    h = (h + 1) & ((1u << BITS) - 1);
+  }
+}
+
+// true = the key was not there
+template <int BITS>
+__device__ __forceinline__ bool set_insert(uint32_t* tab, uint32_t key)
+{
+  uint32_t h = (key * 2654435761u) >> (32 - BITS);
+  for (;;) {
+    const uint32_t old = atomicCAS(tab + h, 0xffffffffu, key);
+    if (old == 0xffffffffu)
+      return true;
+    if (old == key)
+      return false;
+    h = (h + 1) & ((1u << BITS) - 1);
+  }
+}
+
+// thread of the grower-looking seed `seed` in this segment, SWEEP_T if there is none
+__device__ __forceinline__ uint32_t gset_find(const uint32_t* gkey, const uint32_t* gval, uint32_t seed)
+{
+  uint32_t h = (seed * 2654435761u) >> (32 - GSET_BITS);
+  for (;;) {
+    const uint32_t k = gkey[h];
+    if (k == seed)
+      return gval[h];
+    if (k == 0xffffffffu)
+      return (uint32_t)SWEEP_T;
+    h = (h + 1) & (GSET - 1);
+  }
+}
+
+template <int KM>
+struct SweepCfg {
+  static constexpr int HT_BITS = 14;  // hash table slots (keys + vals = 128 KB of shared memory)
+  static constexpr int HT = 1 << HT_BITS;
+  static constexpr size_t SMEM = (size_t)HT * 8;
+};
 
 // the sequential authority: walks the seeds from the frontier in index order
 template <int KM>
 __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
 {
+  constexpr int HT_BITS = SweepCfg<KM>::HT_BITS;
+  constexpr int HT = SweepCfg<KM>::HT;
   extern __shared__ uint32_t smem_u32[];
   uint32_t* hkeys = smem_u32;        // [HT] point, 0xffffffff = empty
-  uint32_t* hvals = smem_u32 + HT;   // [HT] lowest thread of the batch that wants it
+  uint32_t* hvals = smem_u32 + HT;   // [HT] lowest thread of the segment that wants it
   __shared__ SweepShared sh;
   const GrowArgs& A = S.A;
   const int tid = threadIdx.x;
@@ -461,20 +613,59 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   const int K = A.K;
   int64_t F = (int64_t)A.ctl[CTL_FRONTIER];
   const int64_t n_words = (A.n + 31) >> 5;
-  unsigned long long iters = 0, ntiny = 0;
+  uint32_t iters = 0, ntiny = 0;
+  const bool timing = (A.flags & GF_TIMING) != 0;  // BSEG_DEBUG: time split of the block (thread 0's clock)
   const unsigned long long t_begin = gtimer();
   for (int k = tid; k < HT; k += SWEEP_T) {
     hkeys[k] = 0xffffffffu;
     hvals[k] = 0xffffffffu;
   }
-  if (tid == 0) sh.stop = 0;
+  for (int k = tid; k < CSET; k += SWEEP_T) sh.cset[k] = 0xffffffffu;
+  for (int k = tid; k < DSET; k += SWEEP_T) sh.dset[k] = 0xffffffffu;
+  for (int k = tid; k < GSET; k += SWEEP_T) {
+    sh.gkey[k] = 0xffffffffu;
+    sh.gval[k] = (uint32_t)SWEEP_T;
+  }
+  if (tid == 0) {
+    sh.n_cset = 0;
+    sh.n_dset = 0;
+    sh.dset_over = 0;
+    sh.c_off = A.ctl[CTL_POOL];
+    sh.c_pl = A.ctl[CTL_PLANES];
+    sh.c_steps = 0;
+    sh.c_tx = 0;
+  }
   __syncthreads();
-  unsigned long long t_front = 0, t_slow = 0, t_fast = 0, n_slow = 0;
+  unsigned long long t_front = 0;  // (thread 0 only)
+  uint32_t n_sub = 0, n_grow = 0, n_ser = 0, n_pendsum = 0;
   bool stop = false;
+  bool serial = false;     // conflicts are dense: resolve stretches serially (re-probed every 8th batch)
+  bool force_par = false;  // the stretch stopped at a grower: one parallel sub-step decides it
+
+  // this sweep dooms transaction r (a grower ahead of the sweeper that holds a point which is being marked)
+  auto doom_now = [&](uint32_t r) {
+    A.doom[r] = 1;
+    if (sh.dset_over)
+      return;
+    uint32_t h = (r * 2654435761u) >> (32 - DSET_BITS);
+    for (int probe = 0; probe < 32; ++probe) {  // bounded: many threads insert at once
+      const uint32_t old = atomicCAS(sh.dset + h, 0xffffffffu, r);
+      if (old == r)
+        return;
+      if (old == 0xffffffffu) {
+        if (atomicAdd(&sh.n_dset, 1) >= DSET / 2) sh.dset_over = 1;
+        return;
+      }
+      h = (h + 1) & (DSET - 1);
+    }
+    sh.dset_over = 1;  // too many to keep: growers then ask global memory
+  };
 
   while (F < A.n && !stop) {
     ++iters;
-    const unsigned long long ti0 = gtimer();
+    if ((iters & 7) == 0) serial = false;
+    unsigned long long ti0 = 0;
+    if (timing && tid == 0) ti0 = gtimer();
     // ---- the next live seeds: scan the alive bitmap (original index order, a superset of the free points) ----
     // Late in the sweep 5 seeds of 6 are taken; they cost one bit here instead of a gather.
     const int64_t base = F & ~31LL;
@@ -523,295 +714,449 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       i = base + 32LL * lo + bit;
     }
     if (tid == n_eval - 1) sh.last_seed = i;  // the seed after it starts the next batch when all of these are done
+    const uint32_t me = (uint32_t)i;
     uint32_t s = 0, want = 0;
-    int32_t slot = -1;
-    bool live = false, grower = false;
-    int32_t ids[KM];  // neighbour columns that pass depth 0 (registers: every loop over them is unrolled)
+    uint32_t held_lo = 0, held_hi = 0;  // wanted neighbour j carries the reservation of a lower / higher seed
+    uint32_t rs_self = RES_FREE;
+    uint32_t rs[KM];                    // reservation of neighbour j (as gathered by classify)
+    int32_t ids[KM];                    // neighbour columns that pass depth 0, -1 = none (registers: every loop over them is unrolled)
 #pragma unroll
     for (int j = 1; j < KM; ++j) ids[j] = -1;
-    if (valid) {
-      // dependent levels of loads: (inv, gmask, slot) -> (state of the seed, row) -> neighbour states
-      s = __ldg(A.inv + i);
-      const uint32_t m = __ldg(S.gmask + i);
-      slot = __ldcg(A.slotof + i);
-      const int32_t* row = A.nbr + (int64_t)s * K;
+    int32_t slot = -1;
+    bool live = false, glook = false;
+    bool g_ready = false, g_doom0 = false;  // the slot of this seed: finished + verified; doomed before the sweep
+    int64_t g_len = 0;
+    int g_npend = 0;
+    bool pend_done = false, pend_bad = false;  // the block walked this grower's assumed-taken list (more than PEND_CAP were open)
+    // committed state + planes this sweep has accepted: one load level (state and reservation of the seed and of its
+    // depth-0 neighbours)
+    auto classify = [&]() {
       const int32_t st_s = __ldcg(A.state + s);  // the bitmap is only a filter: this is the truth
-#pragma unroll
-      for (int j = 1; j < KM; ++j)
-        if ((m >> j) & 1u) ids[j] = __ldg(row + j);
+      rs_self = __ldcg(A.res + s);
       int32_t stj[KM];
 #pragma unroll
       for (int j = 1; j < KM; ++j) {
         stj[j] = 0;
-        if (ids[j] >= 0) stj[j] = __ldcg(A.state + ids[j]);
+        rs[j] = RES_FREE;
+        const int32_t id = ids[j];
+        if (id >= 0) {
+          stj[j] = __ldcg(A.state + id);
+          rs[j] = __ldcg(A.res + id);
+        }
       }
       live = st_s == -1;
+      want = 0;
+      held_lo = 0;
+      held_hi = 0;
+      if (live && rs_self != RES_FREE && set_has<CSET_BITS>(sh.cset, rs_self)) live = false;
       if (live) {
 #pragma unroll
         for (int j = 1; j < KM; ++j)
-          if (ids[j] >= 0 && stj[j] == -1) want |= 1u << j;
-        grower = __popc(want) == K - 1;  // :238 -- every neighbour accepted
+          if (stj[j] == -1) {  // (-1 only for a column that exists)
+            const uint32_t r = rs[j];
+            if (r != RES_FREE && r != me) {
+              if (set_has<CSET_BITS>(sh.cset, r))
+                continue;  // in a plane this sweep committed: taken
+              if (r < me) held_lo |= 1u << j;
+              else held_hi |= 1u << j;
+            }
+            want |= 1u << j;
+          }
       }
+      glook = live && __popc(want) == K - 1;  // :238 -- every neighbour accepted
+    };
+    if (valid) {
+      // dependent levels of loads: (inv, gmask, slot) -> (row, slot record) -> states
+      s = __ldg(A.inv + i);
+      const uint32_t m = __ldg(S.gmask + i);
+      slot = __ldcg(A.slotof + i);
+      const int32_t* row = A.nbr + (int64_t)s * K;
+#pragma unroll
+      for (int j = 1; j < KM; ++j)
+        if ((m >> j) & 1u) ids[j] = __ldg(row + j);
+      if (slot >= 0) {  // (its own fields: nobody writes them during the sweep)
+        const Slot& sl = S.slots[slot];
+        g_ready = sl.status == ST_FINISHED && sl.verified == 2;
+        g_len = sl.t.len;
+        g_npend = sl.n_pend;
+        g_doom0 = ((volatile uint8_t*)A.doom)[i] != 0;
+      }
+      classify();
     }
-    t_front += gtimer() - ti0;
+    if (timing && tid == 0) t_front += gtimer() - ti0;
 
-    // ---- sub-steps on this batch: threads [0, done) are finished; after every commit the others only
-    //      re-gather the states of what they already know (one load level instead of four) ----
+    // ---- sub-steps on this batch: threads [0, done) are finished ----
     int done = 0;
     while (done < n_eval && !stop) {
-      const unsigned long long ti1 = gtimer();
-      bool state_changed = true;  // false after a roll-back: nothing the other threads know has moved
+      ++n_sub;
       if (tid == 0) {
-        sh.first_special = SWEEP_T;
         sh.first_over = SWEEP_T;
         sh.first_conf = SWEEP_T;
+        sh.first_fail = SWEEP_T;
+        sh.first_g = SWEEP_T;
+        sh.n_conf = 0;
+        sh.sp_big = 0;
+        sh.sp_bad = 0;
+        sh.ser_end = n_eval;
+        sh.ser_ins = 0;
       }
       __syncthreads();
       const bool act = valid && tid >= done;
-      if (act && grower) atomicMin(&sh.first_special, tid);
-      // a slot whose seed is not a grower at its turn is void (the state only gets more taken: it never will be)
-      if (act && slot >= 0 && !grower) A.doom[i] = 1;
-      __syncthreads();
-      int first_special = sh.first_special;
-      if (first_special > n_eval) first_special = n_eval;
 
-      if (first_special == done) {
-        // ---- slow path: the first unfinished seed is a grower at its turn ----
-        ++n_slow;
-        if (tid == done) {
-          sh.sp_slot = slot;
-          sh.sp_bad = 0;
-          sh.sp_seed = i;
+      if (serial && !force_par) {
+        // ---- serial stretch ----
+        for (int wi = done >> 5; wi <= ((n_eval - 1) >> 5); ++wi) {
+          if ((tid >> 5) == wi && sh.ser_end == n_eval) {
+            const bool mine = act && live;
+            uint32_t todo = __ballot_sync(FULL_MASK, mine);
+            int n_ins = sh.ser_ins;
+            const int nw = mine ? __popc(want) : 0;  // log space: one entry per want (unused ones are voided)
+            int wincl = nw;
+            for (int o = 1; o < 32; o <<= 1) {
+              const int v = __shfl_up_sync(FULL_MASK, wincl, o);
+              if (lane >= o) wincl += v;
+            }
+            const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
+            unsigned long long lbase = 0;
+            if (wtot > 0) {
+              if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
+              lbase = __shfl_sync(FULL_MASK, lbase, 0);
+            }
+            const int woff = wincl - nw;
+            int end_tid = -1;
+            while (todo) {
+              const int l = __ffs(todo) - 1;
+              const uint32_t s_l = __shfl_sync(FULL_MASK, s, l);
+              const uint32_t want_l = __shfl_sync(FULL_MASK, want, l), hi_l = __shfl_sync(FULL_MASK, held_hi, l);
+              const uint32_t seed_l = __shfl_sync(FULL_MASK, me, l);
+              const int woff_l = __shfl_sync(FULL_MASK, woff, l);
+              const int slot_l = __shfl_sync(FULL_MASK, slot, l);
+              const bool glook_l = __shfl_sync(FULL_MASK, (int)glook, l) != 0;
+              const bool w = lane >= 1 && lane < KM && ((want_l >> lane) & 1u);
+              int32_t myid = -1;  // lane j looks after neighbour column j of the seed
+#pragma unroll
+              for (int j = 1; j < KM; ++j) {
+                const int32_t v = __shfl_sync(FULL_MASK, ids[j], l);
+                if (lane == j) myid = v;
+              }
+              const bool dead = set_has<HT_BITS>(hkeys, s_l);  // marked by a lower seed of the stretch (:185)
+              if (!dead && glook_l) {
+                // still a grower at its turn?  (a neighbour may have been marked in the stretch)
+                const bool gone = w && set_has<HT_BITS>(hkeys, (uint32_t)myid);
+                if (__popc(__ballot_sync(FULL_MASK, w && !gone)) == K - 1) {
+                  end_tid = wi * 32 + l;  // yes: the stretch ends in front of it
+                  break;
+                }
+              }
+              todo &= todo - 1;
+              if (slot_l >= 0 && lane == 0) A.doom[seed_l] = 1;  // dead, or not a grower at its turn: the slot is void
+              bool ins = false;
+              if (w && !dead) ins = set_insert<HT_BITS>(hkeys, (uint32_t)myid);
+              if (w) {
+                const unsigned long long pos = lbase + (unsigned long long)(woff_l + __popc(want_l & lanemask_lt()));
+                if (pos < S.marklog_cap) S.marklog[pos] = make_uint2(ins ? (uint32_t)myid : 0xffffffffu, seed_l);
+              }
+              if (ins) {
+                A.state[myid] = (int32_t)seed_l;  // the first marker of the stretch owns the point
+                if ((hi_l >> lane) & 1u) {        // held by a higher transaction (rare): it is void
+                  const uint32_t r = __ldcg(A.res + myid);
+                  if (r != RES_FREE && r > seed_l) doom_now(r);
+                }
+              }
+              if (!dead && lane == l) ++ntiny;
+              n_ins += __popc(__ballot_sync(FULL_MASK, ins));
+              if (n_ins > HT / 2 - 32) {  // the set is full: the stretch ends after this seed
+                end_tid = wi * 32 + l + 1;
+                break;
+              }
+            }
+            if (end_tid >= 0 && mine && tid >= end_tid) {  // log space of the seeds the warp did not reach
+              int k = 0;
+              for (uint32_t b = want; b; b &= b - 1, ++k) {
+                const unsigned long long pos = lbase + (unsigned long long)(woff + k);
+                if (pos < S.marklog_cap) S.marklog[pos] = make_uint2(0xffffffffu, me);
+              }
+            }
+            if (lane == 0) {
+              sh.ser_ins = n_ins;
+              if (end_tid >= 0 && end_tid < n_eval) sh.ser_end = end_tid;
+            }
+          }
+          __syncthreads();
         }
+        const int ser_end = sh.ser_end;
+        if (tid == ser_end && valid) sh.last_open = i;
+        for (int k = tid; k < HT; k += SWEEP_T) hkeys[k] = 0xffffffffu;
         __syncthreads();
-        const int64_t Fs = sh.sp_seed;  // everything before it is done
-        F = Fs;
+        if (ser_end == done) force_par = true;  // a grower at its turn: the parallel sub-step decides it
+        done = ser_end;
+        if (done < n_eval) {
+          F = sh.last_open;
+          if (valid && tid >= done && !force_par) classify();
+        }
+        ++n_ser;
+        continue;
+      }
+      force_par = false;
+
+      // a slot whose seed is not a grower at its turn is void (the state only gets more taken: it never will be)
+      if (act && slot >= 0 && !glook) A.doom[i] = 1;
+      // the first unfinished seed is a grower with more open assumed-taken points than its thread can look at:
+      // the block walks the list (rare)
+      if (tid == done && glook && g_ready && g_npend > PEND_CAP && !pend_done) {
+        sh.sp_big = 1;
+        sh.sp_slot = slot;
+      }
+      if (act && glook) atomicMin(&sh.first_g, tid);
+      // cap the segment so that the hash table stays at most half full
+      const bool tiny = act && live && !glook;
+      int wsum = tiny ? __popc(want) : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL_MASK, wsum, o);
+        if (lane >= o) wsum += v;
+      }
+      if (lane == 31) sh.warp_sum[tid >> 5] = wsum;
+      __syncthreads();
+      if (sh.sp_big) {
         const int g = sh.sp_slot;
-        if (g < 0) {  // no slot: the scout gives it one
-          if (tid == 0) S.sc[SC_STUCK] = 1;
-          stop = true;
-          break;
-        }
-        Slot& sl = S.slots[g];
-        const int status = sl.status;
-        const bool doomed = ((volatile uint8_t*)A.doom)[Fs] != 0;
-        if (status != ST_FINISHED || doomed) {
-          // still growing (the head), or void: released next round, then the scout re-assigns it
-          if (tid == 0 && status != ST_RUNNING) S.sc[SC_STUCK] = 1;
-          stop = true;
-          break;
-        }
+        const Slot& sl = S.slots[g];
         const PagedStore st = slot_store(S, g);
-        const int64_t len = sl.t.len, n_at = sl.t.n_at;
-        // the slot's page table goes to shared memory: one dependent load level less in every loop below
-        if (tid < PT_CACHE && tid < sl.n_pages) sh.ptc[tid] = st.ptab[tid];
-        if (tid == 0) {
-          sh.c_off = A.ctl[CTL_POOL];
-          sh.c_pl = A.ctl[CTL_PLANES];
-        }
-        __syncthreads();
-        auto at = [&](int64_t e) -> size_t {
-          const int64_t pg = e >> PAGE_SHIFT;
-          const uint32_t page = pg < PT_CACHE ? sh.ptc[pg] : st.ptab[pg];
-          return ((size_t)page << PAGE_SHIFT) + (size_t)(e & (PAGE_SIZE - 1));
-        };
-        // every point it treated as taken (reserved by a lower transaction at the time) must be taken now,
-        // and every point it accepted must still be free (a lower tiny transaction may have marked it)
+        const int64_t n_at = sl.t.n_at;
         bool bad = false;
-        // (four entries per thread and trip: the loads of a trip are independent, one block has to do it all)
-        for (int64_t k0 = tid; k0 < n_at; k0 += 4 * SWEEP_T) {
-          int32_t pt[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) pt[u] = k0 + u * SWEEP_T < n_at ? S.pool.at_pages[at(k0 + u * SWEEP_T)] : -1;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (pt[u] >= 0) bad |= __ldcg(A.state + pt[u]) == -1;
-        }
-        for (int64_t e0 = 1 + tid; e0 < len; e0 += 4 * SWEEP_T) {
-          int32_t pt[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) pt[u] = e0 + u * SWEEP_T < len ? S.pool.list_pages[at(e0 + u * SWEEP_T)] : -1;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (pt[u] >= 0) bad |= __ldcg(A.state + pt[u]) != -1;
+        for (int64_t k = tid; k < n_at; k += SWEEP_T) {
+          const int32_t pt = st.get_at(k);
+          if (__ldcg(A.state + pt) == -1) {
+            const uint32_t r = __ldcg(A.res + pt);
+            bad |= r == RES_FREE || !set_has<CSET_BITS>(sh.cset, r);
+          }
         }
         if (bad) sh.sp_bad = 1;
         __syncthreads();
-        if (sh.sp_bad) {
-          if (tid == 0) {
-            A.doom[Fs] = 1;
-            S.sc[SC_STUCK] = 1;
-            atomicAdd(&S.sc[SC_ATFAIL], 1ull);
-          }
-          stop = true;
-          break;
+        if (tid == done) {
+          pend_done = true;
+          pend_bad = sh.sp_bad != 0;
         }
-        if (len > A.th_count) {  // :199-202
-          const unsigned long long off = sh.c_off, pl = sh.c_pl;
-          if ((int64_t)(off + len) > A.pool_cap - A.n - 2 || (int64_t)pl >= A.planes_cap) {
-            if (tid == 0) A.ctl[CTL_ERR] = 2;
-            stop = true;
-            break;
-          }
-          for (int64_t e0 = tid; e0 < len; e0 += 4 * SWEEP_T) {
-            int32_t id[4];
+      }
+      int incl = wsum;  // inclusive prefix of wants in index order
+      for (int w = 0; w < (tid >> 5); ++w) incl += sh.warp_sum[w];
+      if (tiny && incl > HT / 2) atomicMin(&sh.first_over, tid);
+      __syncthreads();
+      int seg_hi = sh.first_over < n_eval ? sh.first_over : n_eval;
+      if (seg_hi <= done) seg_hi = done + 1;  // a single seed always fits (K-1 <= 31 wants)
+      const int first_g = sh.first_g;
+      const bool in_seg = act && tid < seg_hi;
+      if (in_seg && tiny && want) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) id[u] = e0 + u * SWEEP_T < len ? S.pool.list_pages[at(e0 + u * SWEEP_T)] : -1;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (id[u] < 0)
-                continue;
-              const int64_t e = e0 + u * SWEEP_T;
-              A.pool[off + e] = id[u];  // (the alive bits of these points are cleared from the pool by the apply kernel)
-              if (e >= 1) {
-                A.state[id[u]] = (int32_t)Fs;
-                A.res[id[u]] = RES_FREE;
-              }
-            }
-          }
-          if (tid == 0) {
-            PlaneRec r;
-            r.seed = (int32_t)Fs; r.pad = 0;
-            r.off = (int64_t)off; r.len = len;
-            r.nrm[0] = sl.t.m.mn0; r.nrm[1] = sl.t.m.mn1; r.nrm[2] = sl.t.m.mn2;
-            r.ctr[0] = sl.t.m.mc0; r.ctr[1] = sl.t.m.mc1; r.ctr[2] = sl.t.m.mc2; r.pad2 = 0;
-            A.planes[pl] = r;
-            A.ctl[CTL_POOL] = off + (unsigned long long)len;
-            A.ctl[CTL_PLANES] = pl + 1;
-          }
-        } else {  // roll back (:203-209): nothing persists
-          state_changed = false;
-          for (int64_t e = 1 + tid; e < len; e += SWEEP_T) {
-            const int32_t pt = S.pool.list_pages[at(e)];
-            if (atomicCAS(A.res + pt, (uint32_t)Fs, RES_FREE) == (uint32_t)Fs) unreserve_notify(A.atby, A.slotof, A.doom, pt);
-          }
-        }
-        // the slot and its pages go back in the next round's release pass (parallel), not on this block's path
-        if (tid == 0) {
-          A.ctl[CTL_STEPS] += sl.steps;
-          A.ctl[CTL_TX] += 1;
-          sl.status = ST_DONE;
-        }
-        __syncthreads();
-        F = Fs + 1;  // the seed is done (its own point stays unmarked, :191)
-        done += 1;
-        t_slow += gtimer() - ti1;
-      } else {
-        // ---- fast path: seeds of threads [done, first_special) are dead or tiny ----
-        const bool cand = act && tid < first_special && live;
-        // cap the batch so that the hash table stays at most half full
-        int wsum = cand ? __popc(want) : 0;
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(FULL_MASK, wsum, o);
-          if (lane >= o) wsum += v;
-        }
-        if (lane == 31) sh.warp_sum[tid >> 5] = wsum;
-        __syncthreads();
-        int incl = wsum;  // inclusive prefix of wants in index order
-        for (int w = 0; w < (tid >> 5); ++w) incl += sh.warp_sum[w];
-        if (cand && incl > HT / 2) atomicMin(&sh.first_over, tid);
-        __syncthreads();
-        int seg_hi = sh.first_over < first_special ? sh.first_over : first_special;
-        if (seg_hi <= done) seg_hi = done + 1;  // a single seed always fits (K-1 <= 31 wants)
-        const bool in_seg = cand && tid < seg_hi;
-        // which seeds are about to be marked by a LOWER seed of this batch?
-        if (in_seg && want) {
-#pragma unroll
-          for (int j = 1; j < KM; ++j) {
-            if (!((want >> j) & 1u))
-              continue;
-            const uint32_t id = (uint32_t)ids[j];
-            uint32_t h = sweep_hash(id);
-            for (;;) {
-              const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
-              if (old == 0xffffffffu || old == id) {
-                atomicMin(hvals + h, (uint32_t)tid);
-                break;
-              }
-              h = (h + 1) & (HT - 1);
-            }
-          }
-        }
-        __syncthreads();
-        if (in_seg) {
-          uint32_t h = sweep_hash(s);
+        for (int j = 1; j < KM; ++j) {
+          if (!((want >> j) & 1u))
+            continue;
+          const uint32_t id = (uint32_t)ids[j];
+          uint32_t h = (id * 2654435761u) >> (32 - HT_BITS);
           for (;;) {
-            const uint32_t k = hkeys[h];
-            if (k == 0xffffffffu)
-              break;
-            if (k == s) {
-              if (hvals[h] < (uint32_t)tid) atomicMin(&sh.first_conf, tid);
+            const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
+            if (old == 0xffffffffu || old == id) {
+              atomicMin(hvals + h, (uint32_t)tid);
               break;
             }
             h = (h + 1) & (HT - 1);
           }
         }
-        __syncthreads();
-        const int seg_end = sh.first_conf < seg_hi ? sh.first_conf : seg_hi;  // > done: the first one has nobody below it
-        // ---- commit the conflict-free prefix: orphan marks of the tiny transactions (:233 then :238-239) ----
-        // Only the owner mark is on the sweeper's path; what the mark means for others (reservation void, holder
-        // doomed, alive bit, seed of a waiting grower taken) is logged and applied by a parallel kernel after the
-        // sweep -- none of it is needed for correctness (a slot is verified point by point before it commits).
-        {
-          const bool commit = in_seg && tid < seg_end;
-          const int nw = commit ? __popc(want) : 0;
-          if (commit) ++ntiny;
-          int wincl = nw;
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL_MASK, wincl, o);
-            if (lane >= o) wincl += v;
+      }
+      if (in_seg && glook) {
+        uint32_t h = (me * 2654435761u) >> (32 - GSET_BITS);
+        for (;;) {
+          const uint32_t old = atomicCAS(sh.gkey + h, 0xffffffffu, me);
+          if (old == 0xffffffffu) {
+            sh.gval[h] = (uint32_t)tid;
+            break;
           }
-          const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
-          unsigned long long lbase = 0;
-          if (wtot > 0) {
-            if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
-            lbase = __shfl_sync(FULL_MASK, lbase, 0);
-          }
-          if (nw) {
-            unsigned long long pos = lbase + (unsigned long long)(wincl - nw);
+          h = (h + 1) & (GSET - 1);
+        }
+      }
+      __syncthreads();
+      // lowest thread of the segment that wants point p (SWEEP_T: nobody)
+      auto wanted_by = [&](uint32_t p) -> uint32_t {
+        uint32_t h = (p * 2654435761u) >> (32 - HT_BITS);
+        for (;;) {
+          const uint32_t k = hkeys[h];
+          if (k == 0xffffffffu)
+            return (uint32_t)SWEEP_T;
+          if (k == p)
+            return hvals[h];
+          h = (h + 1) & (HT - 1);
+        }
+      };
+      const bool have_g = first_g < seg_hi;  // grower-looking seeds in the segment
+      // ---- conflicts with lower seeds of the segment ----
+      bool g_bad = false;  // grower-looking: an assumed-taken point is free at its turn
+      if (in_seg && live) {
+        bool conf = wanted_by(s) < (uint32_t)tid;
+        if (have_g) {
+          if (rs_self != RES_FREE && rs_self < me) conf |= gset_find(sh.gkey, sh.gval, rs_self) < (uint32_t)tid;
 #pragma unroll
-            for (int j = 1; j < KM; ++j) {
-              if (!((want >> j) & 1u))
-                continue;
-              const int32_t id = ids[j];
-              atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, (uint32_t)i);  // the lower seed owns a shared point
-              if (pos < S.marklog_cap) S.marklog[pos] = make_uint2((uint32_t)id, (uint32_t)i);
-              ++pos;
+          for (int j = 1; j < KM; ++j)
+            if ((held_lo >> j) & 1u) conf |= gset_find(sh.gkey, sh.gval, rs[j]) < (uint32_t)tid;
+        }
+        if (glook) {
+#pragma unroll
+          for (int j = 1; j < KM; ++j)
+            if ((want >> j) & 1u) conf |= wanted_by((uint32_t)ids[j]) < (uint32_t)tid;
+          if (g_ready) {
+            if (pend_done) {
+              g_bad = pend_bad;
+            } else if (g_npend > PEND_CAP) {
+              conf |= tid != done;  // the block walks its list when it is the first of a segment
+            } else {
+              for (int k0 = 0; k0 < g_npend; k0 += 4) {  // (all loads of a trip in flight together)
+                int32_t pp[4], ps[4];
+                uint32_t pr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pp[u] = k0 + u < g_npend ? S.pend[(size_t)slot * PEND_CAP + k0 + u] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  ps[u] = 0;
+                  pr[u] = RES_FREE;
+                  if (pp[u] >= 0) {
+                    ps[u] = __ldcg(A.state + pp[u]);
+                    pr[u] = __ldcg(A.res + pp[u]);
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (pp[u] < 0 || ps[u] != -1)
+                    continue;  // marked by a lower seed since
+                  const uint32_t r = pr[u];
+                  if (r != RES_FREE && set_has<CSET_BITS>(sh.cset, r))
+                    continue;  // in a plane this sweep committed
+                  if (wanted_by((uint32_t)pp[u]) < (uint32_t)tid)
+                    continue;  // a lower tiny seed of this segment marks it
+                  if (r != RES_FREE && gset_find(sh.gkey, sh.gval, r) < (uint32_t)tid) conf = true;  // depends on that grower
+                  else g_bad = true;
+                }
+              }
             }
           }
         }
-        for (int k = tid; k < HT; k += SWEEP_T) {  // (a list of the used slots would need one contended counter)
-          hkeys[k] = 0xffffffffu;
-          hvals[k] = 0xffffffffu;
+        if (conf) {
+          atomicMin(&sh.first_conf, tid);
+          atomicAdd(&sh.n_conf, 1);
         }
-        // (no fence: every reader of these marks is in this block, and the barrier orders the block's accesses)
-        if (tid == seg_end && valid) sh.last_open = i;  // first seed of the batch that is not finished
-        __syncthreads();
-        done = seg_end;
-        if (done < n_eval) F = sh.last_open;
-        t_fast += gtimer() - ti1;
       }
-      if (done < n_eval && !stop && state_changed) {
-        // ---- refresh: the states of what this thread already knows (one load level) ----
-        if (valid && tid >= done) {
-          const int32_t st_s = __ldcg(A.state + s);
-          int32_t stj[KM];
+      __syncthreads();
+      const int seg_end = sh.first_conf < seg_hi ? sh.first_conf : seg_hi;  // > done: the first one has nobody below it
+      const int n_conf = sh.n_conf;
+      // ---- tiny seeds: a higher transaction that holds a point which is about to be marked is void ----
+      if (in_seg && tiny && tid < seg_end && held_hi) {
+#pragma unroll
+        for (int j = 1; j < KM; ++j)
+          if ((held_hi >> j) & 1u) doom_now(rs[j]);
+      }
+      const bool g_here = first_g < seg_end;  // (uniform)
+      int first_fail = SWEEP_T;
+      if (g_here) {
+        __syncthreads();
+        // ---- growers decide ----
+        if (in_seg && glook && tid < seg_end) {
+          bool ok = slot >= 0 && g_ready && !g_bad && !g_doom0;
+          if (ok) ok = ((volatile int*)&sh.dset_over)[0] ? ((volatile uint8_t*)A.doom)[i] == 0 : !set_has<DSET_BITS>(sh.dset, me);
+          if (ok && g_len > A.th_count && sh.n_cset >= CSET / 2) ok = false;  // (the set is sized for every slot: never)
+          if (!ok) atomicMin(&sh.first_fail, tid);
+          n_pendsum += (uint32_t)g_npend;
+        }
+        __syncthreads();
+        first_fail = sh.first_fail;
+      }
+      const bool failed = first_fail < SWEEP_T;  // (only threads below seg_end decide: first_fail < seg_end then)
+      const int seg_end2 = failed ? first_fail : seg_end;
+      // ---- commit ----
+      if (in_seg && glook && tid < seg_end2) {
+        Slot& sl = S.slots[slot];
+        if (g_len > A.th_count) {  // :199-202
+          const unsigned long long off = atomicAdd(&sh.c_off, (unsigned long long)g_len);
+          const unsigned long long pl = atomicAdd(&sh.c_pl, 1ull);
+          if ((int64_t)(off + g_len) > A.pool_cap - A.n - 2 || (int64_t)pl >= A.planes_cap) {
+            A.ctl[CTL_ERR] = 2;
+          } else {
+            PlaneRec r;
+            r.seed = (int32_t)i; r.pad = 0;
+            r.off = (int64_t)off; r.len = g_len;
+            r.nrm[0] = sl.t.m.mn0; r.nrm[1] = sl.t.m.mn1; r.nrm[2] = sl.t.m.mn2;
+            r.ctr[0] = sl.t.m.mc0; r.ctr[1] = sl.t.m.mc1; r.ctr[2] = sl.t.m.mc2; r.pad2 = 0;
+            A.planes[pl] = r;
+            sl.pool_off = (int64_t)off;
+            sl.status = ST_COMMIT;
+            atomicAdd(&sh.n_cset, 1);
+            set_insert<CSET_BITS>(sh.cset, me);
+          }
+        } else {  // roll back (:203-209): nothing persists; the reservations are dropped by the next release pass
+          sl.status = ST_ROLLED;
+        }
+        atomicAdd(&sh.c_steps, sl.steps);
+        atomicAdd(&sh.c_tx, 1ull);
+        ++n_grow;
+      }
+      {
+        // orphan marks of the tiny transactions (:233 then :238-239).  Only the owner mark is on the sweeper's path;
+        // what the mark means for others (reservation void, alive bit, seed of a waiting grower taken) is logged and
+        // applied by a parallel kernel after the sweep.
+        const bool commit = in_seg && tiny && tid < seg_end2;
+        if (commit) ++ntiny;
+        const int nw = commit ? __popc(want) : 0;
+        int wincl = nw;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL_MASK, wincl, o);
+          if (lane >= o) wincl += v;
+        }
+        const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
+        unsigned long long lbase = 0;
+        if (wtot > 0) {
+          if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
+          lbase = __shfl_sync(FULL_MASK, lbase, 0);
+        }
+        if (nw) {
+          unsigned long long pos = lbase + (unsigned long long)(wincl - nw);
 #pragma unroll
           for (int j = 1; j < KM; ++j) {
-            stj[j] = 0;
-            if (ids[j] >= 0) stj[j] = __ldcg(A.state + ids[j]);
-          }
-          slot = __ldcg(A.slotof + i);
-          live = st_s == -1;
-          want = 0;
-          grower = false;
-          if (live) {
-#pragma unroll
-            for (int j = 1; j < KM; ++j)
-              if (ids[j] >= 0 && stj[j] == -1) want |= 1u << j;
-            grower = __popc(want) == K - 1;
+            if (!((want >> j) & 1u))
+              continue;
+            const int32_t id = ids[j];
+            atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, me);  // the lower seed owns a shared point
+            if (pos < S.marklog_cap) S.marklog[pos] = make_uint2((uint32_t)id, me);
+            ++pos;
           }
         }
+      }
+      if (failed && tid == first_fail) {
+        // the sweep stops here: still growing (the head), no slot yet (the scout gives it one), or void (released next
+        // round, then re-run)
+        sh.last_open = i;
+        if (slot < 0 || S.slots[slot].status != ST_RUNNING) S.sc[SC_STUCK] = 1;
+        if (g_ready && g_bad) {
+          A.doom[i] = 1;
+          atomicAdd(&S.sc[SC_ATFAIL], 1ull);
+        }
+      }
+      for (int k = tid; k < HT; k += SWEEP_T) {  // (a list of the used slots would need one contended counter)
+        hkeys[k] = 0xffffffffu;
+        hvals[k] = 0xffffffffu;
+      }
+      if (have_g)
+        for (int k = tid; k < GSET; k += SWEEP_T) {
+          sh.gkey[k] = 0xffffffffu;
+          sh.gval[k] = (uint32_t)SWEEP_T;
+        }
+      // (no fence: every reader of these marks is in this block, and the barrier orders the block's accesses)
+      if (!failed && tid == seg_end2 && valid) sh.last_open = i;  // first seed of the batch that is not finished
+      __syncthreads();
+      if (!failed && seg_end < seg_hi && n_conf * 8 > seg_hi - done) serial = true;  // conflicts are dense here (scan order)
+      done = seg_end2;
+      if (failed) {
+        stop = true;
+        F = sh.last_open;
+      } else if (done < n_eval) {
+        F = sh.last_open;
+        // ---- refresh: the states of what this thread already knows (one load level) ----
+        if (valid && tid >= done) classify();
       }
     }
     if (!stop) {  // the whole batch is done
@@ -824,20 +1169,27 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
 
   if (tid == 0) {
     S.sc[SC_T_FRONT] += t_front;
-    S.sc[SC_T_SLOW] += t_slow;
-    S.sc[SC_T_FAST] += t_fast;
-    S.sc[SC_N_SLOW] += n_slow;
+    S.sc[SC_N_SLOW] += n_sub;
+    S.sc[SC_N_SER] += n_ser;
     A.ctl[CTL_FRONTIER] = (unsigned long long)F;
+    A.ctl[CTL_POOL] = sh.c_off;
+    A.ctl[CTL_PLANES] = sh.c_pl;
+    A.ctl[CTL_STEPS] += sh.c_steps;
+    A.ctl[CTL_TX] += sh.c_tx;
     S.sc[SC_SWEEP_ITERS] += iters;
     S.sc[SC_SWEEP_NS] += gtimer() - t_begin;
   }
   // tiny transactions committed: one atomic per warp
   for (int o = 16; o; o >>= 1) ntiny += __shfl_down_sync(FULL_MASK, ntiny, o);
+  for (int o = 16; o; o >>= 1) n_grow += __shfl_down_sync(FULL_MASK, n_grow, o);
+  for (int o = 16; o; o >>= 1) n_pendsum += __shfl_down_sync(FULL_MASK, n_pendsum, o);
   if (lane == 0 && ntiny) {
-    atomicAdd(&S.sc[SC_TINY], ntiny);
-    atomicAdd(&A.ctl[CTL_TX], ntiny);
-    atomicAdd(&A.ctl[CTL_STEPS], ntiny);
+    atomicAdd(&S.sc[SC_TINY], (unsigned long long)ntiny);
+    atomicAdd(&A.ctl[CTL_TX], (unsigned long long)ntiny);
+    atomicAdd(&A.ctl[CTL_STEPS], (unsigned long long)ntiny);
   }
+  if (lane == 0 && n_grow) atomicAdd(&S.sc[SC_N_GROW], (unsigned long long)n_grow);
+  if (lane == 0 && n_pendsum) atomicAdd(&S.sc[SC_T_SLOW], (unsigned long long)n_pendsum);
 }
 
 __global__ void __launch_bounds__(TPB) spec_alive_init_kernel(uint32_t* alive, int64_t n, int64_t n_alloc_words)
@@ -882,8 +1234,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   int64_t pages = (3 * n) / PAGE_SIZE + 2 * S.G;
   if (pages > 32768) pages = 32768;
   S.n_pool_pages = (uint32_t)pages;
+  if (S.G > CSET / 2) S.G = CSET / 2;  // every plane a sweep accepts names its seed in the sweeper's set
   const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 8 + 256;
-  RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + 64));
+  const size_t pend_bytes = (size_t)S.G * PEND_CAP * 4;
+  RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + pend_bytes + 64));
   // flag[CMAX+4] | gmask[n] | slotof[n] | atby[n] | alive[words] | doom[n] | hinted[n]
   const int64_t alive_words = (n + 31) / 32 + SWEEP_WORDS + 4;
   RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 14 + (size_t)alive_words * 4 + 256));
@@ -893,6 +1247,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.free_ids = reinterpret_cast<uint32_t*>(S.slots + S.G);
   S.ptabs = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(c->g_tx.p) + slot_bytes);
   S.pool.free_pages = S.ptabs + (size_t)S.G * MAX_PAGES_PER_SLOT;
+  S.pend = reinterpret_cast<int32_t*>(S.pool.free_pages + pages);
   S.pool.stack_pages = dptr<int2>(c->g_queue);
   S.pool.list_pages = reinterpret_cast<int32_t*>(S.pool.stack_pages + (size_t)pages * PAGE_SIZE);
   S.pool.at_pages = S.pool.list_pages + (size_t)pages * PAGE_SIZE;
@@ -922,10 +1277,9 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     spec_alive_init_kernel<<<(unsigned)ceil_div64(alive_words, TPB), TPB, 0, c->stream>>>(S.alive, n, alive_words);
     KLAUNCH_CHECK(c);
   }
-  const size_t sweep_smem = (size_t)HT * 8;
   if (!c->attr_sweep_set) {
-    CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
-    CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
+    CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<16>::SMEM));
+    CU_CHECK(c, cudaFuncSetAttribute(spec_sweep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<32>::SMEM));
     c->attr_sweep_set = true;
   }
 
@@ -964,15 +1318,21 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       cudaEventRecord(pe[2], c->stream);
       spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget);
       KLAUNCH_CHECK(c);
+      spec_preverify_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
+      spec_preverify_done_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
     }
     cudaEventRecord(pe[3], c->stream);
-    if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
-    else spec_sweep_kernel<32><<<1, SWEEP_T, sweep_smem, c->stream>>>(S);
+    if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, SweepCfg<16>::SMEM, c->stream>>>(S);
+    else spec_sweep_kernel<32><<<1, SWEEP_T, SweepCfg<32>::SMEM, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     spec_apply_marks_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
-    spec_apply_planes_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
-    KLAUNCH_CHECK(c);
+    if (rounds > 0) {  // (the first sweep runs before any slot exists)
+      spec_apply_commits_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
+    }
     spec_reset_log_kernel<<<1, 1, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     cudaEventRecord(pe[4], c->stream);
@@ -1028,8 +1388,8 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   c->tm.grow_slice_ms = pt[2];
   c->tm.grow_sweep_ms = pt[3];
   if (dbg)
-    fprintf(stderr, "[bseg] sweeper: front %.1f ms, slow path %.1f ms (%llu), fast path %.1f ms\n", ctl[8 + SC_T_FRONT] / 1e6,
-            ctl[8 + SC_T_SLOW] / 1e6, ctl[8 + SC_N_SLOW], ctl[8 + SC_T_FAST] / 1e6);
+    fprintf(stderr, "[bseg] sweeper: front %.1f ms of %.1f ms (%llu segments, %llu of them serial stretches, %llu growers decided with %llu open assumed-taken points), %llu batches\n",
+            ctl[8 + SC_T_FRONT] / 1e6, ctl[8 + SC_SWEEP_NS] / 1e6, ctl[8 + SC_N_SLOW], ctl[8 + SC_N_SER], ctl[8 + SC_N_GROW], ctl[8 + SC_T_SLOW], ctl[8 + SC_SWEEP_ITERS]);
   c->tm.grow_rounds = rounds;
   c->tm.grow_wasted_steps = (int64_t)ctl[8 + SC_WASTED];
   c->tm.grow_sweep_iters = (int64_t)ctl[8 + SC_SWEEP_ITERS];
