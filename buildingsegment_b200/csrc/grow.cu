@@ -348,6 +348,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.slotof = nullptr;
   A.atby = nullptr;
   A.stop_flag = nullptr;
+  A.slice_min_ns = 0;
   A.frontier = 0;
   {
     const char* gf = getenv("BSEG_GROW_FLAGS");  // tuning switches of the step engine (grow.cuh GF_*)

@@ -28,7 +28,8 @@ struct GrowArgs {
   uint8_t* doom;     // 1 = a lower transaction took a point this one holds, or its seed
   int32_t* slotof;   // grower slot attached to this seed, -1 = none
   // speculative slices: set by the head slot when it finishes, polled by the others
-  unsigned long long* stop_flag;
+  unsigned long long* stop_flag;  // 1 = stop now; 2 = the head is done: stop once the slice is slice_min_ns old
+  unsigned long long slice_min_ns;  // (stop_flag[1] = globaltimer at the start of the slice)
   int64_t frontier;  // first unresolved seed at slice start (everything below is committed)
   int flags;         // tuning switches (BSEG_GROW_FLAGS): see GF_*
   const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
@@ -238,6 +239,23 @@ __device__ __forceinline__ void prefetch_l2(const void* p)
 __device__ __forceinline__ void prefetch_l1(const void* p)
 {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// speculative slices: the head finishing ends the slice for everybody -- but not before the slice is slice_min_ns old
+// (a round has a fixed cost: release, scout, sweep; several short planes in a row share one)
+__device__ __forceinline__ bool slice_over(const GrowArgs& A)
+{
+  const unsigned long long st = *(volatile unsigned long long*)A.stop_flag;
+  if (st == 0)
+    return false;
+  if (st == 1)
+    return true;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (now - ((volatile unsigned long long*)A.stop_flag)[1] < A.slice_min_ns)
+    return false;
+  *(volatile unsigned long long*)A.stop_flag = 1ull;
+  return true;
 }
 
 // ---- list / frame storage ---------------------------------------------------------------------------
@@ -565,7 +583,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
         out = TX_DOOMED;
         break;
       }
-      if (*(volatile unsigned long long*)A.stop_flag) break;  // the head finished: let the sweeper commit
+      if (slice_over(A)) break;  // the head finished: let the sweeper commit
     }
   }
   steps_out += steps;
@@ -744,7 +762,7 @@ __device__ __forceinline__ unsigned long long tx_skip_noops(const GrowArgs& A, S
       end = f.y;
     }
     const uint8_t doomed = ((volatile uint8_t*)A.doom)[seed_i];
-    const unsigned long long stop = *(volatile unsigned long long*)A.stop_flag;
+    const bool stop = slice_over(A);
     const int len = end - cur;
     int incl = len;
 #pragma unroll
@@ -1046,7 +1064,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
         out = TX_DOOMED;
         break;
       }
-      if (*(volatile unsigned long long*)A.stop_flag) break;  // the head finished: let the sweeper commit
+      if (slice_over(A)) break;  // the head finished: let the sweeper commit
     }
   }
   if (out == TX_FINISHED && !t.model_exact) {  // what the plane reports is the reference's model

@@ -54,7 +54,7 @@ enum { ST_FREE = 0, ST_RUNNING = 1, ST_FINISHED = 2, ST_DEAD = 3, ST_RELEASING =
 enum {
   SC_NFREE = 0,       // free slots
   SC_NCAND = 1,       // candidates of the window (scan total)
-  SC_STOP = 2,        // head finished: slices end
+  SC_STOP = 44,       // head finished: slices end (1 = now, 2 = once the slice is old enough); [45] = start of the slice (globaltimer)
   SC_HEAD_SLOT = 3,   // slot of the seed at the frontier + 1 (0 = none)
   SC_WASTED = 4,      // Broad steps of released slots
   SC_SWEEP_ITERS = 5,
@@ -68,6 +68,7 @@ enum {
   SC_SWEEP_NS = 13,   // time inside the sweeper
   SC_ATFAIL = 14,     // finished slots whose assumed-taken points were not all taken
   SC_NLOG = 19,       // entries of the mark log
+  SC_SWEEP_PH = 46,   // [46, 53): sweeper sub-step phases (ns, thread 0)
   SC_N_SER = 22,      // serial stretches of the sweeper
   SC_N_GROW = 23,     // growers the sweeper decided
   SC_HEAD_ITERS = 21, // warp iterations of the head slot (two-node engine: <= steps)
@@ -109,7 +110,7 @@ struct SpecArgs {
   uint32_t* free_ids;
   uint8_t* hinted;    // [n] original index space: this tiny transaction has published hints
   uint32_t* alive;    // [ceil(n/32)] original index space: bit = the point may still be free (filter)
-  int32_t* pend;      // [G][PEND_CAP] see Slot::n_pend
+  int2* pend;         // [G][PEND_CAP] see Slot::n_pend: (point, who held it when the slot was verified)
   uint2* marklog;     // (point, seed) of the orphan marks the sweeper made this round: side effects applied later
   unsigned long long marklog_cap;
   unsigned long long* sc;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(TPB) spec_preverify_kernel(SpecArgs S)
     const int32_t pt = st.get_at(k);
     if (__ldcg(A.state + pt) == -1) {
       const int idx = atomicAdd(&sl.n_pend, 1);
-      if (idx < PEND_CAP) S.pend[(size_t)g * PEND_CAP + idx] = pt;
+      if (idx < PEND_CAP) S.pend[(size_t)g * PEND_CAP + idx] = make_int2(pt, (int)__ldcg(A.res + pt));
     }
   }
   if (bad) A.doom[i] = 1;
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t F,
 __global__ void spec_pop_free_kernel(SpecArgs S, int64_t F)
 {
   S.sc[SC_NFREE] -= S.sc[SC_NASSIGN];
+  S.sc[SC_STOP + 1] = gtimer();  // the slice starts
   const int32_t g = F < S.A.n ? S.A.slotof[F] : -1;
   S.sc[SC_HEAD_SLOT] = (unsigned long long)(g + 1);
 }
@@ -499,7 +501,11 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
     sl.status = out == TX_RUNNING ? ST_RUNNING : (out == TX_FINISHED ? ST_FINISHED : ST_DEAD);
     // the head sets the pace: when it finishes OR has used its budget the slice is over for everybody
     // (a slot that keeps running after the head has stopped only delays the sweeper)
-    if (is_head) *(volatile unsigned long long*)&S.sc[SC_STOP] = 1ull;
+    if (is_head) {
+      // ... unless it was a short one: then the others run on until the slice is slice_min_ns old
+      const bool early = out != TX_RUNNING && gtimer() - S.sc[SC_STOP + 1] < A.slice_min_ns;
+      *(volatile unsigned long long*)&S.sc[SC_STOP] = early ? 2ull : 1ull;
+    }
   }
 }
 
@@ -533,6 +539,9 @@ struct SweepShared {
   int first_g;        // lowest unfinished grower-looking thread
   int ser_end, ser_ins;  // serial stretch: first thread it did not reach, points in the taken set
   int n_cset, n_dset, dset_over;
+  int n_items;
+  unsigned long long tph[12], tlast;  // BSEG_DEBUG: thread 0's clock per phase of the sub-step
+  unsigned long long log_base;
   int n_conf;         // threads of the segment in conflict
   int sp_big, sp_bad, sp_slot;
   unsigned long long c_off, c_pl, c_steps, c_tx;
@@ -592,9 +601,10 @@ __device__ __forceinline__ uint32_t gset_find(const uint32_t* gkey, const uint32
 
 template <int KM>
 struct SweepCfg {
-  static constexpr int HT_BITS = 14;  // hash table slots (keys + vals = 128 KB of shared memory)
+  static constexpr int ITEMS = 4096;  // wants of the tiny seeds of one segment (flat list: 12 B each)
+  static constexpr int HT_BITS = 13;  // hash table slots of a segment (keys + vals = 64 KB of shared memory): load <= 0.5
   static constexpr int HT = 1 << HT_BITS;
-  static constexpr size_t SMEM = (size_t)HT * 8;
+  static constexpr size_t SMEM = (size_t)HT * 8 + (size_t)ITEMS * 12 + (size_t)SWEEP_T * 4;
 };
 
 // the sequential authority: walks the seeds from the frontier in index order
@@ -606,7 +616,14 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   extern __shared__ uint32_t smem_u32[];
   uint32_t* hkeys = smem_u32;        // [HT] point, 0xffffffff = empty
   uint32_t* hvals = smem_u32 + HT;   // [HT] lowest thread of the segment that wants it
+  constexpr int ITEMS = SweepCfg<KM>::ITEMS;
+  uint32_t* it_id = smem_u32 + 2 * HT;             // [ITEMS] flat list of the segment's wants: point ...
+  uint32_t* it_r = it_id + ITEMS;                  // ... its reservation as gathered ...
+  uint32_t* sh_me = it_r + ITEMS;                  // [SWEEP_T] seed of every thread
+  uint16_t* it_tid = reinterpret_cast<uint16_t*>(sh_me + SWEEP_T);  // ... the thread that wants it ...
+  uint16_t* it_slot = it_tid + ITEMS;              // ... and where it sits in the hash table
   __shared__ SweepShared sh;
+  __shared__ int32_t tile[KM][32];  // serial stretches: id columns of the warp whose turn it is
   const GrowArgs& A = S.A;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -634,8 +651,10 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
     sh.c_pl = A.ctl[CTL_PLANES];
     sh.c_steps = 0;
     sh.c_tx = 0;
+    for (int k = 0; k < 12; ++k) sh.tph[k] = 0;
   }
   __syncthreads();
+#define PHASE(k) if (timing && tid == 0) { const unsigned long long now_ = gtimer(); sh.tph[k] += now_ - sh.tlast; sh.tlast = now_; }
   unsigned long long t_front = 0;  // (thread 0 only)
   uint32_t n_sub = 0, n_grow = 0, n_ser = 0, n_pendsum = 0;
   bool stop = false;
@@ -780,6 +799,15 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         g_len = sl.t.len;
         g_npend = sl.n_pend;
         g_doom0 = ((volatile uint8_t*)A.doom)[i] != 0;
+        if (g_ready) {  // what the decision and the commit read later: towards L1 now
+          prefetch_l1(&sl.t.m);
+          prefetch_l1(reinterpret_cast<const char*>(&sl.t.m) + 64);
+          if (g_npend > 0) {
+            const char* pp = reinterpret_cast<const char*>(&S.pend[(size_t)slot * PEND_CAP]);
+            prefetch_l1(pp);
+            if (g_npend > 16) prefetch_l1(pp + 128);
+          }
+        }
       }
       classify();
     }
@@ -807,7 +835,16 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         // ---- serial stretch ----
         for (int wi = done >> 5; wi <= ((n_eval - 1) >> 5); ++wi) {
           if ((tid >> 5) == wi && sh.ser_end == n_eval) {
-            const bool mine = act && live;
+            bool mine = act && live;
+            if (mine && set_has<HT_BITS>(hkeys, s)) {  // marked by an earlier warp of the stretch (:185)
+              mine = false;
+              if (slot >= 0) A.doom[i] = 1;
+            }
+            if (mine) {
+#pragma unroll
+              for (int j = 1; j < KM; ++j) tile[j][lane] = ids[j];
+            }
+            __syncwarp();
             uint32_t todo = __ballot_sync(FULL_MASK, mine);
             int n_ins = sh.ser_ins;
             const int nw = mine ? __popc(want) : 0;  // log space: one entry per want (unused ones are voided)
@@ -833,12 +870,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
               const int slot_l = __shfl_sync(FULL_MASK, slot, l);
               const bool glook_l = __shfl_sync(FULL_MASK, (int)glook, l) != 0;
               const bool w = lane >= 1 && lane < KM && ((want_l >> lane) & 1u);
-              int32_t myid = -1;  // lane j looks after neighbour column j of the seed
-#pragma unroll
-              for (int j = 1; j < KM; ++j) {
-                const int32_t v = __shfl_sync(FULL_MASK, ids[j], l);
-                if (lane == j) myid = v;
-              }
+              const int32_t myid = w ? tile[lane][l] : -1;  // lane j looks after neighbour column j of the seed
               const bool dead = set_has<HT_BITS>(hkeys, s_l);  // marked by a lower seed of the stretch (:185)
               if (!dead && glook_l) {
                 // still a grower at its turn?  (a neighbour may have been marked in the stretch)
@@ -898,6 +930,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         continue;
       }
       force_par = false;
+      if (timing && tid == 0) sh.tlast = gtimer();
 
       // a slot whose seed is not a grower at its turn is void (the state only gets more taken: it never will be)
       if (act && slot >= 0 && !glook) A.doom[i] = 1;
@@ -939,29 +972,31 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       }
       int incl = wsum;  // inclusive prefix of wants in index order
       for (int w = 0; w < (tid >> 5); ++w) incl += sh.warp_sum[w];
-      if (tiny && incl > HT / 2) atomicMin(&sh.first_over, tid);
+      if (tiny && incl > ITEMS) atomicMin(&sh.first_over, tid);
+      if (valid) sh_me[tid] = me;
       __syncthreads();
+      PHASE(0)
       int seg_hi = sh.first_over < n_eval ? sh.first_over : n_eval;
       if (seg_hi <= done) seg_hi = done + 1;  // a single seed always fits (K-1 <= 31 wants)
       const int first_g = sh.first_g;
       const bool in_seg = act && tid < seg_hi;
+      const bool have_g = first_g < seg_hi;  // grower-looking seeds in the segment
+      // ---- the wants of the tiny seeds as one flat list in thread order (balanced work for the passes below):
+      //      (point, its reservation as gathered, thread) ----
+      const int my_off = incl - (tiny ? __popc(want) : 0);
       if (in_seg && tiny && want) {
+        int pos = my_off;
 #pragma unroll
         for (int j = 1; j < KM; ++j) {
           if (!((want >> j) & 1u))
             continue;
-          const uint32_t id = (uint32_t)ids[j];
-          uint32_t h = (id * 2654435761u) >> (32 - HT_BITS);
-          for (;;) {
-            const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
-            if (old == 0xffffffffu || old == id) {
-              atomicMin(hvals + h, (uint32_t)tid);
-              break;
-            }
-            h = (h + 1) & (HT - 1);
-          }
+          it_id[pos] = (uint32_t)ids[j];
+          it_r[pos] = rs[j];
+          it_tid[pos] = (uint16_t)tid;
+          ++pos;
         }
       }
+      if (tid == seg_hi - 1) sh.n_items = incl;  // wants of the tiny seeds below seg_hi
       if (in_seg && glook) {
         uint32_t h = (me * 2654435761u) >> (32 - GSET_BITS);
         for (;;) {
@@ -974,6 +1009,25 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         }
       }
       __syncthreads();
+      PHASE(1)
+      const int n_items = sh.n_items;
+      if (tid == 0 && n_items > 0) sh.log_base = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)n_items);  // (read after two more barriers)
+      // ---- every want into the hash table: point -> lowest thread of the segment that wants it ----
+      for (int k = tid; k < n_items; k += SWEEP_T) {
+        const uint32_t id = it_id[k];
+        uint32_t h = (id * 2654435761u) >> (32 - HT_BITS);
+        for (;;) {
+          const uint32_t old = atomicCAS(hkeys + h, 0xffffffffu, id);
+          if (old == 0xffffffffu || old == id) {
+            atomicMin(hvals + h, (uint32_t)it_tid[k]);
+            it_slot[k] = (uint16_t)h;
+            break;
+          }
+          h = (h + 1) & (HT - 1);
+        }
+      }
+      __syncthreads();
+      PHASE(2)
       // lowest thread of the segment that wants point p (SWEEP_T: nobody)
       auto wanted_by = [&](uint32_t p) -> uint32_t {
         uint32_t h = (p * 2654435761u) >> (32 - HT_BITS);
@@ -986,52 +1040,75 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           h = (h + 1) & (HT - 1);
         }
       };
-      const bool have_g = first_g < seg_hi;  // grower-looking seeds in the segment
       // ---- conflicts with lower seeds of the segment ----
+      if (have_g) {  // a wanted point that a lower grower-looking seed of the segment holds
+        for (int k = tid; k < n_items; k += SWEEP_T) {
+          const uint32_t r = it_r[k];
+          const uint32_t t = it_tid[k];
+          if (r != RES_FREE && r < sh_me[t] && gset_find(sh.gkey, sh.gval, r) < t) {
+            atomicMin(&sh.first_conf, (int)t);
+            atomicAdd(&sh.n_conf, 1);
+          }
+        }
+      }
       bool g_bad = false;  // grower-looking: an assumed-taken point is free at its turn
       if (in_seg && live) {
         bool conf = wanted_by(s) < (uint32_t)tid;
-        if (have_g) {
-          if (rs_self != RES_FREE && rs_self < me) conf |= gset_find(sh.gkey, sh.gval, rs_self) < (uint32_t)tid;
-#pragma unroll
-          for (int j = 1; j < KM; ++j)
-            if ((held_lo >> j) & 1u) conf |= gset_find(sh.gkey, sh.gval, rs[j]) < (uint32_t)tid;
-        }
+        if (have_g && rs_self != RES_FREE && rs_self < me) conf |= gset_find(sh.gkey, sh.gval, rs_self) < (uint32_t)tid;
         if (glook) {
 #pragma unroll
           for (int j = 1; j < KM; ++j)
-            if ((want >> j) & 1u) conf |= wanted_by((uint32_t)ids[j]) < (uint32_t)tid;
+            if ((want >> j) & 1u) {
+              conf |= wanted_by((uint32_t)ids[j]) < (uint32_t)tid;
+              if ((held_lo >> j) & 1u) conf |= gset_find(sh.gkey, sh.gval, rs[j]) < (uint32_t)tid;
+            }
           if (g_ready) {
             if (pend_done) {
               g_bad = pend_bad;
             } else if (g_npend > PEND_CAP) {
               conf |= tid != done;  // the block walks its list when it is the first of a segment
             } else {
-              for (int k0 = 0; k0 < g_npend; k0 += 4) {  // (all loads of a trip in flight together)
-                int32_t pp[4], ps[4];
-                uint32_t pr[4];
+              // open assumptions (free when the sweep began): usually the holder recorded at verification has committed
+              // a plane in this sweep or a lower tiny seed of the segment marks the point (shared memory answers);
+              // global memory only for the others, all loads of a trip in flight together
+              for (int k0 = 0; k0 < g_npend; k0 += 8) {
+                int2 pe[8];
+                uint32_t need = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pp[u] = k0 + u < g_npend ? S.pend[(size_t)slot * PEND_CAP + k0 + u] : -1;
+                for (int u = 0; u < 8; ++u) pe[u] = k0 + u < g_npend ? S.pend[(size_t)slot * PEND_CAP + k0 + u] : make_int2(-1, -1);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  ps[u] = 0;
-                  pr[u] = RES_FREE;
-                  if (pp[u] >= 0) {
-                    ps[u] = __ldcg(A.state + pp[u]);
-                    pr[u] = __ldcg(A.res + pp[u]);
-                  }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (pp[u] < 0 || ps[u] != -1)
-                    continue;  // marked by a lower seed since
-                  const uint32_t r = pr[u];
+                for (int u = 0; u < 8; ++u) {
+                  if (pe[u].x < 0)
+                    continue;
+                  const uint32_t r = (uint32_t)pe[u].y;
                   if (r != RES_FREE && set_has<CSET_BITS>(sh.cset, r))
                     continue;  // in a plane this sweep committed
-                  if (wanted_by((uint32_t)pp[u]) < (uint32_t)tid)
+                  if (wanted_by((uint32_t)pe[u].x) < (uint32_t)tid)
                     continue;  // a lower tiny seed of this segment marks it
-                  if (r != RES_FREE && gset_find(sh.gkey, sh.gval, r) < (uint32_t)tid) conf = true;  // depends on that grower
-                  else g_bad = true;
+                  need |= 1u << u;
+                }
+                if (need) {
+                  int32_t ps[8];
+                  uint32_t pr[8];
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    ps[u] = 0;
+                    pr[u] = RES_FREE;
+                    if ((need >> u) & 1u) {
+                      ps[u] = __ldcg(A.state + pe[u].x);
+                      pr[u] = __ldcg(A.res + pe[u].x);
+                    }
+                  }
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    if (!((need >> u) & 1u) || ps[u] != -1)
+                      continue;  // marked by a lower seed since
+                    const uint32_t r = pr[u];
+                    if (r != RES_FREE && set_has<CSET_BITS>(sh.cset, r))
+                      continue;
+                    if (r != RES_FREE && gset_find(sh.gkey, sh.gval, r) < (uint32_t)tid) conf = true;  // depends on that grower
+                    else g_bad = true;
+                  }
                 }
               }
             }
@@ -1043,17 +1120,18 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         }
       }
       __syncthreads();
+      PHASE(3)
       const int seg_end = sh.first_conf < seg_hi ? sh.first_conf : seg_hi;  // > done: the first one has nobody below it
       const int n_conf = sh.n_conf;
-      // ---- tiny seeds: a higher transaction that holds a point which is about to be marked is void ----
-      if (in_seg && tiny && tid < seg_end && held_hi) {
-#pragma unroll
-        for (int j = 1; j < KM; ++j)
-          if ((held_hi >> j) & 1u) doom_now(rs[j]);
-      }
       const bool g_here = first_g < seg_end;  // (uniform)
       int first_fail = SWEEP_T;
       if (g_here) {
+        // ---- tiny seeds: a higher transaction that holds a point which is about to be marked is void ----
+        for (int k = tid; k < n_items; k += SWEEP_T) {
+          const uint32_t r = it_r[k];
+          const uint32_t t = it_tid[k];
+          if ((int)t < seg_end && r != RES_FREE && r > sh_me[t]) doom_now(r);
+        }
         __syncthreads();
         // ---- growers decide ----
         if (in_seg && glook && tid < seg_end) {
@@ -1065,6 +1143,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         }
         __syncthreads();
         first_fail = sh.first_fail;
+        PHASE(4)
       }
       const bool failed = first_fail < SWEEP_T;  // (only threads below seg_end decide: first_fail < seg_end then)
       const int seg_end2 = failed ? first_fail : seg_end;
@@ -1095,35 +1174,30 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         atomicAdd(&sh.c_tx, 1ull);
         ++n_grow;
       }
+      if (in_seg && tiny && tid < seg_end2) ++ntiny;
       {
         // orphan marks of the tiny transactions (:233 then :238-239).  Only the owner mark is on the sweeper's path;
         // what the mark means for others (reservation void, alive bit, seed of a waiting grower taken) is logged and
-        // applied by a parallel kernel after the sweep.
-        const bool commit = in_seg && tiny && tid < seg_end2;
-        if (commit) ++ntiny;
-        const int nw = commit ? __popc(want) : 0;
-        int wincl = nw;
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(FULL_MASK, wincl, o);
-          if (lane >= o) wincl += v;
-        }
-        const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
-        unsigned long long lbase = 0;
-        if (wtot > 0) {
-          if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
-          lbase = __shfl_sync(FULL_MASK, lbase, 0);
-        }
-        if (nw) {
-          unsigned long long pos = lbase + (unsigned long long)(wincl - nw);
-#pragma unroll
-          for (int j = 1; j < KM; ++j) {
-            if (!((want >> j) & 1u))
-              continue;
-            const int32_t id = ids[j];
-            atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, me);  // the lower seed owns a shared point
-            if (pos < S.marklog_cap) S.marklog[pos] = make_uint2((uint32_t)id, me);
-            ++pos;
+        // applied by a parallel kernel after the sweep.  The list is in thread order: the marks of the committed seeds
+        // are a prefix of it.  In a segment without growers the higher holders are doomed here.
+        const unsigned long long lbase = sh.log_base;
+        for (int k = tid; k < n_items; k += SWEEP_T) {
+          const uint32_t id = it_id[k];
+          const uint32_t t = it_tid[k];
+          const uint32_t seed = sh_me[t];
+          const bool commit = (int)t < seg_end2;  // (thread order: the committed seeds' wants are a prefix of the list)
+          if (commit) {
+            atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, seed);  // the lower seed owns a shared point
+            if (!g_here) {
+              const uint32_t r = it_r[k];
+              if (r != RES_FREE && r > seed) A.doom[r] = 1;
+            }
           }
+          const unsigned long long pos = lbase + (unsigned long long)k;
+          if (pos < S.marklog_cap) S.marklog[pos] = make_uint2(commit ? id : 0xffffffffu, seed);
+          const int h = it_slot[k];  // the table is emptied item by item
+          hkeys[h] = 0xffffffffu;
+          hvals[h] = 0xffffffffu;
         }
       }
       if (failed && tid == first_fail) {
@@ -1136,10 +1210,6 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           atomicAdd(&S.sc[SC_ATFAIL], 1ull);
         }
       }
-      for (int k = tid; k < HT; k += SWEEP_T) {  // (a list of the used slots would need one contended counter)
-        hkeys[k] = 0xffffffffu;
-        hvals[k] = 0xffffffffu;
-      }
       if (have_g)
         for (int k = tid; k < GSET; k += SWEEP_T) {
           sh.gkey[k] = 0xffffffffu;
@@ -1148,6 +1218,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
       // (no fence: every reader of these marks is in this block, and the barrier orders the block's accesses)
       if (!failed && tid == seg_end2 && valid) sh.last_open = i;  // first seed of the batch that is not finished
       __syncthreads();
+      PHASE(5)
       if (!failed && seg_end < seg_hi && n_conf * 8 > seg_hi - done) serial = true;  // conflicts are dense here (scan order)
       done = seg_end2;
       if (failed) {
@@ -1157,6 +1228,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         F = sh.last_open;
         // ---- refresh: the states of what this thread already knows (one load level) ----
         if (valid && tid >= done) classify();
+        PHASE(6)
       }
     }
     if (!stop) {  // the whole batch is done
@@ -1169,6 +1241,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
 
   if (tid == 0) {
     S.sc[SC_T_FRONT] += t_front;
+    for (int k = 0; k < 7; ++k) S.sc[SC_SWEEP_PH + k] += sh.tph[k];
     S.sc[SC_N_SLOW] += n_sub;
     S.sc[SC_N_SER] += n_ser;
     A.ctl[CTL_FRONTIER] = (unsigned long long)F;
@@ -1236,7 +1309,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.n_pool_pages = (uint32_t)pages;
   if (S.G > CSET / 2) S.G = CSET / 2;  // every plane a sweep accepts names its seed in the sweeper's set
   const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 8 + 256;
-  const size_t pend_bytes = (size_t)S.G * PEND_CAP * 4;
+  const size_t pend_bytes = (size_t)S.G * PEND_CAP * 8 + 16;
   RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + pend_bytes + 64));
   // flag[CMAX+4] | gmask[n] | slotof[n] | atby[n] | alive[words] | doom[n] | hinted[n]
   const int64_t alive_words = (n + 31) / 32 + SWEEP_WORDS + 4;
@@ -1247,7 +1320,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.free_ids = reinterpret_cast<uint32_t*>(S.slots + S.G);
   S.ptabs = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(c->g_tx.p) + slot_bytes);
   S.pool.free_pages = S.ptabs + (size_t)S.G * MAX_PAGES_PER_SLOT;
-  S.pend = reinterpret_cast<int32_t*>(S.pool.free_pages + pages);
+  S.pend = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(S.pool.free_pages + pages) + 15) & ~(uintptr_t)15);
   S.pool.stack_pages = dptr<int2>(c->g_queue);
   S.pool.list_pages = reinterpret_cast<int32_t*>(S.pool.stack_pages + (size_t)pages * PAGE_SIZE);
   S.pool.at_pages = S.pool.list_pages + (size_t)pages * PAGE_SIZE;
@@ -1264,6 +1337,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.sc = A.ctl + 8;
   S.pool.n_free = &S.sc[SC_POOLFREE];
   A.stop_flag = &S.sc[SC_STOP];
+  A.slice_min_ns = getenv("BSEG_SLICE_MIN_US") ? 1000ull * strtoull(getenv("BSEG_SLICE_MIN_US"), nullptr, 10) : 0ull;
   A.frontier = 0;
   S.A = A;
   CU_CHECK(c, cudaMemsetAsync(A.slotof, 0xff, (size_t)n * 8, c->stream));  // slotof = -1, atby = none
@@ -1390,6 +1464,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   if (dbg)
     fprintf(stderr, "[bseg] sweeper: front %.1f ms of %.1f ms (%llu segments, %llu of them serial stretches, %llu growers decided with %llu open assumed-taken points), %llu batches\n",
             ctl[8 + SC_T_FRONT] / 1e6, ctl[8 + SC_SWEEP_NS] / 1e6, ctl[8 + SC_N_SLOW], ctl[8 + SC_N_SER], ctl[8 + SC_N_GROW], ctl[8 + SC_T_SLOW], ctl[8 + SC_SWEEP_ITERS]);
+  if (dbg)
+    fprintf(stderr, "[bseg] sweeper sub-step phases (ms): classify-flags+prefix %.1f, item list %.1f, insert %.1f, conflicts %.1f, dooms+decide %.1f, commit %.1f, refresh %.1f\n",
+            ctl[8 + SC_SWEEP_PH] / 1e6, ctl[8 + SC_SWEEP_PH + 1] / 1e6, ctl[8 + SC_SWEEP_PH + 2] / 1e6, ctl[8 + SC_SWEEP_PH + 3] / 1e6,
+            ctl[8 + SC_SWEEP_PH + 4] / 1e6, ctl[8 + SC_SWEEP_PH + 5] / 1e6, ctl[8 + SC_SWEEP_PH + 6] / 1e6);
   c->tm.grow_rounds = rounds;
   c->tm.grow_wasted_steps = (int64_t)ctl[8 + SC_WASTED];
   c->tm.grow_sweep_iters = (int64_t)ctl[8 + SC_SWEEP_ITERS];
