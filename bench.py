@@ -336,10 +336,13 @@ def run_ours(args):
 
     def tile_step(d_chunk):
         halo0 = args.halo or int(max(20 * p.radius, 2 * p.bin))
-        seg = slabs.segment_tile(backend, d_chunk, halo=halo0, radius=p.radius)
-        img = slabs.raster_tile(backend, d_chunk, seg, p.bin, p.bin_height, p.count_bias)
+        # the raster needs the slabs, not the labels: every rank rasters its columns before the root starts growing
+        seg = slabs.segment_tile(backend, d_chunk, halo=halo0, radius=p.radius,
+                                 between=lambda prep: slabs.raster_tile(backend, d_chunk, prep, p.bin, p.bin_height, p.count_bias,
+                                                                        want_image=False))
+        img = seg["between"]
         info.update(n_planes=seg["n_planes"], halo=seg["halo"], n_halo=seg["n_halo"], raster_tile=[img["W"], img["H"]],
-                    raster_columns=[img["x0"], img["x0"] + int(img["image"].shape[1])],
+                    raster_columns=[img["x0"], img["x0"] + img["cols"]],
                     slab_points=int(seg["partition"].owned_counts[rank]))
         for k, v in seg["t"].items():
             phase[k] = phase.get(k, 0.0) + v
@@ -384,6 +387,7 @@ def run_ours(args):
     barrier()
     ms_wall = (time.perf_counter() - t_wall) * 1e3
     clocks = sampler.stop()
+    phase_dev = dict(phase)  # (the end-to-end leg below runs the same phases again)
     # one context's stream sees only its own kernels: at N > 1 the step also runs torch / NCCL work on other streams,
     # so the step time is the wall clock between the two barriers (device-synchronised on both sides)
     ms_dev = e0.elapsed_time(e1) if world == 1 else ms_wall
@@ -404,7 +408,7 @@ def run_ours(args):
     h_label = torch.empty(n, dtype=torch.int32).pin_memory()
     cols = W if world == 1 else info["raster_columns"][1] - info["raster_columns"][0]
     h_a = torch.empty((H, cols, 3), dtype=torch.uint8).pin_memory()
-    h_b = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if world == 1 else None
+    h_b = torch.empty((H, cols, 3), dtype=torch.uint8).pin_memory()
     d_stage = torch.empty((n, 3), dtype=torch.int32, device=dev) if world > 1 else None
     npl_box = [0]
 
@@ -417,7 +421,8 @@ def run_ours(args):
         origin = torch.from_numpy(seg["partition"].origin.astype(np.int32)).to(dev)
         h_shift.copy_(d_stage - origin[None, :], non_blocking=True)   # D2H: the chunk shifted to the tile origin (TMC3.cpp:71)
         h_label.copy_(seg["labels"], non_blocking=True)               # D2H: labels of the chunk
-        h_a.copy_(img["png_a"], non_blocking=True)                    # D2H: image A columns (image B is made on the host)
+        h_a.copy_(img["png_a"], non_blocking=True)                    # D2H: this rank's columns of images A and B
+        h_b.copy_(img["png_b"], non_blocking=True)
         torch.cuda.synchronize(dev)
         npl_box[0] = seg["n_planes"]
 
@@ -493,7 +498,7 @@ def run_ours(args):
                   "raster": [int(W), int(H)], "generate_s": round(t_gen, 1)}
         if world > 1:
             config["tile"] = {**{k: info[k] for k in ("halo", "n_halo", "slab_points", "raster_columns")},
-                              "phases_ms_per_step_rank0": {k: round(1e3 * v / args.steps, 2) for k, v in phase.items()},
+                              "phases_ms_per_step_rank0": {k: round(1e3 * v / args.steps, 2) for k, v in phase_dev.items()},
                               "labels": "exact: rank 0 grows the undivided tile from the slabs' rows / normals"}
         out = {
             "metric": "points/sec segmented end-to-end", "value": value, "unit": "points/s", "n_gpus": world,

@@ -318,14 +318,16 @@ def local_cloud(P: Partition, halo_xyz, halo_gid):
 # ---------------------------------------------------------------------------------------------------------
 # steps 3 + 4
 def segment_tile(backend, chunk: torch.Tensor, halo: int = 2000, group=None, max_tries: int = 6, radius: float = 100.0,
-                 root: int = 0):
+                 root: int = 0, between=None):
     """The multi-GPU pass for this rank's chunk of the tile.  Returns a dict:
       labels      int32 [m] labels (0 or plane id) of the chunk's points -- the undivided tile's
       plane_idx   int32 [m] the reference's planeIdx (orphan marks included)
       n_planes    planes of the tile
       halo, n_halo, partition (Partition), local_xyz / local_gid / local_owned (step 2's cloud, for the raster),
       owned_gid / owned_rows / owned_normals (step 3's result for this slab: rows as global indices),
-      t (seconds per phase on this rank)."""
+      t (seconds per phase on this rank).
+    `between(prep)`: called on every rank after step 3 and before the root starts growing (its result is returned under
+    "between"); the bench rasters the tile there, while every GPU is free."""
     rank, world = _rank_world(group)
     comm = _Comm(group)
     dev = chunk.device
@@ -361,8 +363,25 @@ def segment_tile(backend, chunk: torch.Tensor, halo: int = 2000, group=None, max
     gid_o = lgid[own_idx].contiguous()
     sync()
     t["halo_knn"] = time.perf_counter() - t0
+    prep = {"halo": halo, "n_halo": int(hg.shape[0]), "partition": P, "local_xyz": lxyz, "local_gid": lgid, "local_owned": lown,
+            "t": t, "owned_gid": gid_o, "owned_rows": rows, "owned_normals": nrm_o}
+    if between is not None:  # e.g. the tile's raster: it needs the slabs, not the labels, and every rank is free now
+        t0 = time.perf_counter()
+        prep["between"] = between(prep)
+        sync()
+        t["between"] = time.perf_counter() - t0
+    return _grow_and_scatter(backend, chunk, prep, group, root)
 
-    # ---- step 4: the tile's rows / normals / points meet on the root, which grows the undivided tile ----
+
+def _grow_and_scatter(backend, chunk, prep, group, root):
+    """Step 4: the tile's rows / normals / points meet on the root, which grows the undivided tile."""
+    rank, world = _rank_world(group)
+    comm = _Comm(group)
+    dev = chunk.device
+    K = backend.p.K
+    P, t = prep["partition"], prep["t"]
+    gid_o, rows, nrm_o = prep["owned_gid"], prep["owned_rows"], prep["owned_normals"]
+    sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
     t0 = time.perf_counter()
     N = P.n_tile
     m = int(chunk.shape[0])
@@ -426,9 +445,9 @@ def segment_tile(backend, chunk: torch.Tensor, halo: int = 2000, group=None, max
     comm.broadcast(npl_t, root)
     sync()
     t["scatter"] = time.perf_counter() - t0
-    return {"labels": labels, "plane_idx": pidx, "n_planes": int(npl_t.item()), "halo": halo, "n_halo": int(hg.shape[0]),
-            "partition": P, "local_xyz": lxyz, "local_gid": lgid, "local_owned": lown, "t": t,
-            "owned_gid": gid_o, "owned_rows": rows, "owned_normals": nrm_o}
+    out = dict(prep)
+    out.update(labels=labels, plane_idx=pidx, n_planes=int(npl_t.item()))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -448,10 +467,12 @@ def ground_threshold(chunk: torch.Tensor, origin, zext: int, n_tile: int, bin_he
 
 
 def raster_tile(backend, chunk: torch.Tensor, seg: dict, bin: int = 100, bin_height: int = 1000, count_bias: float = 20.0,
-                group=None):
-    """This rank's pixel columns of the tile's raster, from the result of segment_tile.  Returns a dict: image (float64
-    [H][cols][3] on the device, the doubles of compute_gird_picture), png_a (uint8 [H][cols][3] device tensor), png_b
-    (uint8 [H][cols][3] numpy, host), x0 (first column), W, H (the tile's), ground_th, maxima (per channel)."""
+                group=None, want_image: bool = True):
+    """This rank's pixel columns of the tile's raster, from step 3's result (`seg`: what segment_tile returns, or the
+    `prep` dict its `between` hook receives -- the raster needs the slabs, not the labels).  Returns a dict: png_a / png_b
+    (uint8 [H][cols][3] device tensors: save_image's images A and B), channels (the float64 [H][cols] planes of channel 0
+    and 1 of compute_gird_picture, device), image (float64 [H][cols][3], only with want_image), x0 (first column),
+    W, H (the tile's), ground_th, maxima (per channel)."""
     rank, world = _rank_world(group)
     dev = chunk.device
     P = seg["partition"]
@@ -469,24 +490,50 @@ def raster_tile(backend, chunk: torch.Tensor, seg: dict, bin: int = 100, bin_hei
     c1 = W if rank == world - 1 else -((-(hi - int(origin[0]))) // bin)
     c0 = max(0, min(c0, W))
     c1 = max(c0, min(c1, W))
-    block = torch.zeros((H, c1 - c0, 3), dtype=torch.float64, device=dev)
+    cols = c1 - c0
+    ch0 = torch.zeros((H, cols), dtype=torch.float64, device=dev)
+    ch1 = torch.zeros((H, cols), dtype=torch.float64, device=dev)
     hl_, wl_ = int(img.shape[0]), int(img.shape[1])
     hh, ww = min(H, hl_), min(c1, wl_)
     if ww > c0 and hh > 0:
-        block[:hh, : ww - c0] = img[:hh, c0:ww]
-    # count channel on the host: log(sum + 1) (+ bias) with the platform's libm (TMC3.cpp:159-164)
-    ch1 = np.ascontiguousarray(block[..., 1].cpu().numpy())
-    m1 = backend.count_channel(ch1, count_bias) if ch1.size else 0.0
-    block[..., 1] = torch.from_numpy(ch1).to(dev)
-    # save_image (TMC3.cpp:81-121): per-channel maximum over the tile, byte = (uint8)(255.0 * (v / max))
-    m0 = float(block[..., 0].max().item()) if block.numel() else 0.0
+        ch0[:hh, : ww - c0] = img[:hh, c0:ww, 0]
+        ch1[:hh, : ww - c0] = img[:hh, c0:ww, 1]
+    # count channel on the host: log(sum + 1) (+ bias) with the platform's libm (TMC3.cpp:159-164), through a pinned
+    # buffer kept by the backend
+    m1 = 0.0
+    if ch1.numel():
+        if dev.type == "cuda":
+            host = _pinned(backend, H * cols)
+            host.copy_(ch1.view(-1))
+            torch.cuda.current_stream(dev).synchronize()
+            m1 = backend.count_channel(host.numpy(), count_bias)
+            ch1.view(-1).copy_(host, non_blocking=True)
+        else:
+            h = np.ascontiguousarray(ch1.numpy())
+            m1 = backend.count_channel(h, count_bias)
+            ch1 = torch.from_numpy(h)
+    # save_image (TMC3.cpp:81-121): per-channel maximum over the tile, byte = (uint8)(255.0 * (1.0 * v / max))
+    m0 = float(ch0.max().item()) if ch0.numel() else 0.0
     m = torch.tensor([max(m0, 0.0), max(m1, 0.0), 0.0], dtype=torch.float64, device=dev)
     _Comm(group).all_reduce(m, dist.ReduceOp.MAX)
     mh = m.cpu().numpy()
-    png_a = torch.zeros(block.shape, dtype=torch.uint8, device=dev)
+    png_a = torch.zeros((H, cols, 3), dtype=torch.uint8, device=dev)
+    png_b = torch.zeros((H, cols, 3), dtype=torch.uint8, device=dev)
     if mh[0] != 0.0:
-        png_a[..., 0] = (255.0 * (1.0 * block[..., 0] / m[0])).to(torch.uint8)
-    png_b = np.zeros(ch1.shape + (3,), np.uint8)
+        png_a[..., 0] = (255.0 * (1.0 * ch0 / m[0])).to(torch.uint8)
     if mh[1] != 0.0:
-        png_b[..., 1] = (255.0 * (1.0 * ch1 / mh[1])).astype(np.uint8)
-    return {"image": block, "png_a": png_a, "png_b": png_b, "x0": c0, "W": W, "H": H, "ground_th": th, "maxima": m}
+        png_b[..., 1] = (255.0 * (1.0 * ch1 / m[1])).to(torch.uint8)
+    out = {"channels": (ch0, ch1), "png_a": png_a, "png_b": png_b, "x0": c0, "cols": cols, "W": W, "H": H, "ground_th": th,
+           "maxima": m}
+    if want_image:
+        out["image"] = torch.stack([ch0, ch1, torch.zeros_like(ch0)], dim=-1)
+    return out
+
+
+def _pinned(backend, n: int) -> torch.Tensor:
+    """A pinned float64 host buffer of n elements, kept on the backend between calls."""
+    buf = getattr(backend, "_pinned_f64", None)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=torch.float64).pin_memory()
+        backend._pinned_f64 = buf
+    return buf[:n]

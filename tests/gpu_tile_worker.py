@@ -52,7 +52,7 @@ def main():
              n_planes=r["n_planes"], halo=r["halo"], n_halo=r["n_halo"], c0=cuts[rank], c1=cuts[rank + 1],
              owned_gid=r["owned_gid"].cpu().numpy(), owned_rows=r["owned_rows"].cpu().numpy(),
              owned_normals=r["owned_normals"].cpu().numpy(), cuts=P.cuts, origin=P.origin,
-             image=img["image"].cpu().numpy(), a=img["png_a"].cpu().numpy(), b=img["png_b"], x0=img["x0"], W=img["W"],
+             image=img["image"].cpu().numpy(), a=img["png_a"].cpu().numpy(), b=img["png_b"].cpu().numpy(), x0=img["x0"], W=img["W"],
              H=img["H"], th=img["ground_th"], launches=ctx.timings()["kernel_launches"])
     be.close()
     ctx.close()

@@ -109,7 +109,7 @@ def _worker(rank, world, port, case, kw, halo, out_dir, want_raster):
                    owned_xyz=P.owned.numpy(), part_gid=P.gid.numpy(), origin=P.origin, owned_counts=P.owned_counts)
         if want_raster:
             img = slabs.raster_tile(be, chunk, r)
-            out.update(image=img["image"].numpy(), a=img["png_a"].numpy(), b=img["png_b"], x0=img["x0"], W=img["W"], H=img["H"],
+            out.update(image=img["image"].numpy(), a=img["png_a"].numpy(), b=img["png_b"].numpy(), x0=img["x0"], W=img["W"], H=img["H"],
                        th=img["ground_th"])
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), **out)
     finally:
