@@ -106,7 +106,7 @@ struct bseg_ctx {
   DevBuf x_neigh, x_normals;  // rows / normals in original order kept on the device (bseg_knn_device_results)
   // grower (sorted-position space unless noted)
   DevBuf g_state;     // int32 [n]: -1 free, else original index of the owning seed
-  DevBuf g_res;       // u32 [n]: reservation = min original seed index that accepted the point
+  DevBuf g_res;       // (unused: the reservations live next to the owners in g_state, 8 bytes per point)
   DevBuf g_spec;      // u32 [n] (original index space): speculation record of the seed
   DevBuf g_pool;      // int32 list pool (sorted positions): pointIdx of running / committed planes
   DevBuf g_planes;    // PlaneRec []

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
     bool free_l = false;
     if (i_l < A.n) {
       s_l = __ldg(A.inv + i_l);
-      free_l = __ldcg(A.state + s_l) == -1;
+      free_l = __ldcg(A.state + 2 * (int64_t)(s_l)) == -1;
     }
     uint32_t todo = __ballot_sync(FULL_MASK, free_l);
     frontier = base;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
       todo &= todo - 1;
       const int64_t seed_i = base + b;
       const uint32_t seed_s = __shfl_sync(FULL_MASK, s_l, b);
-      if (__ldcg(A.state + seed_s) != -1)
+      if (__ldcg(A.state + 2 * (int64_t)(seed_s)) != -1)
         continue;  // taken by a transaction of this very batch
       if (NOTIFY && A.slotof[seed_i] >= 0) {  // a speculative grower owns this seed: leave it to the window
         frontier = seed_i;
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(32) grow_seq_kernel(GrowArgs A, unsigned long 
         ++n_planes;
       } else {
         for (int64_t e = lane; e < t.len; e += 32) {  // :203-209
-          A.state[st.list[e]] = -1;
-          if (NOTIFY) atomicCAS(A.res + st.list[e], (uint32_t)seed_i, RES_FREE);
+          A.state[2 * (int64_t)st.list[e]] = -1;
+          if (NOTIFY) atomicCAS(A.res + 2 * (int64_t)(st.list[e]), (uint32_t)seed_i, RES_FREE);
         }
         __syncwarp();
       }
@@ -206,7 +206,7 @@ __global__ void finalize_kernel(const int32_t* __restrict__ state, const uint32_
   int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n)
     return;
-  int32_t owner = state[inv[o]];
+  int32_t owner = state[2 * (int64_t)inv[o]];  // (owner, reservation) records
   int32_t pi = -1, lb = 0;
   if (owner >= 0) {
     int r = lower_bound_i32(seeds, n_planes, owner);
@@ -316,8 +316,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
     return 0;
   const int64_t planes_cap = n / (p->th_point_count > 0 ? p->th_point_count : 1) + 16;
   const int64_t pool_cap = 2 * n + planes_cap + 64;
-  RC_CHECK(dev_ensure(c, c->g_state, (size_t)n * 4));
-  RC_CHECK(dev_ensure(c, c->g_res, (size_t)n * 4));
+  RC_CHECK(dev_ensure(c, c->g_state, (size_t)n * 8));
   RC_CHECK(dev_ensure(c, c->g_pool, (size_t)pool_cap * 4));
   RC_CHECK(dev_ensure(c, c->g_stack, (size_t)(n + 64) * 8));
   RC_CHECK(dev_ensure(c, c->g_planes, (size_t)planes_cap * sizeof(PlaneRec)));
@@ -331,8 +330,8 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   A.nrm = dptr<double>(c->nrm);
   A.nbr = dptr<int32_t>(c->nbr);
   A.inv = dptr<uint32_t>(c->inv);
-  A.state = dptr<int32_t>(c->g_state);
-  A.res = dptr<uint32_t>(c->g_res);
+  A.state = dptr<int32_t>(c->g_state);                // owner and reservation of point p side by side: state[2p], res[2p]
+  A.res = dptr<uint32_t>(c->g_state) + 1;             // (one 8-byte record, one sector for both gathers)
   A.n = n;
   A.K = p->K;
   A.th_thick = (double)p->th_thickness;
@@ -379,8 +378,7 @@ int stage_grow(bseg_ctx* c, const bseg_params* p)
   }
   rowdup_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(A.nbr, A.K, n, dptr<uint8_t>(c->g_rowdup));
   KLAUNCH_CHECK(c);
-  CU_CHECK(c, cudaMemsetAsync(A.state, 0xff, (size_t)n * 4, c->stream));
-  CU_CHECK(c, cudaMemsetAsync(A.res, 0xff, (size_t)n * 4, c->stream));
+  CU_CHECK(c, cudaMemsetAsync(A.state, 0xff, (size_t)n * 8, c->stream));  // state = -1 (free), res = RES_FREE
   CU_CHECK(c, cudaMemsetAsync(A.ctl, 0, 64 * sizeof(unsigned long long), c->stream));
   int64_t rounds = 0;
   if (p->grow_mode == 1) {

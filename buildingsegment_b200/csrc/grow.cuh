@@ -56,6 +56,12 @@ __device__ __forceinline__ void unreserve_notify(uint32_t* atby, const int32_t* 
   if (a != 0xffffffffu && __ldcg(slotof + a) >= 0) doom[a] = 1;
 }
 
+// owner and reservation of point p in one 8-byte load (.x = state, .y = reservation): the two live in one sector
+__device__ __forceinline__ int2 ld_state_res(const GrowArgs& A, int64_t p)
+{
+  return __ldcg(reinterpret_cast<const int2*>(A.state) + p);
+}
+
 enum { CTL_FRONTIER = 0, CTL_POOL = 1, CTL_PLANES = 2, CTL_STEPS = 3, CTL_ERR = 4, CTL_TX = 5 };
 
 // model of the running plane, replicated on every lane of the warp
@@ -395,8 +401,8 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     id = __ldg(A.nbr + (int64_t)t.node * K + lane);
   if (id >= 0) {
     // inside a speculative slice nobody writes `state` (the sweeper is a different kernel): L1 may keep it
-    stt = (MODE == MODE_SPEC && state_nc) ? __ldg(A.state + id) : __ldcg(A.state + id);
-    if (MODE == MODE_SPEC) rs = __ldcg(A.res + id);
+    stt = (MODE == MODE_SPEC && state_nc) ? __ldg(A.state + 2 * (int64_t)(id)) : __ldcg(A.state + 2 * (int64_t)(id));
+    if (MODE == MODE_SPEC) rs = __ldcg(A.res + 2 * (int64_t)(id));
     p = __ldg(A.pts + id);
     const double* nr = A.nrm + 3 * (int64_t)id;
     n0 = __ldg(nr); n1 = __ldg(nr + 1); n2 = __ldg(nr + 2);
@@ -434,14 +440,14 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
           uint32_t cur = rs;
           for (;;) {
             if (cur < fr) {
-              const uint32_t seen = atomicCAS(A.res + id, cur, me);
+              const uint32_t seen = atomicCAS(A.res + 2 * (int64_t)(id), cur, me);
               if (seen == cur) {
                 old = RES_FREE;
                 break;
               }
               cur = seen;
             } else {
-              old = atomicMin(A.res + id, me);
+              old = atomicMin(A.res + 2 * (int64_t)(id), me);
               if (old >= fr)
                 break;
               cur = old;
@@ -458,13 +464,13 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
           ok = false;
           relied = true;
         } else {
-          old = atomicMin(A.res + id, me);  // result looked at after the next gather is on its way
+          old = atomicMin(A.res + 2 * (int64_t)(id), me);  // result looked at after the next gather is on its way
           fired = true;
         }
       } else {
-        A.state[id] = (int32_t)seed_i;
+        A.state[2 * (int64_t)id] = (int32_t)seed_i;
         if (MODE == MODE_SEQ_NOTIFY) {
-          const uint32_t o = atomicMin(A.res + id, me);
+          const uint32_t o = atomicMin(A.res + 2 * (int64_t)(id), me);
           if (o != RES_FREE && o > me) A.doom[o] = 1;
           if (p.w > (int32_t)me) A.doom[p.w] = 1;
         }
@@ -539,8 +545,8 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     int4 np = make_int4(0, 0, 0, 0);
     double m0 = 0, m1 = 0, m2 = 0;
     if (nid >= 0) {
-      nstt = (MODE == MODE_SPEC && state_nc) ? __ldg(A.state + nid) : __ldcg(A.state + nid);
-      if (MODE == MODE_SPEC) nrs = __ldcg(A.res + nid);
+      nstt = (MODE == MODE_SPEC && state_nc) ? __ldg(A.state + 2 * (int64_t)(nid)) : __ldcg(A.state + 2 * (int64_t)(nid));
+      if (MODE == MODE_SPEC) nrs = __ldcg(A.res + 2 * (int64_t)(nid));
       np = __ldg(A.pts + nid);
       const double* nr = A.nrm + 3 * (int64_t)nid;
       m0 = __ldg(nr); m1 = __ldg(nr + 1); m2 = __ldg(nr + 2);
@@ -605,14 +611,14 @@ __device__ __forceinline__ void tx_reserve_lane(const GrowArgs& A, int32_t id, u
     uint32_t cur = rs;
     for (;;) {
       if (cur < fr) {
-        const uint32_t seen = atomicCAS(A.res + id, cur, me);
+        const uint32_t seen = atomicCAS(A.res + 2 * (int64_t)(id), cur, me);
         if (seen == cur) {
           old = RES_FREE;
           break;
         }
         cur = seen;
       } else {
-        old = atomicMin(A.res + id, me);
+        old = atomicMin(A.res + 2 * (int64_t)(id), me);
         if (old >= fr)
           break;
         cur = old;
@@ -630,7 +636,7 @@ __device__ __forceinline__ void tx_reserve_lane(const GrowArgs& A, int32_t id, u
     ok = false;
     relied = true;
   } else {
-    old = atomicMin(A.res + id, me);  // result looked at after the next gather is on its way
+    old = atomicMin(A.res + 2 * (int64_t)(id), me);  // result looked at after the next gather is on its way
     fired = true;
   }
 }
@@ -675,8 +681,8 @@ __device__ __forceinline__ uint32_t skip_eval(const GrowArgs& A, const Model& m,
 #pragma unroll
   for (int k = 1; k < 16; ++k) {
     const uint32_t sid = ids[k] >= 0 ? (uint32_t)ids[k] : nd;
-    stt[k] = ld_cg_u32(A.state + sid);
-    rs[k] = ld_cg_u32(A.res + sid);
+    stt[k] = ld_cg_u32(A.state + 2 * (int64_t)(sid));  // (two 32-bit loads of one sector: a 64-bit one costs registers here)
+    rs[k] = ld_cg_u32(A.res + 2 * (int64_t)(sid));
   }
   // Every test below is made to depend on ALL the loads above (a mask that is zero at run time but unknown to
   // the compiler): ptxas would otherwise sink each load next to its test to save registers and serialise the
@@ -866,8 +872,9 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     if (act) has_dup = __ldg(A.rowdup + node) != 0;
     if (act && sl >= 1 && sl < K) id = __ldg(A.nbr + (int64_t)node * K + sl);
     if (id >= 0) {
-      stt = __ldcg(A.state + id);
-      rs = __ldcg(A.res + id);
+      const int2 sr = ld_state_res(A, id);
+      stt = sr.x;
+      rs = (uint32_t)sr.y;
       p = __ldg(A.pts + id);
       const double* nr = A.nrm + 3 * (int64_t)id;
       n0 = __ldg(nr); n1 = __ldg(nr + 1); n2 = __ldg(nr + 2);
@@ -1003,8 +1010,9 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     int4 np = make_int4(0, 0, 0, 0);
     double m0 = 0, m1 = 0, m2 = 0;
     if (nid >= 0) {
-      nstt = __ldcg(A.state + nid);
-      nrs = __ldcg(A.res + nid);
+      const int2 sr = ld_state_res(A, nid);
+      nstt = sr.x;
+      nrs = (uint32_t)sr.y;
       np = __ldg(A.pts + nid);
       const double* nr = A.nrm + 3 * (int64_t)nid;
       m0 = __ldg(nr); m1 = __ldg(nr + 1); m2 = __ldg(nr + 2);

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
   const int64_t len = sl.started ? sl.t.len : 0;
   for (int64_t e = 1 + (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB) {
     const int32_t pt = st.get(e);
-    if (atomicCAS(A.res + pt, (uint32_t)i, RES_FREE) == (uint32_t)i) unreserve_notify(A.atby, A.slotof, A.doom, pt);
+    if (atomicCAS(A.res + 2 * (int64_t)(pt), (uint32_t)i, RES_FREE) == (uint32_t)i) unreserve_notify(A.atby, A.slotof, A.doom, pt);
   }
 }
 
@@ -235,10 +235,10 @@ __global__ void __launch_bounds__(TPB) spec_apply_marks_kernel(SpecArgs S)
     const uint2 e = S.marklog[k];
     if (e.x == 0xffffffffu)
       continue;  // log space a serial stretch reserved and did not need
-    const uint32_t r = __ldcg(A.res + e.x);
+    const uint32_t r = __ldcg(A.res + 2 * (int64_t)(e.x));
     if (r != RES_FREE) {
       if (r != e.y) A.doom[r] = 1;  // a grower ahead of the sweeper held it: void
-      A.res[e.x] = RES_FREE;        // (a hint of this or a higher tiny transaction: obsolete)
+      A.res[2 * (int64_t)e.x] = RES_FREE;        // (a hint of this or a higher tiny transaction: obsolete)
     }
     const int32_t w = __ldg(&A.pts[e.x].w);
     atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
@@ -268,13 +268,15 @@ __global__ void __launch_bounds__(TPB) spec_preverify_kernel(SpecArgs S)
   bool bad = false;
   for (int64_t e = 1 + (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB) {
     const int32_t pt = st.get(e);
-    bad |= __ldcg(A.state + pt) != -1 || __ldcg(A.res + pt) != (uint32_t)i;
+    const int2 sr = ld_state_res(A, pt);
+    bad |= sr.x != -1 || (uint32_t)sr.y != (uint32_t)i;
   }
   for (int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x; k < n_at; k += (int64_t)RCH * TPB) {
     const int32_t pt = st.get_at(k);
-    if (__ldcg(A.state + pt) == -1) {
+    const int2 sr = ld_state_res(A, pt);
+    if (sr.x == -1) {
       const int idx = atomicAdd(&sl.n_pend, 1);
-      if (idx < PEND_CAP) S.pend[(size_t)g * PEND_CAP + idx] = make_int2(pt, (int)__ldcg(A.res + pt));
+      if (idx < PEND_CAP) S.pend[(size_t)g * PEND_CAP + idx] = make_int2(pt, sr.y);
     }
   }
   if (bad) A.doom[i] = 1;
@@ -304,8 +306,8 @@ __global__ void __launch_bounds__(TPB) spec_apply_commits_kernel(SpecArgs S)
     const int32_t id = st.get(e);
     A.pool[off + e] = id;
     if (e >= 1) {  // the seed's own entry is not a mark (:191)
-      A.state[id] = i;
-      A.res[id] = RES_FREE;
+      A.state[2 * (int64_t)id] = i;
+      A.res[2 * (int64_t)id] = RES_FREE;
     }
     const int32_t w = __ldg(&A.pts[id].w);
     atomicAnd(S.alive + (w >> 5), ~(1u << (w & 31)));
@@ -347,7 +349,8 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, 
     const uint32_t m = __ldg(S.gmask + i);
     const int32_t* row = A.nbr + (int64_t)s * K;
     const bool hinted = S.hinted[i] != 0;
-    const bool dead = __ldcg(A.state + s) != -1 || eff_res(__ldcg(A.res + s), fr) < me;
+    const int2 sr_s = ld_state_res(A, s);
+    const bool dead = sr_s.x != -1 || eff_res((uint32_t)sr_s.y, fr) < me;
     uint32_t want = 0;
     bool lower = false;
     if (!dead) {
@@ -356,9 +359,10 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, 
         const int j = __ffs(mm) - 1;
         mm &= mm - 1;
         const int32_t id = __ldg(row + j);
-        if (__ldcg(A.state + id) == -1) {
+        const int2 sr = ld_state_res(A, id);
+        if (sr.x == -1) {
           want |= 1u << j;
-          lower |= eff_res(__ldcg(A.res + id), fr) < me;
+          lower |= eff_res((uint32_t)sr.y, fr) < me;
         }
       }
       cand = (__popc(m) == K - 1 && __popc(want) == K - 1 && !lower) ? 1u : 0u;
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, 
           const int j = __ffs(mm) - 1;
           mm &= mm - 1;
           const int32_t pt = __ldg(row + j);
-          if (atomicCAS(A.res + pt, me, RES_FREE) == me) unreserve_notify(A.atby, A.slotof, A.doom, pt);
+          if (atomicCAS(A.res + 2 * (int64_t)(pt), me, RES_FREE) == me) unreserve_notify(A.atby, A.slotof, A.doom, pt);
         }
         S.hinted[i] = 0;
       }
@@ -380,19 +384,19 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, 
         const int j = __ffs(mm) - 1;
         mm &= mm - 1;
         const int32_t id = __ldg(row + j);
-        uint32_t cur = __ldcg(A.res + id);
+        uint32_t cur = __ldcg(A.res + 2 * (int64_t)(id));
         for (;;) {
           if (cur != RES_FREE && cur >= fr && cur <= me)
             break;  // ours already, or a lower transaction's
           uint32_t prev;
           if (cur < fr) {  // stale: replace
-            prev = atomicCAS(A.res + id, cur, me);
+            prev = atomicCAS(A.res + 2 * (int64_t)(id), cur, me);
             if (prev != cur) {
               cur = prev;
               continue;
             }
           } else {
-            prev = atomicMin(A.res + id, me);
+            prev = atomicMin(A.res + 2 * (int64_t)(id), me);
             if (prev < fr) {  // cannot happen inside this kernel (nobody writes stale values); be safe
               cur = prev;
               continue;
@@ -750,8 +754,9 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
     // committed state + planes this sweep has accepted: one load level (state and reservation of the seed and of its
     // depth-0 neighbours)
     auto classify = [&]() {
-      const int32_t st_s = __ldcg(A.state + s);  // the bitmap is only a filter: this is the truth
-      rs_self = __ldcg(A.res + s);
+      const int2 sr_s = ld_state_res(A, s);
+      const int32_t st_s = sr_s.x;  // the bitmap is only a filter: this is the truth
+      rs_self = (uint32_t)sr_s.y;
       int32_t stj[KM];
 #pragma unroll
       for (int j = 1; j < KM; ++j) {
@@ -759,8 +764,9 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         rs[j] = RES_FREE;
         const int32_t id = ids[j];
         if (id >= 0) {
-          stj[j] = __ldcg(A.state + id);
-          rs[j] = __ldcg(A.res + id);
+          const int2 sr = ld_state_res(A, id);
+          stj[j] = sr.x;
+          rs[j] = (uint32_t)sr.y;
         }
       }
       live = st_s == -1;
@@ -889,9 +895,9 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
                 if (pos < S.marklog_cap) S.marklog[pos] = make_uint2(ins ? (uint32_t)myid : 0xffffffffu, seed_l);
               }
               if (ins) {
-                A.state[myid] = (int32_t)seed_l;  // the first marker of the stretch owns the point
+                A.state[2 * (int64_t)myid] = (int32_t)seed_l;  // the first marker of the stretch owns the point
                 if ((hi_l >> lane) & 1u) {        // held by a higher transaction (rare): it is void
-                  const uint32_t r = __ldcg(A.res + myid);
+                  const uint32_t r = __ldcg(A.res + 2 * (int64_t)(myid));
                   if (r != RES_FREE && r > seed_l) doom_now(r);
                 }
               }
@@ -958,8 +964,8 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         bool bad = false;
         for (int64_t k = tid; k < n_at; k += SWEEP_T) {
           const int32_t pt = st.get_at(k);
-          if (__ldcg(A.state + pt) == -1) {
-            const uint32_t r = __ldcg(A.res + pt);
+          if (__ldcg(A.state + 2 * (int64_t)(pt)) == -1) {
+            const uint32_t r = __ldcg(A.res + 2 * (int64_t)(pt));
             bad |= r == RES_FREE || !set_has<CSET_BITS>(sh.cset, r);
           }
         }
@@ -1095,8 +1101,8 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
                     ps[u] = 0;
                     pr[u] = RES_FREE;
                     if ((need >> u) & 1u) {
-                      ps[u] = __ldcg(A.state + pe[u].x);
-                      pr[u] = __ldcg(A.res + pe[u].x);
+                      ps[u] = __ldcg(A.state + 2 * (int64_t)(pe[u].x));
+                      pr[u] = __ldcg(A.res + 2 * (int64_t)(pe[u].x));
                     }
                   }
 #pragma unroll
@@ -1187,7 +1193,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           const uint32_t seed = sh_me[t];
           const bool commit = (int)t < seg_end2;  // (thread order: the committed seeds' wants are a prefix of the list)
           if (commit) {
-            atomicMin(reinterpret_cast<uint32_t*>(A.state) + id, seed);  // the lower seed owns a shared point
+            atomicMin(reinterpret_cast<uint32_t*>(A.state) + 2 * (int64_t)id, seed);  // the lower seed owns a shared point
             if (!g_here) {
               const uint32_t r = it_r[k];
               if (r != RES_FREE && r > seed) A.doom[r] = 1;
