@@ -389,6 +389,17 @@ BSEG_API int bseg_paint(bseg_ctx* c, const int32_t* plane_ids_Q, int32_t n_liste
   return stage_paint(c, plane_ids_Q, n_listed, plane_rgb_Qx3, colors_Nx3);
 }
 
+BSEG_API int bseg_plane_classes(bseg_ctx* c, double facade_max_nz, double roof_min_nz, double ground_z,
+                                double* equations_Px4, uint8_t* plane_class_P, uint8_t* point_class_N)
+{
+  RC_CHECK(check_ctx(c));
+  if (!c->have_grow)
+    return bseg_fail(c, BSEG_E_STATE, "bseg_plane_classes before bseg_grow_planes");
+  if (!(facade_max_nz >= 0.0) || !(roof_min_nz >= facade_max_nz))
+    return bseg_fail(c, BSEG_E_ARG, "bseg_plane_classes: need 0 <= facade_max_nz <= roof_min_nz");
+  return stage_plane_classes(c, facade_max_nz, roof_min_nz, ground_z, equations_Px4, plane_class_P, point_class_N);
+}
+
 BSEG_API int bseg_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H)
 {
   RC_CHECK(check_ctx(c));

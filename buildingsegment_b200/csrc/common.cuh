@@ -204,6 +204,8 @@ int stage_export_grow(bseg_ctx* c, int32_t* h_plane_idx, int32_t* h_label);
 int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* centers, int64_t* offsets,
                      int32_t* point_idx);
 int stage_paint(bseg_ctx* c, const int32_t* h_ids, int32_t n_listed, const uint16_t* h_rgb, uint16_t* h_colors);
+int stage_plane_classes(bseg_ctx* c, double facade_max_nz, double roof_min_nz, double ground_z, double* h_eq,
+                        uint8_t* h_plane_class, uint8_t* h_point_class);
 int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H);
 // mode: host part of the count channel done before returning (SYNC), on a worker thread that raster_host_join()
 // waits for (ASYNC: overlaps the grower), or left to the caller (DEVICE_ONLY: bseg_raster_device)

@@ -278,6 +278,17 @@ __global__ void paint_by_rank_kernel(const int32_t* __restrict__ rank_of, const 
   colors[3 * o + 2] = c2;
 }
 
+// class of the plane a point is labelled with (bseg_plane_classes)
+__global__ void point_class_kernel(const int32_t* __restrict__ label, const uint8_t* __restrict__ plane_class, int64_t n,
+                                   uint8_t* __restrict__ out)
+{
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n)
+    return;
+  const int32_t l = label[o];
+  out[o] = l > 0 ? plane_class[l - 1] : (uint8_t)0;
+}
+
 }  // namespace
 
 // host copy of the committed planes, sorted by seed (kept between grow and get_planes)
@@ -503,6 +514,42 @@ int stage_paint(bseg_ctx* c, const int32_t* h_ids, int32_t n_listed, const uint1
     KLAUNCH_CHECK(c);
   }
   CU_CHECK(c, cudaMemcpyAsync(h_colors, d_colors, (size_t)n * 6, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// DetectedPlane (my_function.h:41-46) of every committed plane + roof / facade / ground classes (include/bseg.h)
+int stage_plane_classes(bseg_ctx* c, double facade_max_nz, double roof_min_nz, double ground_z, double* h_eq,
+                        uint8_t* h_plane_class, uint8_t* h_point_class)
+{
+  std::vector<PlaneRec>& hp = host_planes(c);
+  std::vector<uint8_t> cls(hp.size() + 1, 0);
+  for (size_t i = 0; i < hp.size(); ++i) {
+    const double a = hp[i].nrm[0], b = hp[i].nrm[1], cc = hp[i].nrm[2];
+    const double cx = (double)hp[i].ctr[0], cy = (double)hp[i].ctr[1], cz = (double)hp[i].ctr[2];
+    if (h_eq) {
+      h_eq[4 * i] = a;
+      h_eq[4 * i + 1] = b;
+      h_eq[4 * i + 2] = cc;
+      h_eq[4 * i + 3] = -((a * cx + b * cy) + cc * cz);
+    }
+    const double az = bseg_fabs(cc);
+    uint8_t k = BSEG_CLASS_OTHER;
+    if (az <= facade_max_nz) k = BSEG_CLASS_FACADE;
+    else if (az >= roof_min_nz) k = cz >= ground_z ? BSEG_CLASS_ROOF : BSEG_CLASS_GROUND;
+    cls[i] = k;
+    if (h_plane_class) h_plane_class[i] = k;
+  }
+  const int64_t n = c->n;
+  if (!h_point_class || n == 0)
+    return 0;
+  RC_CHECK(dev_ensure(c, c->out_tmp, (size_t)n + cls.size() + 64));
+  uint8_t* d_out = dptr<uint8_t>(c->out_tmp);
+  uint8_t* d_cls = d_out + ((n + 15) & ~(int64_t)15);
+  CU_CHECK(c, cudaMemcpyAsync(d_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice, c->stream));
+  point_class_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, c->stream>>>(dptr<int32_t>(c->g_label), d_cls, n, d_out);
+  KLAUNCH_CHECK(c);
+  CU_CHECK(c, cudaMemcpyAsync(h_point_class, d_out, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   return 0;
 }

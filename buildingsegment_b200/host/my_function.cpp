@@ -200,3 +200,33 @@ param analyse_path(char* argv[])
   p.savePath = value(argv[2]);
   return p;
 }
+
+// DetectedPlane records (my_function.h:41-46) of the planes get_planes returned, classes from bseg_plane_classes
+std::vector<DetectedPlane> detect_planes(const std::vector<plane>& planes, double ground_z, double facade_max_nz,
+                                         double roof_min_nz, std::vector<uint8_t>* point_class)
+{
+  bseg_ctx* ctx = bseg_host::context();
+  const int32_t P = bseg_plane_count(ctx);
+  if (P < 0 || (size_t)P != planes.size())
+    throw std::runtime_error("detect_planes: the plane vector is not the one the last get_planes returned");
+  std::vector<double> eq((size_t)P * 4);
+  std::vector<uint8_t> cls((size_t)P);
+  size_t n = 0;
+  if (point_class) {
+    n = (size_t)bseg_point_count(ctx);
+    point_class->assign(n, 0);
+  }
+  bseg_host::check(bseg_plane_classes(ctx, facade_max_nz, roof_min_nz, ground_z, eq.data(), cls.data(),
+                                      point_class && n ? point_class->data() : nullptr),
+                   "bseg_plane_classes");
+  std::vector<DetectedPlane> out((size_t)P);
+  for (size_t i = 0; i < out.size(); ++i) {
+    DetectedPlane& d = out[i];
+    d.indices.assign(planes[i].pointIdx.begin(), planes[i].pointIdx.end());
+    for (int k = 0; k < 4; ++k) d.equation[k] = eq[4 * i + k];
+    d.normal = planes[i].normal;
+    d.d = eq[4 * i + 3];
+    d.cls = cls[i];
+  }
+  return out;
+}

@@ -36,6 +36,22 @@ struct plane {
   std::vector<int> pointIdx;
 };
 
+// my_function.h:41-46: the plane record the reference declares and never fills (Eigen types there; plain arrays here,
+// this build has no Eigen).  detect_planes() fills it from the planes of get_planes: equation ax + by + cz + d = 0 with
+// (a, b, c) = plane::normal and d = -(normal . center); `cls` is the roof / facade / ground class (bseg_plane_classes).
+struct DetectedPlane {
+  std::vector<size_t> indices;  // points of the plane (plane::pointIdx)
+  double equation[4];           // ax + by + cz + d = 0
+  Vec3<double> normal;
+  double d;
+  int cls;                      // BSEG_CLASS_*
+};
+
+// The planes of the last seg_plane::get_planes as DetectedPlane records, classified on the device;
+// ground_z: e.g. buildingSeg::groundTH() (TMC3.cpp:181-198).  point_class (optional): class per point.
+std::vector<DetectedPlane> detect_planes(const std::vector<plane>& planes, double ground_z, double facade_max_nz = 0.3,
+                                         double roof_min_nz = 0.7, std::vector<uint8_t>* point_class = nullptr);
+
 param analyse_path(char* argv[]);
 vector<string> Split(const string& s, const string& seperator);
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "bseg_create", "bseg_destroy", "bseg_default_params", "bseg_last_error", "bseg_version",
     "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
-    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_raster_size", "bseg_raster", "bseg_count_channel", "bseg_png_encode", "bseg_png_write", "bseg_png_write_async", "bseg_png_wait", "bseg_raster_device", "bseg_label_raster",
+    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_plane_classes", "bseg_raster_size", "bseg_raster", "bseg_count_channel", "bseg_png_encode", "bseg_png_write", "bseg_png_write_async", "bseg_png_wait", "bseg_raster_device", "bseg_label_raster",
     "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
     "bseg_point_count", "bseg_plane_count", "bseg_set_owned", "bseg_set_origin", "bseg_device_results", "bseg_halo_check", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
 ]
@@ -102,6 +102,7 @@ def lib():
         L.bseg_device_results.argtypes = [vp, vp, vp, vp]
         L.bseg_halo_check.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
         L.bseg_count_channel.argtypes = [vp, i64, C.c_double, vp]
+        L.bseg_plane_classes.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, vp, vp]
         L.bseg_png_encode.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp]
         L.bseg_png_write.argtypes = [C.c_char_p, vp, i32, i32, i32, i32]
         L.bseg_png_write_async.argtypes = [C.c_char_p, vp, i32, i32, i32, i32]
@@ -156,6 +157,7 @@ def _ptr(a):
 
 
 RUN_KNN, RUN_GROW, RUN_RASTER, RUN_ALL = 1, 2, 4, 7
+CLASS_NONE, CLASS_ROOF, CLASS_FACADE, CLASS_GROUND, CLASS_OTHER = range(5)  # bseg_plane_classes
 
 
 class Context:
@@ -290,6 +292,17 @@ class Context:
         ids = None if plane_ids is None else np.ascontiguousarray(plane_ids, np.int32)
         self._ck(lib().bseg_paint(self._h, None if ids is None else _ptr(ids), len(plane_rgb), _ptr(plane_rgb), _ptr(colors)))
         return colors
+
+    def plane_classes(self, ground_z, facade_max_nz=0.3, roof_min_nz=0.7, want_points=True):
+        """DetectedPlane equations (my_function.h:41-46) and roof / facade / ground classes of the planes of the last
+        grow: (equations [P][4] float64, plane_class [P] uint8, point_class [N] uint8 or None)."""
+        P = self.n_planes()
+        eq = np.empty((P, 4), np.float64)
+        pc = np.empty(P, np.uint8)
+        pt = np.empty(self.n, np.uint8) if want_points else None
+        self._ck(lib().bseg_plane_classes(self._h, float(facade_max_nz), float(roof_min_nz), float(ground_z), _ptr(eq), _ptr(pc),
+                                          _ptr(pt)))
+        return eq, pc, pt
 
     # -- a13-a15 ----------------------------------------------------------------------------------
     def raster_size(self, p: Params):

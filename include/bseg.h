@@ -140,6 +140,23 @@ BSEG_API int bseg_set_grow_offset(bseg_ctx* ctx, const int32_t offset[3]);
 BSEG_API int bseg_get_planes(bseg_ctx* ctx, int32_t* seeds_P, double* normals_Px3, int32_t* centers_Px3,
                              int64_t* offsets_Pp1, int32_t* point_idx);
 
+/* Plane post-processing: plane equations and roof / facade / ground classes (north_star stage 4: "... producing roof
+ * and facade labels").  The reference declares the record -- struct DetectedPlane { indices; equation ax+by+cz+d=0;
+ * normal; d }, my_function.h:41-46 -- and never fills it, so there is no reference behaviour to match; the definitions
+ * here are the record's own: for plane p (id p + 1) of the last bseg_grow_planes
+ *   (a, b, c) = the plane's cur_normal (my_function.cpp:249), d = -((a * cx + b * cy) + c * cz) with cur_center
+ *   (my_function.cpp:250), doubles, evaluated in that order;
+ *   class = BSEG_CLASS_FACADE  if |c| <= facade_max_nz                        (the surface is close to vertical)
+ *           BSEG_CLASS_ROOF    if |c| >= roof_min_nz and cz >= ground_z       (flat or pitched, above the ground)
+ *           BSEG_CLASS_GROUND  if |c| >= roof_min_nz and cz <  ground_z
+ *           BSEG_CLASS_OTHER   otherwise (a NaN model, Q9, lands here).
+ * ground_z: normally the threshold bseg_raster reports (buildingSeg::groundTH, TMC3.cpp:181-198), same coordinates as
+ * the plane centres.  point_class_N (may be NULL): class of the plane each point is labelled with, 0 for an unlabelled
+ * point -- one device pass over the labels.  equations_Px4 / plane_class_P may be NULL. */
+enum { BSEG_CLASS_NONE = 0, BSEG_CLASS_ROOF = 1, BSEG_CLASS_FACADE = 2, BSEG_CLASS_GROUND = 3, BSEG_CLASS_OTHER = 4 };
+BSEG_API int bseg_plane_classes(bseg_ctx* ctx, double facade_max_nz, double roof_min_nz, double ground_z,
+                                double* equations_Px4, uint8_t* plane_class_P, uint8_t* point_class_N);
+
 /* ---- stage a10: seg_plane::set_plane_color (my_function.cpp:260-275) --------------------------
  * Paints exactly the pointIdx of the planes it is given, in the order given (later planes overwrite, :268-274),
  * black everywhere else.  plane_ids_Q names the planes (ids 1..P of the last bseg_grow_planes, any subset in any

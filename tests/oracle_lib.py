@@ -275,3 +275,21 @@ def label_raster(xyz_shifted, label, W, H, plane_rgb=None, bin=100):
         m = lab > 0
         rgb[m] = np.asarray(plane_rgb, np.uint16)[lab[m] - 1].astype(np.uint8)
     return lab.reshape(H, W), rgb.reshape(H, W, 3)
+
+
+def plane_classes(normals, centers, label, ground_z, facade_max_nz=0.3, roof_min_nz=0.7):
+    """numpy restatement of bseg_plane_classes (include/bseg.h): DetectedPlane equations (my_function.h:41-46) and
+    roof / facade / ground classes.  No reference behaviour exists for this (the record is never filled there)."""
+    n = np.asarray(normals, np.float64).reshape(-1, 3)
+    c = np.asarray(centers, np.float64).reshape(-1, 3)
+    d = -((n[:, 0] * c[:, 0] + n[:, 1] * c[:, 1]) + n[:, 2] * c[:, 2])
+    eq = np.concatenate([n, d[:, None]], axis=1)
+    az = np.abs(n[:, 2])
+    cls = np.full(len(n), 4, np.uint8)
+    cls[az <= facade_max_nz] = 2
+    hor = az >= roof_min_nz
+    cls[hor & (c[:, 2] >= ground_z)] = 1
+    cls[hor & (c[:, 2] < ground_z)] = 3
+    lab = np.asarray(label)
+    pt = np.where(lab > 0, np.concatenate([[0], cls])[np.clip(lab, 0, None)], 0).astype(np.uint8)
+    return eq, cls, pt

@@ -267,3 +267,27 @@ def test_radius_search_growing(ctx, case, kw, r, mode):
     # and back to the reference's rows with the radius off
     pidx, label, npl = ctx.grow_planes(lib.default_params(grow_mode=mode))
     assert npl == P0["grow"].n_planes and np.array_equal(pidx, P0["grow"].plane_idx)
+
+
+@pytest.mark.parametrize("case,kw", [("building", dict(n=60000)), ("block", dict(n=150000))])
+def test_plane_classes(ctx, case, kw):
+    """DetectedPlane equations and roof / facade / ground classes (my_function.h:41-46; bseg_plane_classes) against the
+    numpy restatement, per plane and per point; argument checks."""
+    from buildingsegment_b200 import lib
+
+    xyz = getattr(cases, case)(**kw)
+    p = lib.default_params()
+    ctx.set_points(xyz)
+    ctx.knn_normals(p, want_neigh=False, want_normals=False)
+    pidx, label, npl = ctx.grow_planes(p)
+    assert npl > 0
+    seeds, normals, centers, off, idx = ctx.get_planes(npl)
+    _, _, _, _, th = ctx.raster(p, want_image=False, want_png=False)
+    eq, pc, pt = ctx.plane_classes(th)
+    oeq, opc, opt = O.plane_classes(normals, centers, label, th)
+    assert np.array_equal(eq.view(np.int64), oeq.view(np.int64))
+    assert np.array_equal(pc, opc) and np.array_equal(pt, opt)
+    assert set(np.unique(pc)) <= {1, 2, 3, 4} and (pt[label == 0] == 0).all()
+    assert (pc == lib.CLASS_ROOF).any() or (pc == lib.CLASS_GROUND).any()
+    with pytest.raises(lib.BsegError):
+        ctx.plane_classes(th, facade_max_nz=0.8, roof_min_nz=0.5)
