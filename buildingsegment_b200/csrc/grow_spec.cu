@@ -1058,8 +1058,6 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         }
       }
       bool g_bad = false;  // grower-looking: an assumed-taken point is free at its turn
-      uint32_t pend_need = 0;  // open assumptions whose owner was asked for (pend_st: the answers, read when the growers decide)
-      int32_t pend_st[16];
       if (in_seg && live) {
         bool conf = wanted_by(s) < (uint32_t)tid;
         if (have_g && rs_self != RES_FREE && rs_self < me) conf |= gset_find(sh.gkey, sh.gval, rs_self) < (uint32_t)tid;
@@ -1076,34 +1074,46 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
             } else if (g_npend > PEND_CAP) {
               conf |= tid != done;  // the block walks its list when it is the first of a segment
             } else {
-              // open assumptions (free when the sweep began; their holders cannot have changed since: nobody writes
-              // reservations between the verification pass and the end of the sweep).  Taken now iff the holder has
-              // committed a plane in this sweep, a lower tiny seed of this segment marks the point (shared memory
-              // answers both), or an earlier segment marked it: that is a load of the owner, issued here and looked
-              // at when the growers decide, two barriers later.
-              for (int k0 = 0; k0 < g_npend; k0 += 16) {
-                int2 pes[16];  // (all entries of a trip in flight together)
+              // open assumptions (free when the sweep began): usually the holder recorded at verification has committed
+              // a plane in this sweep or a lower tiny seed of the segment marks the point (shared memory answers);
+              // global memory only for the others, all loads of a trip in flight together
+              for (int k0 = 0; k0 < g_npend; k0 += 8) {
+                int2 pe[8];
+                uint32_t need = 0;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) pes[u] = k0 + u < g_npend ? S.pend[(size_t)slot * PEND_CAP + k0 + u] : make_int2(-1, -1);
+                for (int u = 0; u < 8; ++u) pe[u] = k0 + u < g_npend ? S.pend[(size_t)slot * PEND_CAP + k0 + u] : make_int2(-1, -1);
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                  const int2 pe = pes[u];
-                  if (pe.x < 0)
+                for (int u = 0; u < 8; ++u) {
+                  if (pe[u].x < 0)
                     continue;
-                  const uint32_t r = (uint32_t)pe.y;
+                  const uint32_t r = (uint32_t)pe[u].y;
                   if (r != RES_FREE && set_has<CSET_BITS>(sh.cset, r))
                     continue;  // in a plane this sweep committed
-                  if (wanted_by((uint32_t)pe.x) < (uint32_t)tid)
+                  if (wanted_by((uint32_t)pe[u].x) < (uint32_t)tid)
                     continue;  // a lower tiny seed of this segment marks it
-                  if (r != RES_FREE && gset_find(sh.gkey, sh.gval, r) < (uint32_t)tid) {
-                    conf = true;  // depends on that grower
-                    continue;
+                  need |= 1u << u;
+                }
+                if (need) {
+                  int32_t ps[8];
+                  uint32_t pr[8];
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    ps[u] = 0;
+                    pr[u] = RES_FREE;
+                    if ((need >> u) & 1u) {
+                      ps[u] = __ldcg(A.state + 2 * (int64_t)(pe[u].x));
+                      pr[u] = __ldcg(A.res + 2 * (int64_t)(pe[u].x));
+                    }
                   }
-                  if (k0 == 0) {
-                    pend_need |= 1u << u;
-                    pend_st[u] = __ldcg(A.state + 2 * (int64_t)pe.x);
-                  } else if (__ldcg(A.state + 2 * (int64_t)pe.x) == -1) {  // (more than 16 open: rare, looked at right away)
-                    g_bad = true;
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    if (!((need >> u) & 1u) || ps[u] != -1)
+                      continue;  // marked by a lower seed since
+                    const uint32_t r = pr[u];
+                    if (r != RES_FREE && set_has<CSET_BITS>(sh.cset, r))
+                      continue;
+                    if (r != RES_FREE && gset_find(sh.gkey, sh.gval, r) < (uint32_t)tid) conf = true;  // depends on that grower
+                    else g_bad = true;
                   }
                 }
               }
@@ -1131,9 +1141,6 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         __syncthreads();
         // ---- growers decide ----
         if (in_seg && glook && tid < seg_end) {
-#pragma unroll
-          for (int u = 0; u < 16; ++u)
-            if (((pend_need >> u) & 1u) && pend_st[u] == -1) g_bad = true;  // still free at its turn: the assumption was wrong
           bool ok = slot >= 0 && g_ready && !g_bad && !g_doom0;
           if (ok) ok = ((volatile int*)&sh.dset_over)[0] ? ((volatile uint8_t*)A.doom)[i] == 0 : !set_has<DSET_BITS>(sh.dset, me);
           if (ok && g_len > A.th_count && sh.n_cset >= CSET / 2) ok = false;  // (the set is sized for every slot: never)
