@@ -400,6 +400,54 @@ BSEG_API int bseg_plane_classes(bseg_ctx* c, double facade_max_nz, double roof_m
   return stage_plane_classes(c, facade_max_nz, roof_min_nz, ground_z, equations_Px4, plane_class_P, point_class_N);
 }
 
+BSEG_API int bseg_contour_mask(bseg_ctx* c, const uint8_t* pixels, int32_t w, int32_t h, int32_t comp, int32_t channel,
+                               int32_t thresh, int32_t iterations, uint8_t* mask_out)
+{
+  RC_CHECK(check_ctx(c));
+  if (!pixels || !mask_out || w < 0 || h < 0 || comp < 1 || comp > 4 || channel < 0 || channel >= comp || iterations < 0 ||
+      iterations > 64)
+    return bseg_fail(c, BSEG_E_ARG, "bseg_contour_mask: bad arguments");
+  return stage_contour_mask(c, pixels, w, h, comp, channel, thresh, iterations, mask_out);
+}
+
+BSEG_API int bseg_find_contours(const uint8_t* mask, int32_t w, int32_t h, int32_t simple, int32_t* points_xy, int64_t cap_points,
+                                int64_t* offsets, int64_t cap_contours, int64_t* n_contours, int64_t* n_points)
+{
+  if (!mask || w < 0 || h < 0 || !n_contours || !n_points)
+    return bseg_fail(nullptr, BSEG_E_ARG, "bseg_find_contours: bad arguments");
+  std::vector<int32_t> pts;
+  std::vector<int64_t> off;
+  contour_find_host(mask, w, h, simple != 0, pts, off);
+  *n_contours = (int64_t)off.size() - 1;
+  *n_points = (int64_t)pts.size() / 2;
+  if (points_xy || offsets) {
+    if (!points_xy || !offsets || cap_points < *n_points || cap_contours < *n_contours)
+      return bseg_fail(nullptr, BSEG_E_CAPACITY, "bseg_find_contours: %lld contours / %lld points do not fit the buffers",
+                       (long long)*n_contours, (long long)*n_points);
+    if (!pts.empty()) memcpy(points_xy, pts.data(), pts.size() * 4);
+    memcpy(offsets, off.data(), off.size() * 8);
+  }
+  return 0;
+}
+
+BSEG_API int bseg_contour_measure(const int32_t* points_xy, int64_t n, double* area, double* perimeter)
+{
+  if ((n > 0 && !points_xy) || n < 0)
+    return bseg_fail(nullptr, BSEG_E_ARG, "bseg_contour_measure: bad arguments");
+  if (area) *area = contour_area(points_xy, n);
+  if (perimeter) *perimeter = contour_perimeter(points_xy, n);
+  return 0;
+}
+
+BSEG_API int bseg_draw_contour(uint8_t* image, int32_t w, int32_t h, int32_t comp, const int32_t* points_xy, int64_t n,
+                               const uint8_t* color3)
+{
+  if (!image || w < 0 || h < 0 || comp < 1 || comp > 4 || (n > 0 && !points_xy) || !color3)
+    return bseg_fail(nullptr, BSEG_E_ARG, "bseg_draw_contour: bad arguments");
+  contour_draw(image, w, h, comp, points_xy, n, color3);
+  return 0;
+}
+
 BSEG_API int bseg_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H)
 {
   RC_CHECK(check_ctx(c));

@@ -1,5 +1,6 @@
 // common.cuh -- context, device buffers and launch helpers shared by the sm_100a kernels.
 #pragma once
+#include <vector>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -206,6 +207,12 @@ int stage_get_planes(bseg_ctx* c, int32_t* seeds, double* normals, int32_t* cent
 int stage_paint(bseg_ctx* c, const int32_t* h_ids, int32_t n_listed, const uint16_t* h_rgb, uint16_t* h_colors);
 int stage_plane_classes(bseg_ctx* c, double facade_max_nz, double roof_min_nz, double ground_z, double* h_eq,
                         uint8_t* h_plane_class, uint8_t* h_point_class);
+int stage_contour_mask(bseg_ctx* c, const uint8_t* h_pixels, int32_t W, int32_t H, int32_t comp, int32_t channel, int32_t thresh,
+                       int32_t iterations, uint8_t* h_mask);  // contour.cu
+void contour_find_host(const uint8_t* mask, int32_t W, int32_t H, bool simple, std::vector<int32_t>& pts, std::vector<int64_t>& offsets);
+double contour_area(const int32_t* xy, int64_t n);
+double contour_perimeter(const int32_t* xy, int64_t n);
+void contour_draw(uint8_t* img, int32_t W, int32_t H, int32_t comp, const int32_t* xy, int64_t n, const uint8_t* color);
 int stage_raster_size(bseg_ctx* c, const bseg_params* p, int32_t* W, int32_t* H);
 // mode: host part of the count channel done before returning (SYNC), on a worker thread that raster_host_join()
 // waits for (ASYNC: overlaps the grower), or left to the caller (DEVICE_ONLY: bseg_raster_device)

@@ -120,7 +120,7 @@ public:
 int main(int argc, char* argv[])
 {
   if (argc < 3) {
-    std::cerr << "usage: tmc3 -a=<in.ply> -s=<out.ply> [--raster=<dir/>]" << std::endl;
+    std::cerr << "usage: tmc3 -a=<in.ply> -s=<out.ply> [--raster=<dir/>] [--contours=<dir/>] [--classes]" << std::endl;
     return 2;
   }
   try {
@@ -152,6 +152,24 @@ int main(int argc, char* argv[])
         seg.save_image(std::string(argv[a] + 9));
       }
     bseg_host::check(bseg_png_wait(), "bseg_png_wait");  // the images encoded on worker threads are on disk now
+    // TMC3.cpp:226 (commented out there): outlines from the count image save_image has just written; and the plane
+    // classes the data structures hint at (my_function.h:41-46)
+    for (int a = 3; a < argc; ++a) {
+      if (std::strncmp(argv[a], "--contours=", 11) == 0) {
+        const std::string base(argv[a] + 11);
+        extracted_contour(base + "\xcf\xf1\xcb\xd8\xca\xfd\xc1\xbf.png", base + "extracted_contours.png",
+                          base + "extracted_contours_flip.png");
+      }
+      if (std::strcmp(argv[a], "--classes") == 0) {
+        std::vector<uint8_t> cls;
+        const std::vector<DetectedPlane> dp = detect_planes(plances, seg.groundTH(), 0.3, 0.7, &cls);
+        size_t per[5] = {0, 0, 0, 0, 0};
+        for (uint8_t k : cls) per[k < 5 ? k : 4]++;
+        std::cout << "tmc3: " << dp.size() << " planes; points: roof " << per[BSEG_CLASS_ROOF] << ", facade " << per[BSEG_CLASS_FACADE]
+                  << ", ground " << per[BSEG_CLASS_GROUND] << ", other " << per[BSEG_CLASS_OTHER] << ", unlabelled " << per[0]
+                  << std::endl;
+      }
+    }
     std::cout << "tmc3: " << pointCloud.getPointCount() << " points, " << plances.size() << " planes -> "
               << path.savePath << std::endl;
   } catch (const std::exception& e) {

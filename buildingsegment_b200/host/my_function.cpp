@@ -4,6 +4,12 @@
 #include "my_function.h"
 
 #include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "png_read.h"
+
+#include <cstring>
 
 namespace bseg_host {
 namespace {
@@ -229,4 +235,74 @@ std::vector<DetectedPlane> detect_planes(const std::vector<plane>& planes, doubl
     d.cls = cls[i];
   }
   return out;
+}
+
+// ---- extracted_contour (my_function.cpp:8-145) ---------------------------------------------------------------------
+void extracted_contour(string read_path, string save_path, string flip)
+{
+  std::vector<uint8_t> src;  // R,G,B (cv::imread keeps B,G,R; channel 1 is green either way)
+  int cols = 0, rows = 0;
+  std::string why;
+  if (!bseg_png::read_rgb(read_path, src, cols, rows, &why))
+    throw std::runtime_error("extracted_contour: " + read_path + ": " + why);  // (:10-12 prints and then crashes on the empty Mat)
+  bseg_ctx* ctx = bseg_host::context();
+  // :17-26 extractChannel(src, 1), threshold(10, 255, THRESH_BINARY), morphologyEx(MORPH_CLOSE, ellipse 5x5, iterations 2)
+  std::vector<uint8_t> morphed((size_t)cols * rows);
+  bseg_host::check(bseg_contour_mask(ctx, src.data(), cols, rows, 3, 1, 10, 2, morphed.data()), "bseg_contour_mask");
+  // :30-33 findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)
+  int64_t nc = 0, np = 0;
+  bseg_host::check(bseg_find_contours(morphed.data(), cols, rows, 1, nullptr, 0, nullptr, 0, &nc, &np), "bseg_find_contours");
+  std::vector<int32_t> pts((size_t)(np > 0 ? np : 1) * 2);
+  std::vector<int64_t> off((size_t)nc + 1);
+  bseg_host::check(bseg_find_contours(morphed.data(), cols, rows, 1, pts.data(), np, off.data(), nc, &nc, &np), "bseg_find_contours");
+  // :36-59 the contours that look like buildings, drawn into a copy of the image
+  std::vector<uint8_t> result(src);
+  const uint8_t yellow_bgr_as_rgb[3] = {0, 255, 255};  // Scalar(255, 255, 0) is B, G, R
+  for (int64_t k = 0; k < nc; ++k) {
+    double area = 0, perimeter = 0;
+    bseg_host::check(bseg_contour_measure(pts.data() + 2 * off[k], off[k + 1] - off[k], &area, &perimeter), "bseg_contour_measure");
+    if (area > 500 && perimeter > 100)
+      bseg_host::check(bseg_draw_contour(result.data(), cols, rows, 3, pts.data() + 2 * off[k], off[k + 1] - off[k], yellow_bgr_as_rgb),
+                       "bseg_draw_contour");
+  }
+  // :64-128 csa.obj: every contour (not only the drawn ones), normalised to [0,1], y flipped, extruded to z = 0 and 1.
+  // The three comment lines are the reference's, GBK bytes as they stand in its source file.
+  {
+    std::ofstream obj("csa.obj");
+    if (!obj.is_open()) {
+      std::cerr << "extracted_contour: cannot create csa.obj" << std::endl;
+      return;  // (:66-69)
+    }
+    obj << "# \xb4\xd3\xc2\xd6\xc0\xaa\xc9\xfa\xb3\xc9\xb5\xc4" "3D\xc4\xa3\xd0\xcd" << std::endl;
+    obj << "# \xc2\xd6\xc0\xaa\xca\xfd\xc1\xbf: " << (size_t)nc << std::endl;
+    obj << "# \xb6\xa5\xb5\xe3\xb9\xe9\xd2\xbb\xbb\xaf\xb5\xbd\xb7\xb6\xce\xa7 [0,1] (x,y)" << std::endl << std::endl;
+    int vertexIndex = 1;
+    std::vector<std::vector<int>> groups;
+    for (int64_t k = 0; k < nc; ++k) {
+      std::vector<int> group;
+      for (int64_t e = off[k]; e < off[k + 1]; ++e) {
+        const float x = static_cast<float>(pts[2 * e]) / cols;
+        const float y = 1.0f - static_cast<float>(pts[2 * e + 1]) / rows;
+        obj << "v " << x << " " << y << " 0.0" << std::endl;
+        group.push_back(vertexIndex++);
+        obj << "v " << x << " " << y << " " << 1 << std::endl;
+        group.push_back(vertexIndex++);
+      }
+      groups.push_back(group);
+    }
+    obj << std::endl << "# \xb2\xe0\xc3\xe6 (\xcb\xc4\xb1\xdf\xd0\xce\xc3\xe6)" << std::endl;
+    for (const std::vector<int>& v : groups) {
+      const int n = (int)v.size() / 2;
+      for (int i = 0; i < n; ++i) {
+        const int next = (i + 1) % n;
+        obj << "f " << v[i * 2] << " " << v[next * 2] << " " << v[next * 2 + 1] << " " << v[i * 2 + 1] << std::endl;
+      }
+    }
+  }
+  // :141-144 imwrite(save_path, result); flip(result, 0); imwrite(flip, flipped)
+  bseg_host::check(bseg_png_write(save_path.c_str(), result.data(), cols, rows, 3, 0), "bseg_png_write");
+  std::vector<uint8_t> flipped(result.size());
+  for (int y = 0; y < rows; ++y)
+    memcpy(&flipped[(size_t)y * cols * 3], &result[(size_t)(rows - 1 - y) * cols * 3], (size_t)cols * 3);
+  bseg_host::check(bseg_png_write(flip.c_str(), flipped.data(), cols, rows, 3, 0), "bseg_png_write");
 }

@@ -52,6 +52,13 @@ struct DetectedPlane {
 std::vector<DetectedPlane> detect_planes(const std::vector<plane>& planes, double ground_z, double facade_max_nz = 0.3,
                                          double roof_min_nz = 0.7, std::vector<uint8_t>* point_class = nullptr);
 
+// my_function.cpp:8-145: building outlines from the count image ("像素数量.png" of save_image).  Green channel > 10,
+// closed with the 5x5 ellipse twice (on the device: bseg_contour_mask), external contours (bseg_find_contours), those with
+// area > 500 and perimeter > 100 drawn 2 pixels thick in Scalar(255,255,0) into a copy of the image that is written to
+// save_path and, flipped vertically, to `flip`; EVERY contour is extruded to z in {0, 1} in "csa.obj" (current
+// directory, as in the reference).  No OpenCV: PNG in through host/png_read.cpp, PNG out through bseg_png_write.
+void extracted_contour(string read_path, string save_path, string flip);
+
 param analyse_path(char* argv[]);
 vector<string> Split(const string& s, const string& seperator);
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 EXPORTS = [
     "bseg_create", "bseg_destroy", "bseg_default_params", "bseg_last_error", "bseg_version",
     "bseg_set_points", "bseg_set_points_device", "bseg_knn_normals", "bseg_override_neigh_normals",
-    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_plane_classes", "bseg_raster_size", "bseg_raster", "bseg_count_channel", "bseg_png_encode", "bseg_png_write", "bseg_png_write_async", "bseg_png_wait", "bseg_raster_device", "bseg_label_raster",
+    "bseg_grow_planes", "bseg_set_grow_offset", "bseg_knn_device_results", "bseg_import_neigh_normals_device", "bseg_get_planes", "bseg_paint", "bseg_plane_classes", "bseg_contour_mask", "bseg_find_contours", "bseg_contour_measure", "bseg_draw_contour", "bseg_raster_size", "bseg_raster", "bseg_count_channel", "bseg_png_encode", "bseg_png_write", "bseg_png_write_async", "bseg_png_wait", "bseg_raster_device", "bseg_label_raster",
     "bseg_run_device", "bseg_segment_host", "bseg_get_timings", "bseg_reset_counters", "bseg_stream",
     "bseg_point_count", "bseg_plane_count", "bseg_set_owned", "bseg_set_origin", "bseg_device_results", "bseg_halo_check", "bseg_debug_sort_pairs", "bseg_debug_exclusive_scan",
 ]
@@ -102,6 +102,10 @@ def lib():
         L.bseg_device_results.argtypes = [vp, vp, vp, vp]
         L.bseg_halo_check.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
         L.bseg_count_channel.argtypes = [vp, i64, C.c_double, vp]
+        L.bseg_contour_mask.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.bseg_find_contours.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, i64, vp, i64, vp, vp]
+        L.bseg_contour_measure.argtypes = [vp, i64, vp, vp]
+        L.bseg_draw_contour.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, i64, vp]
         L.bseg_plane_classes.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, vp, vp]
         L.bseg_png_encode.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp]
         L.bseg_png_write.argtypes = [C.c_char_p, vp, i32, i32, i32, i32]
@@ -124,6 +128,44 @@ def default_params(**kw) -> Params:
             raise TypeError(f"unknown parameter {k}")
         setattr(p, k, v)
     return p
+
+
+def find_contours(mask: np.ndarray, simple: bool = True):
+    """bseg_find_contours: list of int32 [k][2] arrays, as cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE/NONE)."""
+    mask = np.ascontiguousarray(mask, np.uint8)
+    H, W = mask.shape
+    nc, npt = C.c_int64(0), C.c_int64(0)
+    rc = lib().bseg_find_contours(mask.ctypes.data, W, H, int(simple), None, 0, None, 0, C.addressof(nc), C.addressof(npt))
+    if rc != 0:
+        raise BsegError(rc, last_error(None))
+    pts = np.empty((max(npt.value, 1), 2), np.int32)
+    off = np.empty(nc.value + 1, np.int64)
+    rc = lib().bseg_find_contours(mask.ctypes.data, W, H, int(simple), pts.ctypes.data, npt.value, off.ctypes.data, nc.value,
+                                  C.addressof(nc), C.addressof(npt))
+    if rc != 0:
+        raise BsegError(rc, last_error(None))
+    return [pts[off[k]: off[k + 1]].copy() for k in range(nc.value)]
+
+
+def contour_measure(pts: np.ndarray):
+    pts = np.ascontiguousarray(pts, np.int32).reshape(-1, 2)
+    a, l = C.c_double(0.0), C.c_double(0.0)
+    rc = lib().bseg_contour_measure(pts.ctypes.data, len(pts), C.addressof(a), C.addressof(l))
+    if rc != 0:
+        raise BsegError(rc, last_error(None))
+    return a.value, l.value
+
+
+def draw_contour(image: np.ndarray, pts: np.ndarray, color=(0, 255, 255)):
+    """bseg_draw_contour in place on a C-contiguous uint8 [H][W][comp] image."""
+    assert image.dtype == np.uint8 and image.flags.c_contiguous
+    pts = np.ascontiguousarray(pts, np.int32).reshape(-1, 2)
+    col = np.asarray(color, np.uint8)
+    H, W = image.shape[:2]
+    comp = 1 if image.ndim == 2 else image.shape[2]
+    rc = lib().bseg_draw_contour(image.ctypes.data, W, H, comp, pts.ctypes.data, len(pts), col.ctypes.data)
+    if rc != 0:
+        raise BsegError(rc, last_error(None))
 
 
 def count_channel(values: np.ndarray, bias: float) -> float:
@@ -303,6 +345,15 @@ class Context:
         self._ck(lib().bseg_plane_classes(self._h, float(facade_max_nz), float(roof_min_nz), float(ground_z), _ptr(eq), _ptr(pc),
                                           _ptr(pt)))
         return eq, pc, pt
+
+    def contour_mask(self, pixels: np.ndarray, channel=1, thresh=10, iterations=2):
+        """bseg_contour_mask: threshold + morphological close on the device; pixels uint8 [H][W][comp] (host)."""
+        pixels = np.ascontiguousarray(pixels, np.uint8)
+        H, W = pixels.shape[:2]
+        comp = 1 if pixels.ndim == 2 else pixels.shape[2]
+        out = np.empty((H, W), np.uint8)
+        self._ck(lib().bseg_contour_mask(self._h, _ptr(pixels), W, H, comp, channel, thresh, iterations, _ptr(out)))
+        return out
 
     # -- a13-a15 ----------------------------------------------------------------------------------
     def raster_size(self, p: Params):

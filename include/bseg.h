@@ -180,6 +180,26 @@ BSEG_API int bseg_raster(bseg_ctx* ctx, const bseg_params* p, double* image_WxHx
  * platform's std::log on worker threads; *max_out = the channel maximum save_image needs (TMC3.cpp:85-90). */
 BSEG_API int bseg_count_channel(double* values, int64_t n, double bias, double* max_out);
 
+/* ---- extracted_contour (my_function.cpp:8-145), without OpenCV -----------------------------------------------------
+ * bseg_contour_mask   (device) :19-26: mask = 255 where pixels[.., channel] > thresh (extractChannel + THRESH_BINARY; the
+ *                     reference takes channel 1 of the count image and 10), then MORPH_CLOSE with the 5x5 elliptic
+ *                     element of getStructuringElement, `iterations` times (2) -- `iterations` dilations followed by
+ *                     `iterations` erosions, pixels outside the image not taking part.  pixels / mask_out: host.
+ * bseg_find_contours  (host) :30-33: findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE when simple != 0, else _NONE): the
+ *                     same contours, in the same order, each with the same first point and orientation.  offsets has
+ *                     n_contours + 1 entries (in points); call with points_xy == offsets == NULL to size the buffers.
+ * bseg_contour_measure (host) :37-38: contourArea and arcLength(closed) of one contour.
+ * bseg_draw_contour   (host) :58: one closed contour, 2 pixels thick: every pixel within one pixel of a segment gets
+ *                     color3 (the reference's Scalar(255,255,0) in the image's channel order).  OpenCV's fixed-point
+ *                     polygon fill is not reproduced bit for bit; everything else above is. */
+BSEG_API int bseg_contour_mask(bseg_ctx* ctx, const uint8_t* pixels, int32_t w, int32_t h, int32_t comp, int32_t channel,
+                               int32_t thresh, int32_t iterations, uint8_t* mask_out);
+BSEG_API int bseg_find_contours(const uint8_t* mask, int32_t w, int32_t h, int32_t simple, int32_t* points_xy, int64_t cap_points,
+                                int64_t* offsets, int64_t cap_contours, int64_t* n_contours, int64_t* n_points);
+BSEG_API int bseg_contour_measure(const int32_t* points_xy, int64_t n, double* area, double* perimeter);
+BSEG_API int bseg_draw_contour(uint8_t* image, int32_t w, int32_t h, int32_t comp, const int32_t* points_xy, int64_t n,
+                               const uint8_t* color3);
+
 /* ---- the PNG files of save_image (TMC3.cpp:98,108,119 call stbi_write_png, stb_image_write.h:1215) --------------
  * Host-only.  The file is BYTE-identical to what stbi_write_png of the reference's vendored stb_image_write v1.16
  * writes with its default settings (per-row filter choice, its own deflate at level 8): comp = bytes per pixel (1..4),
