@@ -839,9 +839,34 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
 
       if (serial && !force_par) {
         // ---- serial stretch ----
+        // log space for the whole stretch, one entry per want of a live seed (unused ones are voided): ONE reservation
+        // in global memory instead of one round trip per warp turn
+        int s_woff;  // this thread's first entry, relative to its warp's
+        {
+          const int nw = (act && live) ? __popc(want) : 0;
+          int wincl = nw;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, wincl, o);
+            if (lane >= o) wincl += v;
+          }
+          s_woff = wincl - nw;
+          if (lane == 31) sh.warp_sum[tid >> 5] = wincl;
+          __syncthreads();
+          if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < SWEEP_T / 32; ++w) {
+              const int c = sh.warp_sum[w];
+              sh.warp_sum[w] = tot;  // exclusive
+              tot += c;
+            }
+            sh.log_base = tot > 0 ? atomicAdd(&S.sc[SC_NLOG], (unsigned long long)tot) : 0ull;
+          }
+          __syncthreads();
+        }
         for (int wi = done >> 5; wi <= ((n_eval - 1) >> 5); ++wi) {
           if ((tid >> 5) == wi && sh.ser_end == n_eval) {
-            bool mine = act && live;
+            const bool logged = act && live;  // (has log space, whatever happens to it below)
+            bool mine = logged;
             if (mine && set_has<HT_BITS>(hkeys, s)) {  // marked by an earlier warp of the stretch (:185)
               mine = false;
               if (slot >= 0) A.doom[i] = 1;
@@ -853,19 +878,15 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
             __syncwarp();
             uint32_t todo = __ballot_sync(FULL_MASK, mine);
             int n_ins = sh.ser_ins;
-            const int nw = mine ? __popc(want) : 0;  // log space: one entry per want (unused ones are voided)
-            int wincl = nw;
-            for (int o = 1; o < 32; o <<= 1) {
-              const int v = __shfl_up_sync(FULL_MASK, wincl, o);
-              if (lane >= o) wincl += v;
+            const unsigned long long lbase = sh.log_base + (unsigned long long)sh.warp_sum[wi];
+            const int woff = s_woff;
+            if (logged && !mine) {  // dead before its turn: its entries are void
+              int k = 0;
+              for (uint32_t b = want; b; b &= b - 1, ++k) {
+                const unsigned long long pos = lbase + (unsigned long long)(woff + k);
+                if (pos < S.marklog_cap) S.marklog[pos] = make_uint2(0xffffffffu, me);
+              }
             }
-            const int wtot = __shfl_sync(FULL_MASK, wincl, 31);
-            unsigned long long lbase = 0;
-            if (wtot > 0) {
-              if (lane == 0) lbase = atomicAdd(&S.sc[SC_NLOG], (unsigned long long)wtot);
-              lbase = __shfl_sync(FULL_MASK, lbase, 0);
-            }
-            const int woff = wincl - nw;
             int end_tid = -1;
             while (todo) {
               const int l = __ffs(todo) - 1;
@@ -923,6 +944,12 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
           __syncthreads();
         }
         const int ser_end = sh.ser_end;
+        if (act && live && tid >= ser_end) {  // log space of the seeds the stretch did not reach: void
+          const unsigned long long lb = sh.log_base + (unsigned long long)(sh.warp_sum[tid >> 5] + s_woff);
+          int k = 0;
+          for (uint32_t b = want; b; b &= b - 1, ++k)
+            if (lb + k < S.marklog_cap) S.marklog[lb + k] = make_uint2(0xffffffffu, me);
+        }
         if (tid == ser_end && valid) sh.last_open = i;
         for (int k = tid; k < HT; k += SWEEP_T) hkeys[k] = 0xffffffffu;
         __syncthreads();

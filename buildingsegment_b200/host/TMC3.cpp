@@ -8,6 +8,8 @@
 #include <memory>
 #include <vector>
 
+#include <algorithm>
+
 #include "my_function.h"
 
 struct Box {
@@ -143,6 +145,30 @@ int main(int argc, char* argv[])
 
     ply::write(pointCloud, {"x", "y", "z"}, 1.00, {0, 0, 0}, path.savePath, false);
 
+    // the plane classes the data structures hint at (my_function.h:41-46), while the device still holds the planes
+    // (the raster below uploads buildingSeg's own copy of the cloud); ground level = groundTH's rule (TMC3.cpp:181-198)
+    for (int a = 3; a < argc; ++a)
+      if (std::strcmp(argv[a], "--classes") == 0) {
+        const size_t n = pointCloud.getPointCount();
+        int zmax = 0;
+        for (size_t i = 0; i < n; ++i) zmax = std::max(zmax, (int)pointCloud[i][2]);
+        std::vector<size_t> hist((size_t)zmax / 1000 + 1, 0);
+        for (size_t i = 0; i < n; ++i) hist[(size_t)pointCloud[i][2] / 1000]++;
+        size_t total = 0, bin = 0;
+        for (; bin < hist.size(); ++bin) {
+          total += hist[bin];
+          if (total > n / 2)
+            break;
+        }
+        std::vector<uint8_t> cls;
+        const std::vector<DetectedPlane> dp = detect_planes(plances, 1000.0 * (double)bin, 0.3, 0.7, &cls);
+        size_t per[5] = {0, 0, 0, 0, 0};
+        for (uint8_t k : cls) per[k < 5 ? k : 4]++;
+        std::cout << "tmc3: " << dp.size() << " planes; points: roof " << per[BSEG_CLASS_ROOF] << ", facade " << per[BSEG_CLASS_FACADE]
+                  << ", ground " << per[BSEG_CLASS_GROUND] << ", other " << per[BSEG_CLASS_OTHER] << ", unlabelled " << per[0]
+                  << std::endl;
+      }
+
     // the raster path is compiled but commented out of the reference's main (TMC3.cpp:223-226);
     // here it is opt-in
     for (int a = 3; a < argc; ++a)
@@ -159,15 +185,6 @@ int main(int argc, char* argv[])
         const std::string base(argv[a] + 11);
         extracted_contour(base + "\xcf\xf1\xcb\xd8\xca\xfd\xc1\xbf.png", base + "extracted_contours.png",
                           base + "extracted_contours_flip.png");
-      }
-      if (std::strcmp(argv[a], "--classes") == 0) {
-        std::vector<uint8_t> cls;
-        const std::vector<DetectedPlane> dp = detect_planes(plances, seg.groundTH(), 0.3, 0.7, &cls);
-        size_t per[5] = {0, 0, 0, 0, 0};
-        for (uint8_t k : cls) per[k < 5 ? k : 4]++;
-        std::cout << "tmc3: " << dp.size() << " planes; points: roof " << per[BSEG_CLASS_ROOF] << ", facade " << per[BSEG_CLASS_FACADE]
-                  << ", ground " << per[BSEG_CLASS_GROUND] << ", other " << per[BSEG_CLASS_OTHER] << ", unlabelled " << per[0]
-                  << std::endl;
       }
     }
     std::cout << "tmc3: " << pointCloud.getPointCount() << " points, " << plances.size() << " planes -> "
