@@ -142,6 +142,11 @@ BSEG_API void bseg_destroy(bseg_ctx* c)
   }
   for (auto& e : c->grow_ev)
     if (e) cudaEventDestroy(e);
+  if (c->grow_fork) cudaEventDestroy(c->grow_fork);
+  for (auto& e : c->grow_join)
+    if (e) cudaEventDestroy(e);
+  if (c->grow_hi) cudaStreamDestroy(c->grow_hi);
+  if (c->grow_lo) cudaStreamDestroy(c->grow_lo);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   if (c->raster_done) cudaEventDestroy(c->raster_done);

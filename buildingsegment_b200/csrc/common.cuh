@@ -145,6 +145,9 @@ struct bseg_ctx {
   // per-device one-time setup (cudaFuncSetAttribute is per device, a context is bound to one)
   bool attr_sweep_set = false, attr_knn_set = false;
   cudaEvent_t grow_ev[5] = {nullptr};  // phase events of the speculative grower (created on first use)
+  // the sweeper (high priority) and the background slice of the growers run side by side (grow_spec.cu)
+  cudaStream_t grow_hi = nullptr, grow_lo = nullptr;
+  cudaEvent_t grow_fork = nullptr, grow_join[2] = {nullptr, nullptr};
 };
 
 int bseg_fail(bseg_ctx* c, int code, const char* fmt, ...);

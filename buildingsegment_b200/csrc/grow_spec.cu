@@ -69,6 +69,8 @@ enum {
   SC_ATFAIL = 14,     // finished slots whose assumed-taken points were not all taken
   SC_NLOG = 19,       // entries of the mark log
   SC_SWEEP_PH = 46,   // [46, 53): sweeper sub-step phases (ns, thread 0)
+  SC_SWEEP_ON = 41,   // the sweeper of this round is running (background slice: the growers of the other SMs work while it does)
+  SC_BG_STEPS = 42,   // Broad steps made by background slices
   SC_N_SER = 22,      // serial stretches of the sweeper
   SC_N_GROW = 23,     // growers the sweeper decided
   SC_HEAD_ITERS = 21, // warp iterations of the head slot (two-node engine: <= steps)
@@ -287,6 +289,10 @@ __global__ void __launch_bounds__(TPB) spec_preverify_done_kernel(SpecArgs S)
 {
   const int g = blockIdx.x * TPB + threadIdx.x;
   if (g < S.G && S.slots[g].verified == 1) S.slots[g].verified = 2;
+  if (g == 0) {  // the background slice that runs beside the sweeper: ends when the sweeper does
+    S.sc[SC_STOP] = 0;
+    S.sc[SC_SWEEP_ON] = 0;
+  }
 }
 
 // ---- planes the sweep accepted: list -> committed pool, owner marks, reservations dropped, alive bits ---------------
@@ -447,10 +453,19 @@ __global__ void spec_pop_free_kernel(SpecArgs S, int64_t F)
   S.sc[SC_STOP + 1] = gtimer();  // the slice starts
   const int32_t g = F < S.A.n ? S.A.slotof[F] : -1;
   S.sc[SC_HEAD_SLOT] = (unsigned long long)(g + 1);
+  // the head finished in a background slice: nothing to wait for, verification and the sweeper are next
+  if (g >= 0 && S.slots[g].status != ST_RUNNING) S.sc[SC_STOP] = 1;
 }
 
 // ---- K2: one warp per slot, a time slice of Broad steps with reservations ----------------------------------
-__global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned long long budget)
+// bg = 1: the BACKGROUND slice.  The sweeper is one block on one SM; while it walks the seeds the slots keep growing on
+// the other SMs.  Nothing the sweeper decides depends on a slot that is still running (it stops at the first grower
+// that is not finished AND verified), a running slot reads the committed state (which only gets more taken: reading an
+// old value is reading earlier) and reserves with atomics, and whatever the sweeper marks under a running slot's
+// reservation is found by spec_apply_marks_kernel after both have ended (the holder is doomed) and again by the
+// full-list verification of the slot.  The slice ends when the sweeper sets SC_STOP; a slot that does not see the
+// sweeper running within a few microseconds (it could not be placed, or has already ended) does nothing.
+__global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned long long budget, int bg)
 {
   const GrowArgs& A = S.A;
   const int lane = threadIdx.x & 31;
@@ -460,6 +475,18 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   Slot& sl = S.slots[g];
   if (sl.status != ST_RUNNING)
     return;
+  if (bg) {
+    const unsigned long long t_wait = gtimer();
+    for (;;) {
+      if (*(volatile unsigned long long*)&S.sc[SC_STOP] != 0)
+        return;
+      if (*(volatile unsigned long long*)&S.sc[SC_SWEEP_ON] != 0)
+        break;
+      if (gtimer() - t_wait > 20000ull)
+        return;
+      __nanosleep(200);
+    }
+  }
   const int64_t seed_i = sl.seed_i;
   if (((volatile uint8_t*)A.doom)[seed_i]) {
     __syncwarp();
@@ -481,7 +508,7 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
   }
   __syncwarp();
   unsigned long long steps = 0, iters = 0;
-  const bool is_head = (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT];
+  const bool is_head = !bg && (unsigned long long)(g + 1) == S.sc[SC_HEAD_SLOT];
   const unsigned long long t0 = is_head ? gtimer() : 0ull;
   // K <= 16: two DFS nodes per warp step (grow.cuh tx_run_pair); BSEG_GROW_FLAGS bit 6 forces the single-node engine
   const bool pair = A.K <= 16 && !(A.flags & GF_NOPAIR);
@@ -497,6 +524,7 @@ __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned
     S.sc[SC_HEAD_ITERS] += iters;
     S.sc[SC_HEAD_NS] += gtimer() - t0;
   }
+  if (lane == 0 && bg) atomicAdd(&S.sc[SC_BG_STEPS], steps);
   if (lane == 0) {
     sl.t = t;
     sl.started = 1;
@@ -637,6 +665,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   uint32_t iters = 0, ntiny = 0;
   const bool timing = (A.flags & GF_TIMING) != 0;  // BSEG_DEBUG: time split of the block (thread 0's clock)
   const unsigned long long t_begin = gtimer();
+  if (tid == 0) *(volatile unsigned long long*)&S.sc[SC_SWEEP_ON] = 1ull;  // the background slice may start
   for (int k = tid; k < HT; k += SWEEP_T) {
     hkeys[k] = 0xffffffffu;
     hvals[k] = 0xffffffffu;
@@ -1273,6 +1302,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   }
 
   if (tid == 0) {
+    *(volatile unsigned long long*)&S.sc[SC_STOP] = 1ull;  // the background slice ends with the sweep
     S.sc[SC_T_FRONT] += t_front;
     for (int k = 0; k < 7; ++k) S.sc[SC_SWEEP_PH + k] += sh.tph[k];
     S.sc[SC_N_SLOW] += n_sub;
@@ -1392,6 +1422,18 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
 
   int64_t F = 0, rounds = 0, stalls = 0, fallbacks = 0;
   const bool dbg = getenv("BSEG_DEBUG") != nullptr;
+  // background slices beside the sweeper (BSEG_BG=0: off); bounded in warp iterations even if the stop flag never came
+  const bool bg_on = !(getenv("BSEG_BG") && atoi(getenv("BSEG_BG")) == 0);
+  const unsigned long long bg_budget = 1ull << 20;
+  if (bg_on && !c->grow_hi) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // (numerically lower = higher priority)
+    CU_CHECK(c, cudaStreamCreateWithPriority(&c->grow_hi, cudaStreamNonBlocking, prio_hi));
+    CU_CHECK(c, cudaStreamCreateWithPriority(&c->grow_lo, cudaStreamNonBlocking, prio_lo));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->grow_fork, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->grow_join[0], cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->grow_join[1], cudaEventDisableTiming));
+  }
   cudaEvent_t* pe = c->grow_ev;  // owned by the context: no leak on the error returns below
   float pt[4] = {0, 0, 0, 0};
   for (int k = 0; k < 5; ++k)
@@ -1423,7 +1465,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       spec_pop_free_kernel<<<1, 1, 0, c->stream>>>(S, F);
       KLAUNCH_CHECK(c);
       cudaEventRecord(pe[2], c->stream);
-      spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget);
+      spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget, 0);
       KLAUNCH_CHECK(c);
       spec_preverify_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
@@ -1431,9 +1473,26 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       KLAUNCH_CHECK(c);
     }
     cudaEventRecord(pe[3], c->stream);
-    if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, SweepCfg<16>::SMEM, c->stream>>>(S);
-    else spec_sweep_kernel<32><<<1, SWEEP_T, SweepCfg<32>::SMEM, c->stream>>>(S);
-    KLAUNCH_CHECK(c);
+    if (bg_on && rounds > 0) {
+      // the sweeper (one block, a whole SM: launched first, on the high-priority stream) and the background slice of
+      // the growers side by side; both rejoin c->stream before the side effects of the sweep are applied
+      cudaEventRecord(c->grow_fork, c->stream);
+      cudaStreamWaitEvent(c->grow_hi, c->grow_fork, 0);
+      cudaStreamWaitEvent(c->grow_lo, c->grow_fork, 0);
+      if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, SweepCfg<16>::SMEM, c->grow_hi>>>(S);
+      else spec_sweep_kernel<32><<<1, SWEEP_T, SweepCfg<32>::SMEM, c->grow_hi>>>(S);
+      KLAUNCH_CHECK(c);
+      spec_grow_kernel<<<sb, GW * 32, 0, c->grow_lo>>>(S, bg_budget, 1);
+      KLAUNCH_CHECK(c);
+      cudaEventRecord(c->grow_join[0], c->grow_hi);
+      cudaEventRecord(c->grow_join[1], c->grow_lo);
+      cudaStreamWaitEvent(c->stream, c->grow_join[0], 0);
+      cudaStreamWaitEvent(c->stream, c->grow_join[1], 0);
+    } else {
+      if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, SweepCfg<16>::SMEM, c->stream>>>(S);
+      else spec_sweep_kernel<32><<<1, SWEEP_T, SweepCfg<32>::SMEM, c->stream>>>(S);
+      KLAUNCH_CHECK(c);
+    }
     spec_apply_marks_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     if (rounds > 0) {  // (the first sweep runs before any slot exists)
@@ -1489,8 +1548,8 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       fprintf(stderr, "[bseg] head skip batches %llu: cycles/batch enumerate %llu, evaluate %llu; pairs/batch %.1f; regular steps %llu, "
               "batch time %.1f ms of head %.1f ms\n", sd[0], sd[1] / sd[0], sd[2] / sd[0], (double)sd[4] / (double)sd[0], sd[3],
               (double)(sd[1] + sd[2]) / 1.965e6, ctl[8 + SC_HEAD_NS] / 1e6);
-    fprintf(stderr, "[bseg] rounds %lld: release %.1f ms, scout+assign %.1f ms, slices %.1f ms, sweep+apply %.1f ms\n", (long long)rounds,
-            pt[0], pt[1], pt[2], pt[3]);
+    fprintf(stderr, "[bseg] rounds %lld: release %.1f ms, scout+assign %.1f ms, slices %.1f ms, sweep+apply %.1f ms; background slices %s, %llu steps\n",
+            (long long)rounds, pt[0], pt[1], pt[2], pt[3], bg_on ? "on" : "off", ctl[8 + SC_BG_STEPS]);
   }
   c->tm.grow_slice_ms = pt[2];
   c->tm.grow_sweep_ms = pt[3];
