@@ -142,11 +142,15 @@ BSEG_API void bseg_destroy(bseg_ctx* c)
   }
   for (auto& e : c->grow_ev)
     if (e) cudaEventDestroy(e);
+  if (c->grow_pinned) cudaFreeHost(c->grow_pinned);
   if (c->grow_fork) cudaEventDestroy(c->grow_fork);
   for (auto& e : c->grow_join)
     if (e) cudaEventDestroy(e);
   if (c->grow_hi) cudaStreamDestroy(c->grow_hi);
   if (c->grow_lo) cudaStreamDestroy(c->grow_lo);
+  if (c->grow_pf) cudaStreamDestroy(c->grow_pf);
+  if (c->out_ready) cudaEventDestroy(c->out_ready);
+  if (c->out_stream) cudaStreamDestroy(c->out_stream);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   if (c->raster_done) cudaEventDestroy(c->raster_done);
@@ -538,16 +542,29 @@ BSEG_API int bseg_segment_host(bseg_ctx* c, const bseg_params* p, const int32_t*
   RC_CHECK(check_ctx(c));
   RC_CHECK(check_params(c, p));
   int32_t mn[3], mx[3];
-  RC_CHECK(bseg_set_points(c, xyz_aos, n, mn, mx, xyz_shifted_out));
-  RC_CHECK(bseg_knn_normals(c, p, nullptr, nullptr, nullptr));
-  if (png_a || png_b || W || H) {
-    RC_CHECK(stage_raster_size(c, p, W, H));
-    if (png_a || png_b)  // device pass now, host half (count channel, image B) overlapped with the grower
-      RC_CHECK(stage_raster(c, p, nullptr, png_a, png_b, nullptr, nullptr, RASTER_ASYNC));
+  RC_CHECK(bseg_set_points(c, xyz_aos, n, mn, mx, nullptr));
+  // the shifted cloud (TMC3.cpp:71 moves the caller's copy too) goes back on its own stream, beside the kNN: nothing
+  // writes xyz_raw after the shift
+  bool out_pending = false;
+  if (xyz_shifted_out && n > 0) {
+    if (!c->out_stream) CU_CHECK(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    if (!c->out_ready) CU_CHECK(c, cudaEventCreateWithFlags(&c->out_ready, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventRecord(c->out_ready, c->stream));
+    CU_CHECK(c, cudaStreamWaitEvent(c->out_stream, c->out_ready, 0));
+    CU_CHECK(c, cudaMemcpyAsync(xyz_shifted_out, c->xyz_raw.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->out_stream));
+    out_pending = true;
   }
-  const int rc = bseg_grow_planes(c, p, nullptr, label_N, n_planes);
-  RC_CHECK(raster_host_join(c));
+  int rc = bseg_knn_normals(c, p, nullptr, nullptr, nullptr);
+  if (rc == 0 && (png_a || png_b || W || H)) {
+    rc = stage_raster_size(c, p, W, H);
+    if (rc == 0 && (png_a || png_b))  // device pass now, host half (count channel, image B) overlapped with the grower
+      rc = stage_raster(c, p, nullptr, png_a, png_b, nullptr, nullptr, RASTER_ASYNC);
+  }
+  if (rc == 0) rc = bseg_grow_planes(c, p, nullptr, label_N, n_planes);
+  const int rc_join = raster_host_join(c);
+  if (out_pending) cudaStreamSynchronize(c->out_stream);  // (also on an error path: the caller's buffer must be quiet)
   RC_CHECK(rc);
+  RC_CHECK(rc_join);
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   return 0;
 }

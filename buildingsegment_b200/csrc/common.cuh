@@ -144,10 +144,13 @@ struct bseg_ctx {
   int64_t launches = 0;
   // per-device one-time setup (cudaFuncSetAttribute is per device, a context is bound to one)
   bool attr_sweep_set = false, attr_knn_set = false;
-  cudaEvent_t grow_ev[5] = {nullptr};  // phase events of the speculative grower (created on first use)
+  cudaEvent_t grow_ev[12] = {nullptr};  // two sets of phase events of the speculative grower (created on first use)
+  unsigned long long* grow_pinned = nullptr;  // pinned copies of the grower's control block, one per round in flight
   // the sweeper (high priority) and the background slice of the growers run side by side (grow_spec.cu)
-  cudaStream_t grow_hi = nullptr, grow_lo = nullptr;
-  cudaEvent_t grow_fork = nullptr, grow_join[2] = {nullptr, nullptr};
+  cudaStream_t out_stream = nullptr;  // bseg_segment_host: the shifted cloud travels back beside the kNN
+  cudaEvent_t out_ready = nullptr;
+  cudaStream_t grow_hi = nullptr, grow_lo = nullptr, grow_pf = nullptr;
+  cudaEvent_t grow_fork = nullptr, grow_join[3] = {nullptr, nullptr, nullptr};
 };
 
 int bseg_fail(bseg_ctx* c, int code, const char* fmt, ...);

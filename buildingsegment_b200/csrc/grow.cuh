@@ -30,7 +30,7 @@ struct GrowArgs {
   // speculative slices: set by the head slot when it finishes, polled by the others
   unsigned long long* stop_flag;  // 1 = stop now; 2 = the head is done: stop once the slice is slice_min_ns old
   unsigned long long slice_min_ns;  // (stop_flag[1] = globaltimer at the start of the slice)
-  int64_t frontier;  // first unresolved seed at slice start (everything below is committed)
+  int64_t frontier;  // first unresolved seed at slice start (everything below is committed); < 0: read ctl[CTL_FRONTIER]
   int flags;         // tuning switches (BSEG_GROW_FLAGS): see GF_*
   const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
   uint32_t* atby;    // [n] lowest in-flight transaction that assumed the point taken (early notification)
@@ -386,7 +386,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
   const bool row_l1 = (A.flags & GF_ROW_L1) != 0, row_l2 = (A.flags & GF_ROW_L2) != 0;
   const bool early_pop = (A.flags & GF_EARLY_POP) != 0, state_nc = (A.flags & GF_STATE_NC) != 0;
   const bool use_rowdup = (A.flags & GF_ROWDUP) != 0, fastdiv = (A.flags & GF_FASTDIV) != 0;
-  const uint32_t fr = MODE == MODE_SPEC ? (uint32_t)A.frontier : 0u;
+  const uint32_t fr = MODE == MODE_SPEC ? (A.frontier < 0 ? (uint32_t)__ldcg(A.ctl + CTL_FRONTIER) : (uint32_t)A.frontier) : 0u;
   bool has_dup = true;  // of the row being tested
   if (use_rowdup) has_dup = __ldg(A.rowdup + t.node) != 0;
   unsigned long long steps = 0;
@@ -848,7 +848,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
 {
   const int K = KT ? KT : A.K;  // <= 16: one half-warp holds a row
   const uint32_t me = (uint32_t)seed_i;
-  const uint32_t fr = (uint32_t)A.frontier;
+  const uint32_t fr = A.frontier < 0 ? (uint32_t)__ldcg(A.ctl + CTL_FRONTIER) : (uint32_t)A.frontier;
   const bool fastdiv = (A.flags & GF_FASTDIV) != 0, row_l1 = (A.flags & GF_ROW_L1) != 0;
   const bool skip = ss != nullptr && (A.flags & GF_NOSKIP) == 0;
   const bool approx = (A.flags & GF_EXACT_MODEL) == 0;

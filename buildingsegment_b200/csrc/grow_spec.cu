@@ -71,6 +71,7 @@ enum {
   SC_SWEEP_PH = 46,   // [46, 53): sweeper sub-step phases (ns, thread 0)
   SC_SWEEP_ON = 41,   // the sweeper of this round is running (background slice: the growers of the other SMs work while it does)
   SC_BG_STEPS = 42,   // Broad steps made by background slices
+  SC_LIVE_F = 43,     // the sweeper's frontier, published once per batch (the prefetch block walks ahead of it)
   SC_N_SER = 22,      // serial stretches of the sweeper
   SC_N_GROW = 23,     // growers the sweeper decided
   SC_HEAD_ITERS = 21, // warp iterations of the head slot (two-node engine: <= steps)
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(TPB) spec_preverify_done_kernel(SpecArgs S)
   if (g == 0) {  // the background slice that runs beside the sweeper: ends when the sweeper does
     S.sc[SC_STOP] = 0;
     S.sc[SC_SWEEP_ON] = 0;
+    S.sc[SC_LIVE_F] = 0;
   }
 }
 
@@ -335,26 +337,35 @@ __global__ void spec_reset_log_kernel(SpecArgs S)
 //     held the point is doomed.
 __device__ __forceinline__ uint32_t eff_res(uint32_t r, uint32_t F) { return r < F ? RES_FREE : r; }
 
-__global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, int64_t C)
+// The frontier F is read from the control block (the host runs a round ahead of what it has seen); the window is
+// [F, F + min(n - F, CW)), the flags of the rest of the CW entries are zero for the fixed-size scan.
+__global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t CW)
 {
   const GrowArgs& A = S.A;
   const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  const int64_t F = (int64_t)__ldcg(A.ctl + CTL_FRONTIER);
+  const int64_t C = A.n - F < CW ? A.n - F : CW;
   if (t == 0) {
     S.sc[SC_STOP] = 0;
     S.sc[SC_NCAND] = 0;
     S.sc[SC_NASSIGN] = 0;
   }
-  if (t >= C)
+  if (t >= C) {
+    if (t < CW) S.flag[t] = 0;
     return;
+  }
   const int64_t i = F + t;
   const uint32_t me = (uint32_t)i, fr = (uint32_t)F;
   uint32_t cand = 0;
-  if (__ldcg(A.slotof + i) < 0) {
+  // the alive bitmap is a filter (bit clear => the point is taken): late in the pass five seeds of six end here, for one
+  // coalesced word and one byte instead of three loads and a gather
+  const bool hinted = S.hinted[i] != 0;
+  const bool maybe_free = ((__ldcg(S.alive + (i >> 5)) >> (int)(i & 31)) & 1u) != 0;
+  if ((maybe_free || hinted) && __ldcg(A.slotof + i) < 0) {
     const uint32_t s = __ldg(A.inv + i);
     const int K = A.K;
     const uint32_t m = __ldg(S.gmask + i);
     const int32_t* row = A.nbr + (int64_t)s * K;
-    const bool hinted = S.hinted[i] != 0;
     const int2 sr_s = ld_state_res(A, s);
     const bool dead = sr_s.x != -1 || eff_res((uint32_t)sr_s.y, fr) < me;
     uint32_t want = 0;
@@ -419,9 +430,11 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t F, 
 }
 
 // flag[] holds the exclusive scan of the candidate flags; the lowest candidates take the free slots
-__global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t F, int64_t C)
+__global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t CW)
 {
   const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  const int64_t F = (int64_t)__ldcg(S.A.ctl + CTL_FRONTIER);
+  const int64_t C = S.A.n - F < CW ? S.A.n - F : CW;
   if (t >= C)
     return;
   const uint32_t r = S.flag[t];
@@ -447,8 +460,9 @@ __global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t F,
   S.A.doom[F + t] = 0;
 }
 
-__global__ void spec_pop_free_kernel(SpecArgs S, int64_t F)
+__global__ void spec_pop_free_kernel(SpecArgs S)
 {
+  const int64_t F = (int64_t)S.A.ctl[CTL_FRONTIER];
   S.sc[SC_NFREE] -= S.sc[SC_NASSIGN];
   S.sc[SC_STOP + 1] = gtimer();  // the slice starts
   const int32_t g = F < S.A.n ? S.A.slotof[F] : -1;
@@ -715,6 +729,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
 
   while (F < A.n && !stop) {
     ++iters;
+    if (tid == 0) *(volatile unsigned long long*)&S.sc[SC_LIVE_F] = (unsigned long long)F;
     if ((iters & 7) == 0) serial = false;
     unsigned long long ti0 = 0;
     if (timing && tid == 0) ti0 = gtimer();
@@ -1328,6 +1343,86 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
   if (lane == 0 && n_pendsum) atomicAdd(&S.sc[SC_T_SLOW], (unsigned long long)n_pendsum);
 }
 
+// ---- the sweeper's L2 warmer -------------------------------------------------------------------------------------
+// The sweeper is one block bound by three dependent load levels per batch (seed -> row -> owner / reservation records),
+// most of them DRAM misses.  This block runs beside it on another SM, a few stretches AHEAD of the frontier the sweeper
+// publishes, and walks the same chain for every live seed -- inv / gmask / slot, the depth-0 columns of the row, then a
+// prefetch.global.L2 of every record the sweeper is going to gather (and of the slot, its model and its open
+// assumptions for a seed that has one).  It writes nothing: the sweeper finds its lines in L2 instead of in DRAM.
+// Ends with the sweep (SC_STOP), when it reaches the end of the cloud, or when no sweeper shows up.
+constexpr int PF_T = 512;
+__global__ void __launch_bounds__(PF_T) spec_sweep_prefetch_kernel(SpecArgs S, int64_t lead)
+{
+  const GrowArgs& A = S.A;
+  __shared__ unsigned long long sh_f;
+  __shared__ int sh_stop;
+  const int tid = threadIdx.x;
+  const int K = A.K;
+  const int64_t n_words = (A.n + 31) >> 5;
+  const int64_t F0 = (int64_t)A.ctl[CTL_FRONTIER];
+  int64_t P = F0 & ~31LL;  // first seed of the next stretch to warm
+  const unsigned long long t0 = gtimer();
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned long long now = gtimer();
+      const unsigned long long on = *(volatile unsigned long long*)&S.sc[SC_SWEEP_ON];
+      int stop = *(volatile unsigned long long*)&S.sc[SC_STOP] != 0;
+      if (!on && now - t0 > 1000000ull) stop = 1;      // no sweeper within a millisecond
+      if (now - t0 > 4000000000ull) stop = 1;          // (safety net)
+      sh_stop = stop;
+      sh_f = *(volatile unsigned long long*)&S.sc[SC_LIVE_F];
+    }
+    __syncthreads();
+    if (sh_stop)
+      break;
+    int64_t F = (int64_t)sh_f;
+    if (F < F0) F = F0;
+    if (P < (F & ~31LL)) P = F & ~31LL;  // the sweeper caught up
+    if (P >= A.n)
+      break;
+    if (P >= F + lead) {
+      __nanosleep(1000);
+      continue;
+    }
+    // one stretch of the alive bitmap: 4 threads per word, 8 seeds each
+    const int64_t wi = (P >> 5) + (tid >> 2);
+    uint32_t w = wi < n_words ? __ldcg(S.alive + wi) : 0u;
+    w = (w >> (8 * (tid & 3))) & 0xffu;
+    const int64_t i0 = (wi << 5) + 8 * (tid & 3);
+    while (w) {
+      const int b = __ffs(w) - 1;
+      w &= w - 1;
+      const int64_t i = i0 + b;
+      if (i < F || i >= A.n)
+        continue;
+      const uint32_t s = __ldg(A.inv + i);
+      const uint32_t m = __ldg(S.gmask + i);
+      const int32_t slot = __ldcg(A.slotof + i);
+      prefetch_l2(A.state + 2 * (int64_t)s);
+      const int32_t* row = A.nbr + (int64_t)s * K;
+      uint32_t mm = m;
+      while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int32_t id = __ldg(row + j);
+        if (id >= 0) prefetch_l2(A.state + 2 * (int64_t)id);
+      }
+      if (slot >= 0) {
+        const char* sl = reinterpret_cast<const char*>(&S.slots[slot]);
+        prefetch_l2(sl);
+        prefetch_l2(sl + 128);
+        prefetch_l2(A.doom + i);
+        // the open assumptions of a finished slot: the records the sweeper asks for when it decides the grower
+        int np = __ldcg(&S.slots[slot].n_pend);
+        np = np < 0 ? 0 : (np > PEND_CAP ? PEND_CAP : np);
+        for (int k = 0; k < np; ++k) prefetch_l2(A.state + 2 * (int64_t)__ldcg(&S.pend[(size_t)slot * PEND_CAP + k].x));
+      }
+    }
+    P += 32LL * (PF_T / 4);
+  }
+}
+
 __global__ void __launch_bounds__(TPB) spec_alive_init_kernel(uint32_t* alive, int64_t n, int64_t n_alloc_words)
 {
   const int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -1425,31 +1520,39 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   // background slices beside the sweeper (BSEG_BG=0: off); bounded in warp iterations even if the stop flag never came
   const bool bg_on = !(getenv("BSEG_BG") && atoi(getenv("BSEG_BG")) == 0);
   const unsigned long long bg_budget = 1ull << 20;
+  // the sweeper's L2 warmer (BSEG_PF=0: off; BSEG_PF_LEAD: how many seeds it may run ahead of the frontier)
+  const bool pf_on = bg_on && !(getenv("BSEG_PF") && atoi(getenv("BSEG_PF")) == 0);
+  const int64_t pf_lead = getenv("BSEG_PF_LEAD") ? atoll(getenv("BSEG_PF_LEAD")) : 32768;
+  // the host runs one round ahead of the control block it has seen (BSEG_PIPE=0: launch, wait, look, launch)
+  const bool pipe_on = !(getenv("BSEG_PIPE") && atoi(getenv("BSEG_PIPE")) == 0);
   if (bg_on && !c->grow_hi) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // (numerically lower = higher priority)
     CU_CHECK(c, cudaStreamCreateWithPriority(&c->grow_hi, cudaStreamNonBlocking, prio_hi));
     CU_CHECK(c, cudaStreamCreateWithPriority(&c->grow_lo, cudaStreamNonBlocking, prio_lo));
+    CU_CHECK(c, cudaStreamCreateWithPriority(&c->grow_pf, cudaStreamNonBlocking, prio_lo));
     CU_CHECK(c, cudaEventCreateWithFlags(&c->grow_fork, cudaEventDisableTiming));
-    CU_CHECK(c, cudaEventCreateWithFlags(&c->grow_join[0], cudaEventDisableTiming));
-    CU_CHECK(c, cudaEventCreateWithFlags(&c->grow_join[1], cudaEventDisableTiming));
+    for (int k = 0; k < 3; ++k) CU_CHECK(c, cudaEventCreateWithFlags(&c->grow_join[k], cudaEventDisableTiming));
   }
-  cudaEvent_t* pe = c->grow_ev;  // owned by the context: no leak on the error returns below
   float pt[4] = {0, 0, 0, 0};
-  for (int k = 0; k < 5; ++k)
-    if (!pe[k]) cudaEventCreate(&pe[k]);
+  for (int k = 0; k < 12; ++k)  // two sets of phase events + "control block copied" (a round in flight, a round being looked at)
+    if (!c->grow_ev[k]) CU_CHECK(c, cudaEventCreate(&c->grow_ev[k]));
+  if (!c->grow_pinned) CU_CHECK(c, cudaHostAlloc(&c->grow_pinned, 2 * 64 * sizeof(unsigned long long), cudaHostAllocDefault));
   unsigned long long ctl[64] = {0};
   uint32_t* d_ncand = reinterpret_cast<uint32_t*>(&S.sc[SC_NCAND]);
   const unsigned sb = (unsigned)((S.G + GW - 1) / GW);
   // slice length in warp iterations of the head (two-node engine: ~1.6 calls each, a skip batch weighs 3)
   const unsigned long long budget = getenv("BSEG_SLICE") ? strtoull(getenv("BSEG_SLICE"), nullptr, 10) : 2560;
-  // the first pass of the sweeper runs before anything is in flight: it stops at the first grower
-  while (F < n) {
-    const int64_t C = n - F < CMAX ? n - F : CMAX;
-    const unsigned gb = (unsigned)ceil_div64(C, TPB);
-    S.A.frontier = F;
+  // every kernel of a round reads the frontier from the control block: a round can be launched before the host has seen
+  // the result of the one before it.  Past the end of the cloud a round is a no-op.
+  const int64_t CW = n < CMAX ? n : CMAX;
+  const unsigned gb = (unsigned)ceil_div64(CW, TPB);
+  S.A.frontier = -1;
+  int64_t enq = 0;  // rounds launched
+  auto enqueue_round = [&](int set) -> int {
+    cudaEvent_t* pe = c->grow_ev + 6 * set;
     cudaEventRecord(pe[0], c->stream);
-    if (rounds > 0) {
+    if (enq > 0) {
       spec_mark_release_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
       spec_release_entries_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
@@ -1457,12 +1560,12 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       spec_release_slots_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
       cudaEventRecord(pe[1], c->stream);
-      spec_scout_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
+      spec_scout_kernel<<<gb, TPB, 0, c->stream>>>(S, CW);
       KLAUNCH_CHECK(c);
-      RC_CHECK(bseg_exclusive_scan_u32(c, S.flag, C, d_ncand));
-      spec_assign_kernel<<<gb, TPB, 0, c->stream>>>(S, F, C);
+      RC_CHECK(bseg_exclusive_scan_u32(c, S.flag, CW, d_ncand));
+      spec_assign_kernel<<<gb, TPB, 0, c->stream>>>(S, CW);
       KLAUNCH_CHECK(c);
-      spec_pop_free_kernel<<<1, 1, 0, c->stream>>>(S, F);
+      spec_pop_free_kernel<<<1, 1, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
       cudaEventRecord(pe[2], c->stream);
       spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget, 0);
@@ -1471,9 +1574,12 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       KLAUNCH_CHECK(c);
       spec_preverify_done_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
+    } else {
+      cudaEventRecord(pe[1], c->stream);
+      cudaEventRecord(pe[2], c->stream);
     }
     cudaEventRecord(pe[3], c->stream);
-    if (bg_on && rounds > 0) {
+    if (bg_on && enq > 0) {
       // the sweeper (one block, a whole SM: launched first, on the high-priority stream) and the background slice of
       // the growers side by side; both rejoin c->stream before the side effects of the sweep are applied
       cudaEventRecord(c->grow_fork, c->stream);
@@ -1482,44 +1588,107 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, SweepCfg<16>::SMEM, c->grow_hi>>>(S);
       else spec_sweep_kernel<32><<<1, SWEEP_T, SweepCfg<32>::SMEM, c->grow_hi>>>(S);
       KLAUNCH_CHECK(c);
+      if (pf_on) {
+        cudaStreamWaitEvent(c->grow_pf, c->grow_fork, 0);
+        spec_sweep_prefetch_kernel<<<1, PF_T, 0, c->grow_pf>>>(S, pf_lead);
+        KLAUNCH_CHECK(c);
+        cudaEventRecord(c->grow_join[2], c->grow_pf);
+      }
       spec_grow_kernel<<<sb, GW * 32, 0, c->grow_lo>>>(S, bg_budget, 1);
       KLAUNCH_CHECK(c);
       cudaEventRecord(c->grow_join[0], c->grow_hi);
       cudaEventRecord(c->grow_join[1], c->grow_lo);
       cudaStreamWaitEvent(c->stream, c->grow_join[0], 0);
       cudaStreamWaitEvent(c->stream, c->grow_join[1], 0);
+      if (pf_on) cudaStreamWaitEvent(c->stream, c->grow_join[2], 0);
     } else {
+      // (the first sweep runs before anything is in flight: it stops at the first grower)
       if (A.K <= 16) spec_sweep_kernel<16><<<1, SWEEP_T, SweepCfg<16>::SMEM, c->stream>>>(S);
       else spec_sweep_kernel<32><<<1, SWEEP_T, SweepCfg<32>::SMEM, c->stream>>>(S);
       KLAUNCH_CHECK(c);
     }
     spec_apply_marks_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
-    if (rounds > 0) {  // (the first sweep runs before any slot exists)
+    if (enq > 0) {  // (the first sweep runs before any slot exists)
       spec_apply_commits_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
     }
     spec_reset_log_kernel<<<1, 1, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
     cudaEventRecord(pe[4], c->stream);
+    CU_CHECK(c, cudaMemcpyAsync(c->grow_pinned + 64 * set, A.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
+    cudaEventRecord(pe[5], c->stream);
+    ++enq;
+    return 0;
+  };
+  // wait for the round launched with event set `set`: its control block and phase times
+  auto collect_round = [&](int set) -> int {
+    cudaEvent_t* pe = c->grow_ev + 6 * set;
+    CU_CHECK(c, cudaEventSynchronize(pe[5]));
+    memcpy(ctl, c->grow_pinned + 64 * set, sizeof(ctl));
     ++rounds;
-    RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
     if (rounds > 1)
       for (int k = 0; k < 4; ++k) {
         float ms = 0;
         cudaEventElapsedTime(&ms, pe[k], pe[k + 1]);
         pt[k] += ms;
       }
+    return 0;
+  };
+  // what the control block of a finished round says.  0: go on; 1: done (or a capacity error: ctl[CTL_ERR]); 2: the head
+  // cannot get a slot (no pages left, or a plane too large for the page table): grow it alone in the flat region
+  auto look = [&]() -> int {
     if (ctl[CTL_ERR])
-      break;
+      return 1;
     const int64_t Fn = (int64_t)ctl[CTL_FRONTIER];
     if (Fn < F)
       return bseg_fail(c, BSEG_E_STATE, "plane grower: frontier moved backwards");
-    // no progress and nothing growing at the head for several rounds: the head cannot get a slot (no pages
-    // left, or a plane too large for the page table) -- grow it alone in the flat region
     const bool head_has_slot = ctl[8 + SC_HEAD_SLOT] != 0;
-    if (Fn == F && rounds > 1 && !head_has_slot) {
-      if (++stalls >= 2) {
+    const bool stuck = Fn == F && rounds > 1 && !head_has_slot;
+    F = Fn;
+    if (F >= n)
+      return 1;
+    if (rounds > 8 * n + 1024)
+      return bseg_fail(c, BSEG_E_STATE, "plane grower: no progress");
+    if (stuck) {
+      if (++stalls >= 2)
+        return 2;
+    } else {
+      stalls = 0;
+    }
+    return 0;
+  };
+  int in_flight = 0, oldest = 0;  // event sets alternate: `oldest` is the one to collect next
+  for (;;) {
+    while (in_flight < (pipe_on ? 2 : 1)) {
+      RC_CHECK(enqueue_round((oldest + in_flight) & 1));
+      ++in_flight;
+    }
+    RC_CHECK(collect_round(oldest));
+    oldest ^= 1;
+    --in_flight;
+    int r = look();
+    if (r < 0) {
+      cudaStreamSynchronize(c->stream);
+      return r;
+    }
+    if (r != 0) {
+      // nothing may be in flight when the loop ends or when the sequential engine takes the head
+      while (in_flight > 0) {
+        RC_CHECK(collect_round(oldest));
+        oldest ^= 1;
+        --in_flight;
+        if (r == 2) {
+          const int r2 = look();
+          if (r2 < 0)
+            return r2;
+          if (r2 == 1) r = 1;
+          else if (r2 == 0) r = 0;  // it got a slot after all
+        }
+      }
+      if (r == 1)
+        break;
+      if (r == 2) {
         launch_grow_seq(c, S.A, true, 1, 1ull << 40, 1);
         KLAUNCH_CHECK(c);
         RC_CHECK(read_back(c, ctl, A.ctl, sizeof(ctl)));
@@ -1528,14 +1697,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
         stalls = 0;
         ++fallbacks;
         F = (int64_t)ctl[CTL_FRONTIER];
-        continue;
+        if (F >= n)
+          break;
       }
-    } else {
-      stalls = 0;
     }
-    F = Fn;
-    if (rounds > 8 * n + 1024)
-      return bseg_fail(c, BSEG_E_STATE, "plane grower: no progress");
   }
   if (dbg) {
     fprintf(stderr, "[bseg] head: %llu calls in %llu warp steps\n", ctl[8 + SC_HEAD_STEPS], ctl[8 + SC_HEAD_ITERS]);
