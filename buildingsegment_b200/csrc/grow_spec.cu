@@ -109,7 +109,8 @@ struct SpecArgs {
   uint32_t* ptabs;  // [G][MAX_PAGES_PER_SLOT]
   uint32_t n_pool_pages;
   const uint32_t* gmask;  // [n] ORIGINAL index space (the sweeper and the scout walk seeds in index order)
-  uint32_t* flag;   // [C] candidate flags -> exclusive scan
+  uint32_t* flag;   // [CW] candidate bit << 31 | rank of the candidate inside its scout block
+  uint32_t* bsum;   // [blocks of the scout] candidates per block
   uint32_t* free_ids;
   uint8_t* hinted;    // [n] original index space: this tiny transaction has published hints
   uint32_t* alive;    // [ceil(n/32)] original index space: bit = the point may still be free (filter)
@@ -180,7 +181,7 @@ __device__ __forceinline__ void slot_free(const SpecArgs& S, int g)
 
 // ---- K0: release doomed / dead slots ahead of the sweeper, then doom whoever relied on them -----------------
 // A doomed plane can hold 10^5 reservations: RCH blocks per slot walk its list.
-constexpr int RCH = 16;
+constexpr int RCH = 4;  // (x G slots: the grid is launched every round and nearly all of its blocks have nothing to do)
 // which slots go: decided ONCE (releasing a slot can doom others through the early notification, and the
 // three kernels must agree)
 __global__ void __launch_bounds__(TPB) spec_mark_release_kernel(SpecArgs S)
@@ -196,7 +197,10 @@ __global__ void __launch_bounds__(TPB) spec_mark_release_kernel(SpecArgs S)
     return;
   }
   if (sl.status == ST_DEAD || S.A.doom[sl.seed_i]) sl.status = ST_RELEASING;
-  else if (sl.status == ST_FINISHED) sl.n_pend = 0;  // recounted by this round's spec_preverify_kernel
+  else if (sl.status == ST_FINISHED) {
+    sl.n_pend = 0;  // recounted by this round's spec_preverify_kernel
+    if (sl.verified == 1) sl.verified = 2;  // its list was walked last round: only the open assumptions from now on
+  }
 }
 
 __global__ void __launch_bounds__(TPB) spec_release_entries_kernel(SpecArgs S)
@@ -260,6 +264,11 @@ __global__ void __launch_bounds__(TPB) spec_preverify_kernel(SpecArgs S)
 {
   const GrowArgs& A = S.A;
   const int g = blockIdx.y;
+  if (blockIdx.x == 0 && g == 0 && threadIdx.x == 0) {  // the background slice that runs beside the sweeper: ends when the sweeper does
+    S.sc[SC_STOP] = 0;
+    S.sc[SC_SWEEP_ON] = 0;
+    S.sc[SC_LIVE_F] = 0;
+  }
   Slot& sl = S.slots[g];
   if (sl.status != ST_FINISHED)
     return;
@@ -267,7 +276,8 @@ __global__ void __launch_bounds__(TPB) spec_preverify_kernel(SpecArgs S)
   if (((volatile uint8_t*)A.doom)[i])
     return;
   const PagedStore st = slot_store(S, g);
-  const int64_t len = sl.verified == 2 ? 0 : sl.t.len, n_at = sl.t.n_at;  // the list once, the open assumptions every round
+  // the list once (verified: 0 -> 1 here, 1 -> 2 by the next round's spec_mark_release_kernel), the open assumptions every round
+  const int64_t len = sl.verified == 2 ? 0 : sl.t.len, n_at = sl.t.n_at;
   bool bad = false;
   for (int64_t e = 1 + (int64_t)blockIdx.x * TPB + threadIdx.x; e < len; e += (int64_t)RCH * TPB) {
     const int32_t pt = st.get(e);
@@ -283,18 +293,7 @@ __global__ void __launch_bounds__(TPB) spec_preverify_kernel(SpecArgs S)
     }
   }
   if (bad) A.doom[i] = 1;
-  if (threadIdx.x == 0 && blockIdx.x == 0 && sl.verified == 0) sl.verified = 1;  // (2 after the kernel: the other blocks of the slot test it)
-}
-
-__global__ void __launch_bounds__(TPB) spec_preverify_done_kernel(SpecArgs S)
-{
-  const int g = blockIdx.x * TPB + threadIdx.x;
-  if (g < S.G && S.slots[g].verified == 1) S.slots[g].verified = 2;
-  if (g == 0) {  // the background slice that runs beside the sweeper: ends when the sweeper does
-    S.sc[SC_STOP] = 0;
-    S.sc[SC_SWEEP_ON] = 0;
-    S.sc[SC_LIVE_F] = 0;
-  }
+  if (threadIdx.x == 0 && blockIdx.x == 0 && sl.verified == 0) sl.verified = 1;  // (not 2: the other blocks of the slot test it)
 }
 
 // ---- planes the sweep accepted: list -> committed pool, owner marks, reservations dropped, alive bits ---------------
@@ -304,6 +303,10 @@ __global__ void __launch_bounds__(TPB) spec_apply_commits_kernel(SpecArgs S)
 {
   const GrowArgs& A = S.A;
   const int g = blockIdx.y;
+  if (blockIdx.x == 0 && g == 0 && threadIdx.x == 0) {  // the mark log has been applied (spec_apply_marks_kernel): empty it
+    S.sc[SC_NLOG] = 0;
+    S.sc[SC_POOL0] = A.ctl[CTL_POOL];
+  }
   const Slot& sl = S.slots[g];
   if (sl.status != ST_COMMIT)
     return;
@@ -322,12 +325,6 @@ __global__ void __launch_bounds__(TPB) spec_apply_commits_kernel(SpecArgs S)
   }
 }
 
-__global__ void spec_reset_log_kernel(SpecArgs S)
-{
-  S.sc[SC_NLOG] = 0;
-  S.sc[SC_POOL0] = S.A.ctl[CTL_POOL];
-}
-
 // ---- K1: scout -- the window [F, F+C) ahead of the sweeper -------------------------------------------------
 // Every seed of the window without a slot is evaluated against the committed state plus the reservations
 // of LOWER in-flight transactions (reservations below F are stale and count as free):
@@ -338,7 +335,7 @@ __global__ void spec_reset_log_kernel(SpecArgs S)
 __device__ __forceinline__ uint32_t eff_res(uint32_t r, uint32_t F) { return r < F ? RES_FREE : r; }
 
 // The frontier F is read from the control block (the host runs a round ahead of what it has seen); the window is
-// [F, F + min(n - F, CW)), the flags of the rest of the CW entries are zero for the fixed-size scan.
+// [F, F + min(n - F, CW)), the grid always covers CW seeds.
 __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t CW)
 {
   const GrowArgs& A = S.A;
@@ -350,13 +347,10 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t CW)
     S.sc[SC_NCAND] = 0;
     S.sc[SC_NASSIGN] = 0;
   }
-  if (t >= C) {
-    if (t < CW) S.flag[t] = 0;
-    return;
-  }
   const int64_t i = F + t;
   const uint32_t me = (uint32_t)i, fr = (uint32_t)F;
   uint32_t cand = 0;
+  if (t < C) {
   // the alive bitmap is a filter (bit clear => the point is taken): late in the pass five seeds of six end here, for one
   // coalesced word and one byte instead of three loads and a gather
   const bool hinted = S.hinted[i] != 0;
@@ -426,21 +420,48 @@ __global__ void __launch_bounds__(TPB) spec_scout_kernel(SpecArgs S, int64_t CW)
       S.hinted[i] = 1;
     }
   }
-  S.flag[t] = cand;
+  }
+  // rank of a candidate among the candidates of its block, and the block's count: spec_assign_kernel adds the counts of
+  // the blocks below -- the window's exclusive scan without scan kernels (three launches per round)
+  __shared__ uint32_t wsum[TPB / 32];
+  const uint32_t bal = __ballot_sync(FULL_MASK, cand != 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wsum[warp] = (uint32_t)__popc(bal);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < TPB / 32; ++w) {
+    const uint32_t cw = wsum[w];
+    if (w < warp) before += cw;
+    total += cw;
+  }
+  if (t < CW) S.flag[t] = (before + (uint32_t)__popc(bal & lanemask_lt())) | (cand << 31);
+  if (threadIdx.x == 0) S.bsum[blockIdx.x] = total;
 }
 
-// flag[] holds the exclusive scan of the candidate flags; the lowest candidates take the free slots
+// flag[t] = candidate bit << 31 | rank inside the scout's block, bsum[b] = candidates of block b: the lowest candidates
+// of the window take the free slots
 __global__ void __launch_bounds__(TPB) spec_assign_kernel(SpecArgs S, int64_t CW)
 {
   const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
   const int64_t F = (int64_t)__ldcg(S.A.ctl + CTL_FRONTIER);
   const int64_t C = S.A.n - F < CW ? S.A.n - F : CW;
+  // candidates in the blocks below this one
+  __shared__ uint32_t wpart[TPB / 32];
+  uint32_t part = 0;
+  for (uint32_t k = threadIdx.x; k < blockIdx.x; k += TPB) part += S.bsum[k];
+  for (int o = 16; o; o >>= 1) part += __shfl_down_sync(FULL_MASK, part, o);
+  if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5] = part;
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int w = 0; w < TPB / 32; ++w) base += wpart[w];
   if (t >= C)
     return;
-  const uint32_t r = S.flag[t];
-  const uint32_t next = t + 1 < C ? S.flag[t + 1] : (uint32_t)S.sc[SC_NCAND];
-  if (next == r)
+  const uint32_t f = S.flag[t];
+  if (!(f >> 31))
     return;  // not a candidate
+  const uint32_t r = base + (f & 0x7fffffffu);
   // the last free slot is kept for the seed at the frontier: the head can always grow
   const uint32_t nfree = (uint32_t)S.sc[SC_NFREE];
   if (t == 0 ? r >= nfree : r + 1 >= nfree)
@@ -845,7 +866,7 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         if ((m >> j) & 1u) ids[j] = __ldg(row + j);
       if (slot >= 0) {  // (its own fields: nobody writes them during the sweep)
         const Slot& sl = S.slots[slot];
-        g_ready = sl.status == ST_FINISHED && sl.verified == 2;
+        g_ready = sl.status == ST_FINISHED && sl.verified >= 1;
         g_len = sl.t.len;
         g_npend = sl.n_pend;
         g_doom0 = ((volatile uint8_t*)A.doom)[i] != 0;
@@ -1469,9 +1490,10 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   const size_t slot_bytes = (size_t)S.G * sizeof(Slot) + (size_t)S.G * 8 + 256;
   const size_t pend_bytes = (size_t)S.G * PEND_CAP * 8 + 16;
   RC_CHECK(dev_ensure(c, c->g_tx, slot_bytes + (size_t)S.G * MAX_PAGES_PER_SLOT * 4 + (size_t)pages * 4 + pend_bytes + 64));
-  // flag[CMAX+4] | gmask[n] | slotof[n] | atby[n] | alive[words] | doom[n] | hinted[n]
+  // flag[CMAX+4] | bsum[blocks+4] | gmask[n] | slotof[n] | atby[n] | alive[words] | doom[n] | hinted[n]
   const int64_t alive_words = (n + 31) / 32 + SWEEP_WORDS + 4;
-  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4) * 4 + (size_t)n * 14 + (size_t)alive_words * 4 + 256));
+  const int64_t n_bsum = ceil_div64(CMAX, TPB) + 4;
+  RC_CHECK(dev_ensure(c, c->g_spec, (size_t)(CMAX + 4 + n_bsum) * 4 + (size_t)n * 14 + (size_t)alive_words * 4 + 256));
   RC_CHECK(dev_ensure(c, c->g_queue, (size_t)pages * PAGE_SIZE * 16 + 256));
   RC_CHECK(dev_ensure(c, c->g_marklog, ((size_t)n + 4096) * sizeof(uint2)));
   S.slots = dptr<Slot>(c->g_tx);
@@ -1483,7 +1505,8 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
   S.pool.list_pages = reinterpret_cast<int32_t*>(S.pool.stack_pages + (size_t)pages * PAGE_SIZE);
   S.pool.at_pages = S.pool.list_pages + (size_t)pages * PAGE_SIZE;
   S.flag = dptr<uint32_t>(c->g_spec);
-  uint32_t* gmask = S.flag + CMAX + 4;
+  S.bsum = S.flag + CMAX + 4;
+  uint32_t* gmask = S.bsum + n_bsum;
   S.gmask = gmask;
   A.slotof = reinterpret_cast<int32_t*>(gmask + n);
   A.atby = reinterpret_cast<uint32_t*>(A.slotof + n);
@@ -1539,7 +1562,6 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     if (!c->grow_ev[k]) CU_CHECK(c, cudaEventCreate(&c->grow_ev[k]));
   if (!c->grow_pinned) CU_CHECK(c, cudaHostAlloc(&c->grow_pinned, 2 * 64 * sizeof(unsigned long long), cudaHostAllocDefault));
   unsigned long long ctl[64] = {0};
-  uint32_t* d_ncand = reinterpret_cast<uint32_t*>(&S.sc[SC_NCAND]);
   const unsigned sb = (unsigned)((S.G + GW - 1) / GW);
   // slice length in warp iterations of the head (two-node engine: ~1.6 calls each, a skip batch weighs 3)
   const unsigned long long budget = getenv("BSEG_SLICE") ? strtoull(getenv("BSEG_SLICE"), nullptr, 10) : 2560;
@@ -1562,7 +1584,6 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       cudaEventRecord(pe[1], c->stream);
       spec_scout_kernel<<<gb, TPB, 0, c->stream>>>(S, CW);
       KLAUNCH_CHECK(c);
-      RC_CHECK(bseg_exclusive_scan_u32(c, S.flag, CW, d_ncand));
       spec_assign_kernel<<<gb, TPB, 0, c->stream>>>(S, CW);
       KLAUNCH_CHECK(c);
       spec_pop_free_kernel<<<1, 1, 0, c->stream>>>(S);
@@ -1571,8 +1592,6 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       spec_grow_kernel<<<sb, GW * 32, 0, c->stream>>>(S, budget, 0);
       KLAUNCH_CHECK(c);
       spec_preverify_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
-      KLAUNCH_CHECK(c);
-      spec_preverify_done_kernel<<<(S.G + TPB - 1) / TPB, TPB, 0, c->stream>>>(S);
       KLAUNCH_CHECK(c);
     } else {
       cudaEventRecord(pe[1], c->stream);
@@ -1609,11 +1628,7 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
     }
     spec_apply_marks_kernel<<<c->num_sms * 4, TPB, 0, c->stream>>>(S);
     KLAUNCH_CHECK(c);
-    if (enq > 0) {  // (the first sweep runs before any slot exists)
-      spec_apply_commits_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);
-      KLAUNCH_CHECK(c);
-    }
-    spec_reset_log_kernel<<<1, 1, 0, c->stream>>>(S);
+    spec_apply_commits_kernel<<<dim3(RCH, S.G), TPB, 0, c->stream>>>(S);  // (also empties the mark log)
     KLAUNCH_CHECK(c);
     cudaEventRecord(pe[4], c->stream);
     CU_CHECK(c, cudaMemcpyAsync(c->grow_pinned + 64 * set, A.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
