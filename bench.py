@@ -439,6 +439,27 @@ def run_ours(args):
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_max.item())
     e2e_value = n_tile * args.steps / (ms_e2e * 1e-3)
+    # ---- checksum of the labels of the last end-to-end pass (outside the timed region): sum of labels and a
+    #      position-weighted sum mod 2^64 over the TILE's index order -- the same number for every build, engine and N ----
+    off = 0
+    if world > 1:
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev))
+        off = int(sum(int(c.item()) for c in counts[:rank]))
+    s1 = np.uint64(0)
+    s2 = np.uint64(0)
+    lab_all = h_label.numpy()
+    with np.errstate(over="ignore"):
+        for a in range(0, n, 1 << 24):
+            lab = lab_all[a: a + (1 << 24)].astype(np.uint64)
+            w = (np.arange(off + a + 1, off + a + 1 + len(lab), dtype=np.uint64)) * np.uint64(0x9E3779B97F4A7C15)
+            s1 = s1 + lab.sum(dtype=np.uint64)
+            s2 = s2 + (lab * w).sum(dtype=np.uint64)
+    chk = torch.tensor([int(s1) - (1 << 64) if int(s1) >= (1 << 63) else int(s1),
+                        int(s2) - (1 << 64) if int(s2) >= (1 << 63) else int(s2)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(chk)
+    labels_checksum = [int(chk[0].item()) & ((1 << 64) - 1), "%016x" % (int(chk[1].item()) & ((1 << 64) - 1))]
     h2d = n_tile * 12
     d2h = n_tile * 12 + n_tile * 4 + 2 * 3 * W * H
 
@@ -468,7 +489,9 @@ def run_ours(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
-                traffic = json.load(f).get("grow_dram_bytes_per_step")
+                tj = json.load(f)
+                if tj.get("workload_key") == args.workload and n_tile == 10_000_000:  # measured on that workload only
+                    traffic = tj.get("grow_dram_bytes_per_step") / rounds   # per launch (= round), like avg_launch_ms
         except Exception:
             pass
         committed = int(last_t["grow_steps"]) - int(last_t["grow_tiny_tx"])
@@ -495,6 +518,7 @@ def run_ours(args):
         config = {"workload": f"{args.workload}: {Wl['what']}; {n_tile} points" + (f" over {world} x-slabs" if world > 1 else ""),
                   "points": n_tile, "params": Wl["params"], "l2": "inputs larger than L2 (cloud + neighbour rows >> 126 MB)",
                   "grow_engine": "sweeper + speculative growers (grow_mode 0)", "planes": int(npl_box[0]),
+                  "labels_checksum": labels_checksum,
                   "raster": [int(W), int(H)], "generate_s": round(t_gen, 1)}
         if world > 1:
             config["tile"] = {**{k: info[k] for k in ("halo", "n_halo", "slab_points", "raster_columns")},

@@ -72,6 +72,7 @@ enum {
   SC_SWEEP_ON = 41,   // the sweeper of this round is running (background slice: the growers of the other SMs work while it does)
   SC_BG_STEPS = 42,   // Broad steps made by background slices
   SC_LIVE_F = 43,     // the sweeper's frontier, published once per batch (the prefetch block walks ahead of it)
+  SC_END_NOSLOT = 53, SC_END_RUNNING = 54, SC_END_UNVERIFIED = 55,  // why sweeps ended: the grower at the frontier has no slot / is still growing / finished beside the sweeper
   SC_N_SER = 22,      // serial stretches of the sweeper
   SC_N_GROW = 23,     // growers the sweeper decided
   SC_HEAD_ITERS = 21, // warp iterations of the head slot (two-node engine: <= steps)
@@ -1303,6 +1304,9 @@ __global__ void __launch_bounds__(SWEEP_T) spec_sweep_kernel(SpecArgs S)
         // round, then re-run)
         sh.last_open = i;
         if (slot < 0 || S.slots[slot].status != ST_RUNNING) S.sc[SC_STUCK] = 1;
+        if (slot < 0) S.sc[SC_END_NOSLOT] += 1;
+        else if (S.slots[slot].status == ST_RUNNING) S.sc[SC_END_RUNNING] += 1;
+        else if (S.slots[slot].status == ST_FINISHED && S.slots[slot].verified == 0 && !((volatile uint8_t*)A.doom)[i]) S.sc[SC_END_UNVERIFIED] += 1;
         if (g_ready && g_bad) {
           A.doom[i] = 1;
           atomicAdd(&S.sc[SC_ATFAIL], 1ull);
@@ -1728,6 +1732,9 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
       fprintf(stderr, "[bseg] head skip batches %llu: cycles/batch enumerate %llu, evaluate %llu; pairs/batch %.1f; regular steps %llu, "
               "batch time %.1f ms of head %.1f ms\n", sd[0], sd[1] / sd[0], sd[2] / sd[0], (double)sd[4] / (double)sd[0], sd[3],
               (double)(sd[1] + sd[2]) / 1.965e6, ctl[8 + SC_HEAD_NS] / 1e6);
+    fprintf(stderr, "[bseg] sweeps ended at a grower without a slot %llu, still growing %llu, finished beside the sweeper (unverified) %llu, void or failed %lld\n",
+            ctl[8 + SC_END_NOSLOT], ctl[8 + SC_END_RUNNING], ctl[8 + SC_END_UNVERIFIED],
+            (long long)rounds - (long long)(ctl[8 + SC_END_NOSLOT] + ctl[8 + SC_END_RUNNING] + ctl[8 + SC_END_UNVERIFIED]));
     fprintf(stderr, "[bseg] rounds %lld: release %.1f ms, scout+assign %.1f ms, slices %.1f ms, sweep+apply %.1f ms; background slices %s, %llu steps\n",
             (long long)rounds, pt[0], pt[1], pt[2], pt[3], bg_on ? "on" : "off", ctl[8 + SC_BG_STEPS]);
   }
