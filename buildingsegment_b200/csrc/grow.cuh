@@ -35,7 +35,7 @@ struct GrowArgs {
   const uint8_t* rowdup;  // [n] 1 = the neighbour row names some point twice (dedupe needed, rare)
   uint32_t* atby;    // [n] lowest in-flight transaction that assumed the point taken (early notification)
 };
-enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32, GF_NOPAIR = 64, GF_NOSKIP = 128, GF_SKIP_EAGER = 256, GF_EXACT_MODEL = 512, GF_TIMING = 1024, GF_NEVER = 1 << 30 /* never set */ };
+enum { GF_ROW_L1 = 1, GF_ROW_L2 = 2, GF_EARLY_POP = 4, GF_STATE_NC = 8, GF_ROWDUP = 16, GF_FASTDIV = 32, GF_NOPAIR = 64, GF_NOSKIP = 128, GF_SKIP_EAGER = 256, GF_EXACT_MODEL = 512, GF_TIMING = 1024, GF_BG = 2048 /* background slice: see tx_run_pair */, GF_NEVER = 1 << 30 /* never set */ };
 
 // ---- "assumed taken" list of a speculative transaction --------------------------------------------------
 // A point that is free in the committed state and passes the geometric tests, but is reserved by a LOWER
@@ -424,6 +424,13 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
     bool ok = id >= 0 && stt == -1 && (MODE != MODE_SPEC || (rs != me && !mine)) &&
               geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
     if (has_dup) ok = dedupe(ok, id);
+    if (MODE == MODE_SPEC && (A.flags & GF_BG)) {  // background slice: nothing is taken from anybody (see tx_run_pair)
+      const bool contested = ok && rs != RES_FREE && !(rs >= fr && rs < me);
+      if (__any_sync(FULL_MASK, contested)) {
+        --steps;
+        break;
+      }
+    }
     if (leave_growers && t.depth0) {
       if (__popc(__ballot_sync(FULL_MASK, ok)) == K - 1) {
         out = TX_IS_GROWER;
@@ -852,6 +859,7 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
   const bool fastdiv = (A.flags & GF_FASTDIV) != 0, row_l1 = (A.flags & GF_ROW_L1) != 0;
   const bool skip = ss != nullptr && (A.flags & GF_NOSKIP) == 0;
   const bool approx = (A.flags & GF_EXACT_MODEL) == 0;
+  const bool bg = (A.flags & GF_BG) != 0;
   bool halt = false;
   long long klast = dbg ? clock64() : 0;
   const int half = lane >> 4, sl = lane & 15;
@@ -903,6 +911,19 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
                                           : ((1ull << 40) | (unsigned long long)lane);
       const uint32_t same = __match_any_sync(FULL_MASK, key);
       want = want && ((same & lanemask_lt()) == 0);
+    }
+    if (bg) {
+      // Beside the sweeper nothing may be TAKEN from anybody: a slot that is finished and verified is decided by flags, not
+      // by a second look at its reservations, and a plane the sweep has accepted is recognised by the reservations it
+      // still holds.  A wanted point whose reservation is neither free nor a lower in-flight transaction's (it would be
+      // stolen from a higher one, or a stale one replaced) ends this slot's background slice BEFORE the call is made;
+      // the call is made in the next ordinary slice.  What remains is the race with a slot that reserves the same free
+      // point at the same moment -- a running slot, which the sweeper cannot decide in this sweep.
+      const bool contested = want && rs != RES_FREE && !(rs >= fr && rs < me);
+      if (__any_sync(FULL_MASK, contested)) {
+        --iters;
+        break;
+      }
     }
     // ---- node A ----
     bool ok = false, relied = false, fired = false;

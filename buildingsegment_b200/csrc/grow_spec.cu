@@ -497,9 +497,13 @@ __global__ void spec_pop_free_kernel(SpecArgs S)
 // bg = 1: the BACKGROUND slice.  The sweeper is one block on one SM; while it walks the seeds the slots keep growing on
 // the other SMs.  Nothing the sweeper decides depends on a slot that is still running (it stops at the first grower
 // that is not finished AND verified), a running slot reads the committed state (which only gets more taken: reading an
-// old value is reading earlier) and reserves with atomics, and whatever the sweeper marks under a running slot's
-// reservation is found by spec_apply_marks_kernel after both have ended (the holder is doomed) and again by the
-// full-list verification of the slot.  The slice ends when the sweeper sets SC_STOP; a slot that does not see the
+// old value is reading earlier) and reserves FREE points with atomics, and whatever the sweeper marks under a running
+// slot's reservation is found by spec_apply_marks_kernel after both have ended (the holder is doomed) and again by the
+// full-list verification of the slot.  What a running slot must NOT do beside the sweeper is take a reservation away
+// from its holder: the sweeper decides a finished slot by its flags (read at the front of the batch), and recognises
+// the points of a plane it has accepted in this sweep by the reservations the plane still holds -- a slot the
+// sweeper has just voided can run on for a few steps, and a reservation it stole in that time would make a taken point
+// look free.  With GF_BG a call that would have to steal ends the slot's slice instead (grow.cuh, tx_run_pair).  The slice ends when the sweeper sets SC_STOP; a slot that does not see the
 // sweeper running within a few microseconds (it could not be placed, or has already ended) does nothing.
 __global__ void __launch_bounds__(GW * 32) spec_grow_kernel(SpecArgs S, unsigned long long budget, int bg)
 {
@@ -1617,7 +1621,9 @@ int stage_grow_speculative(bseg_ctx* c, const bseg_params* p, GrowArgs& A)
         KLAUNCH_CHECK(c);
         cudaEventRecord(c->grow_join[2], c->grow_pf);
       }
-      spec_grow_kernel<<<sb, GW * 32, 0, c->grow_lo>>>(S, bg_budget, 1);
+      SpecArgs Sbg = S;
+      Sbg.A.flags |= GF_BG;
+      spec_grow_kernel<<<sb, GW * 32, 0, c->grow_lo>>>(Sbg, bg_budget, 1);
       KLAUNCH_CHECK(c);
       cudaEventRecord(c->grow_join[0], c->grow_hi);
       cudaEventRecord(c->grow_join[1], c->grow_lo);
