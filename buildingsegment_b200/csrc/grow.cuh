@@ -425,7 +425,7 @@ __device__ TxOutcome tx_run(const GrowArgs& A, Store& st, TxState& t, int64_t se
               geo_test(t.m, p, n0, n1, n2, A.th_thick, A.th_dot);
     if (has_dup) ok = dedupe(ok, id);
     if (MODE == MODE_SPEC && (A.flags & GF_BG)) {  // background slice: nothing is taken from anybody (see tx_run_pair)
-      const bool contested = ok && rs != RES_FREE && !(rs >= fr && rs < me);
+      const bool contested = ok && rs != RES_FREE && rs > me;
       if (__any_sync(FULL_MASK, contested)) {
         --steps;
         break;
@@ -915,11 +915,12 @@ __device__ TxOutcome tx_run_pair(const GrowArgs& A, Store& st, TxState& t, int64
     if (bg) {
       // Beside the sweeper nothing may be TAKEN from anybody: a slot that is finished and verified is decided by flags, not
       // by a second look at its reservations, and a plane the sweep has accepted is recognised by the reservations it
-      // still holds.  A wanted point whose reservation is neither free nor a lower in-flight transaction's (it would be
-      // stolen from a higher one, or a stale one replaced) ends this slot's background slice BEFORE the call is made;
-      // the call is made in the next ordinary slice.  What remains is the race with a slot that reserves the same free
-      // point at the same moment -- a running slot, which the sweeper cannot decide in this sweep.
-      const bool contested = want && rs != RES_FREE && !(rs >= fr && rs < me);
+      // still holds.  A wanted point that a HIGHER in-flight transaction holds (it would be stolen) ends this slot's
+      // background slice BEFORE the call is made; the call is made in the next ordinary slice.  A stale reservation
+      // (below the frontier of the sweep's start: a transaction decided in an earlier sweep, never one this sweep can
+      // accept) is replaced as usual.  What remains is the race with a slot that reserves the same free point at the same
+      // moment -- a running slot, which the sweeper cannot decide in this sweep.
+      const bool contested = want && rs != RES_FREE && rs > me;
       if (__any_sync(FULL_MASK, contested)) {
         --iters;
         break;
