@@ -122,6 +122,27 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------
 # workloads
+def labels_checksum_parts(labels, offset):
+    """(sum of labels, sum of labels x weight(global index)) mod 2^64 of a contiguous chunk of the tile that starts at
+    global index `offset`, as two int64 (two's complement of the uint64 sums): chunks add up -- rank by rank through an
+    int64 all_reduce -- to the checksum of the undivided tile, whatever the split."""
+    s1 = np.uint64(0)
+    s2 = np.uint64(0)
+    n = len(labels)
+    with np.errstate(over="ignore"):
+        for a in range(0, n, 1 << 24):
+            lab = labels[a: a + (1 << 24)].astype(np.uint64)
+            w = np.arange(offset + a + 1, offset + a + 1 + len(lab), dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+            s1 = s1 + lab.sum(dtype=np.uint64)
+            s2 = s2 + (lab * w).sum(dtype=np.uint64)
+
+    def signed(v):
+        v = int(v)
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    return signed(s1), signed(s2)
+
+
 def make_chunk(name, n, rank=0, world=1, workers=1):
     """Rank `rank`'s contiguous chunk of workload `name` at `n` points (int32, unshifted); world == 1: the whole
     cloud.  Call before CUDA is initialised in this process (the block generators fork workers)."""
@@ -446,17 +467,8 @@ def run_ours(args):
         counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev))
         off = int(sum(int(c.item()) for c in counts[:rank]))
-    s1 = np.uint64(0)
-    s2 = np.uint64(0)
-    lab_all = h_label.numpy()
-    with np.errstate(over="ignore"):
-        for a in range(0, n, 1 << 24):
-            lab = lab_all[a: a + (1 << 24)].astype(np.uint64)
-            w = (np.arange(off + a + 1, off + a + 1 + len(lab), dtype=np.uint64)) * np.uint64(0x9E3779B97F4A7C15)
-            s1 = s1 + lab.sum(dtype=np.uint64)
-            s2 = s2 + (lab * w).sum(dtype=np.uint64)
-    chk = torch.tensor([int(s1) - (1 << 64) if int(s1) >= (1 << 63) else int(s1),
-                        int(s2) - (1 << 64) if int(s2) >= (1 << 63) else int(s2)], dtype=torch.int64, device=dev)
+    s1, s2 = labels_checksum_parts(h_label.numpy(), off)
+    chk = torch.tensor([s1, s2], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(chk)
     labels_checksum = [int(chk[0].item()) & ((1 << 64) - 1), "%016x" % (int(chk[1].item()) & ((1 << 64) - 1))]

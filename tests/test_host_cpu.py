@@ -149,3 +149,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config"):
         assert k in line
+
+
+def test_bench_labels_checksum_is_split_invariant():
+    """bench.py's labels checksum: the parts of contiguous chunks add up (as the int64 all_reduce at N > 1 adds them,
+    wrapping mod 2^64) to the checksum of the undivided tile."""
+    import importlib.util
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(7)
+    lab = rng.integers(0, 1 << 30, size=3_000_001).astype(np.int32)  # large labels: the weighted sum wraps many times
+    whole = torch.tensor(bench.labels_checksum_parts(lab, 0), dtype=torch.int64)
+    for cuts in ([0, 1_234_567, len(lab)], [0, 1, 2_000_000, 2_000_001, len(lab)]):
+        acc = torch.zeros(2, dtype=torch.int64)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            acc += torch.tensor(bench.labels_checksum_parts(lab[a:b], a), dtype=torch.int64)  # int64 add wraps like the all_reduce
+        assert torch.equal(acc, whole)
+    moved = lab.copy()
+    moved[[5, 6]] = moved[[6, 5]]
+    if moved[5] != moved[6]:
+        assert bench.labels_checksum_parts(moved, 0)[1] != bench.labels_checksum_parts(lab, 0)[1]  # position matters
