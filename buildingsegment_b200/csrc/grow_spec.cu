@@ -29,8 +29,12 @@
 //       stops, the seed gets a slot as the lowest candidate (one slot is kept for it) and -- with nothing
 //       lower in flight -- runs clean: progress is guaranteed.
 // Round = release doomed slots -> scout (lowest candidates of the window take the free slots) -> one slice
-// of Broad steps for every running slot (ends when the head slot finishes) -> sweep.  Plane ids are ordinal
-// in seed order and are assigned after the fact (grow.cu finalize).
+// of Broad steps for every running slot (ends when the head slot finishes) -> verification of the finished
+// slots -> sweep, with a BACKGROUND slice of the growers and an L2 warmer beside it on the other SMs -> the
+// side effects of the sweep (marks, accepted planes) applied by the whole GPU.  Every kernel of a round reads
+// the frontier from the control block, so the host launches round r + 1 before it has seen round r's result
+// (stage_grow_speculative).  Plane ids are ordinal in seed order and are assigned after the fact (grow.cu
+// finalize).
 #include <cstdlib>
 
 #include "grow.cuh"
